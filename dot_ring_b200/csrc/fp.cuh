@@ -1,0 +1,367 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for BLS12-381 Fq (12 limbs) and Fr (8 limbs).
+//
+// Replaces the reference's 4x64-bit CIOS C code (dot_ring/curve/native_field/bls12_381_scalar.c:
+// 43-257, constants :7-27) and blst's Fq assembly.  On the device every operation is one inline PTX
+// block generated (and verified against big integers) by tools/gen_field_asm.py; on the host the
+// same functions fall back to portable uint64 arithmetic, which is what the CPU-side unit tests and
+// the few host-only paths (pairing, setup) use.
+//
+// Elements are little-endian limb vectors in Montgomery form (x * 2^(32 N) mod p), always fully
+// reduced (< p).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "gen/field_consts.h"
+#include "gen/field_asm.inc"
+
+#if defined(__CUDACC__)
+#define DR_HD __host__ __device__ __forceinline__
+#define DR_D __device__ __forceinline__
+#else
+#define DR_HD inline
+#define DR_D inline
+#endif
+
+namespace dr {
+
+struct FqTag {
+    static constexpr int N = DR_FQ_LIMBS;
+    static constexpr uint32_t M0 = DR_FQ_M0;
+    DR_HD static uint32_t mod(int i) {
+        constexpr uint32_t m[N] = DR_FQ_MOD;
+        return m[i];
+    }
+    DR_HD static uint32_t r1(int i) {
+        constexpr uint32_t m[N] = DR_FQ_R1;
+        return m[i];
+    }
+    DR_HD static uint32_t r2(int i) {
+        constexpr uint32_t m[N] = DR_FQ_R2;
+        return m[i];
+    }
+#if defined(__CUDA_ARCH__)
+    DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_mul_ptx(r, a, b); }
+    DR_D static void sqr(uint32_t* r, const uint32_t* a) { fq_sqr_ptx(r, a); }
+    DR_D static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_add_ptx(r, a, b); }
+    DR_D static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_sub_ptx(r, a, b); }
+#endif
+};
+
+struct FrTag {
+    static constexpr int N = DR_FR_LIMBS;
+    static constexpr uint32_t M0 = DR_FR_M0;
+    DR_HD static uint32_t mod(int i) {
+        constexpr uint32_t m[N] = DR_FR_MOD;
+        return m[i];
+    }
+    DR_HD static uint32_t r1(int i) {
+        constexpr uint32_t m[N] = DR_FR_R1;
+        return m[i];
+    }
+    DR_HD static uint32_t r2(int i) {
+        constexpr uint32_t m[N] = DR_FR_R2;
+        return m[i];
+    }
+#if defined(__CUDA_ARCH__)
+    DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_mul_ptx(r, a, b); }
+    DR_D static void sqr(uint32_t* r, const uint32_t* a) { fr_sqr_ptx(r, a); }
+    DR_D static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_add_ptx(r, a, b); }
+    DR_D static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_sub_ptx(r, a, b); }
+#endif
+};
+
+struct FnTag {  // Bandersnatch prime-subgroup order (VRF scalar arithmetic)
+    static constexpr int N = DR_FN_LIMBS;
+    static constexpr uint32_t M0 = DR_FN_M0;
+    DR_HD static uint32_t mod(int i) {
+        constexpr uint32_t m[N] = DR_FN_MOD;
+        return m[i];
+    }
+    DR_HD static uint32_t r1(int i) {
+        constexpr uint32_t m[N] = DR_FN_R1;
+        return m[i];
+    }
+    DR_HD static uint32_t r2(int i) {
+        constexpr uint32_t m[N] = DR_FN_R2;
+        return m[i];
+    }
+#if defined(__CUDA_ARCH__)
+    DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fn_mul_ptx(r, a, b); }
+    DR_D static void sqr(uint32_t* r, const uint32_t* a) { fn_sqr_ptx(r, a); }
+    DR_D static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fn_add_ptx(r, a, b); }
+    DR_D static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fn_sub_ptx(r, a, b); }
+#endif
+};
+
+template <class T>
+struct Fp {
+    static constexpr int N = T::N;
+    uint32_t v[N];
+
+    DR_HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    DR_HD static Fp one() {  // Montgomery form of 1
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = T::r1(i);
+        return r;
+    }
+    DR_HD static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = T::r2(i);
+        return r;
+    }
+    DR_HD static Fp modulus() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = T::mod(i);
+        return r;
+    }
+    DR_HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i];
+        return acc == 0;
+    }
+    DR_HD bool operator==(const Fp& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i] ^ o.v[i];
+        return acc == 0;
+    }
+    DR_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // ---- portable limb helpers (host path, also usable on device for debugging) ----
+    DR_HD static bool geq_mod(const uint32_t* a) {
+        for (int i = N - 1; i >= 0; i--) {
+            uint32_t m = T::mod(i);
+            if (a[i] != m) return a[i] > m;
+        }
+        return true;
+    }
+    DR_HD static void sub_mod_inplace(uint32_t* a) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t t = (uint64_t)a[i] - T::mod(i) - borrow;
+            a[i] = (uint32_t)t;
+            borrow = (t >> 32) & 1;
+        }
+    }
+    DR_HD static void mul_portable(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        uint32_t t[N + 2];
+        for (int i = 0; i < N + 2; i++) t[i] = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < N; j++) {
+                uint64_t x = (uint64_t)a[j] * b[i] + t[j] + c;
+                t[j] = (uint32_t)x;
+                c = x >> 32;
+            }
+            uint64_t x = (uint64_t)t[N] + c;
+            t[N] = (uint32_t)x;
+            t[N + 1] = (uint32_t)(x >> 32);
+            uint32_t m = t[0] * T::M0;
+            c = ((uint64_t)m * T::mod(0) + t[0]) >> 32;
+            for (int j = 1; j < N; j++) {
+                uint64_t y = (uint64_t)m * T::mod(j) + t[j] + c;
+                t[j - 1] = (uint32_t)y;
+                c = y >> 32;
+            }
+            x = (uint64_t)t[N] + c;
+            t[N - 1] = (uint32_t)x;
+            t[N] = t[N + 1] + (uint32_t)(x >> 32);
+        }
+        if (t[N] || geq_mod(t)) sub_mod_inplace(t);
+        for (int i = 0; i < N; i++) r[i] = t[i];
+    }
+    DR_HD static void add_portable(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        uint32_t t[N];
+        uint64_t c = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t x = (uint64_t)a[i] + b[i] + c;
+            t[i] = (uint32_t)x;
+            c = x >> 32;
+        }
+        if (c || geq_mod(t)) sub_mod_inplace(t);
+        for (int i = 0; i < N; i++) r[i] = t[i];
+    }
+    DR_HD static void sub_portable(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        uint32_t t[N];
+        uint64_t borrow = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t x = (uint64_t)a[i] - b[i] - borrow;
+            t[i] = (uint32_t)x;
+            borrow = (x >> 32) & 1;
+        }
+        if (borrow) {
+            uint64_t c = 0;
+            for (int i = 0; i < N; i++) {
+                uint64_t x = (uint64_t)t[i] + T::mod(i) + c;
+                t[i] = (uint32_t)x;
+                c = x >> 32;
+            }
+        }
+        for (int i = 0; i < N; i++) r[i] = t[i];
+    }
+
+    // ---- field operations ----
+    DR_HD friend Fp operator*(const Fp& a, const Fp& b) {
+        Fp r;
+#if defined(__CUDA_ARCH__) && !defined(DR_PORTABLE_FIELD)
+        T::mul(r.v, a.v, b.v);
+#else
+        mul_portable(r.v, a.v, b.v);
+#endif
+        return r;
+    }
+    DR_HD Fp sqr() const {
+        Fp r;
+#if defined(__CUDA_ARCH__) && !defined(DR_PORTABLE_FIELD)
+        T::sqr(r.v, v);
+#else
+        mul_portable(r.v, v, v);
+#endif
+        return r;
+    }
+    DR_HD friend Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+#if defined(__CUDA_ARCH__) && !defined(DR_PORTABLE_FIELD)
+        T::add(r.v, a.v, b.v);
+#else
+        add_portable(r.v, a.v, b.v);
+#endif
+        return r;
+    }
+    DR_HD friend Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+#if defined(__CUDA_ARCH__) && !defined(DR_PORTABLE_FIELD)
+        T::sub(r.v, a.v, b.v);
+#else
+        sub_portable(r.v, a.v, b.v);
+#endif
+        return r;
+    }
+    DR_HD Fp neg() const { return zero() - *this; }
+    DR_HD Fp dbl() const { return *this + *this; }
+    DR_HD Fp& operator*=(const Fp& o) { return *this = *this * o; }
+    DR_HD Fp& operator+=(const Fp& o) { return *this = *this + o; }
+    DR_HD Fp& operator-=(const Fp& o) { return *this = *this - o; }
+
+    // Montgomery <-> canonical
+    DR_HD Fp to_mont() const { return *this * r2(); }
+    DR_HD Fp from_mont() const {
+        Fp o = zero();
+        o.v[0] = 1;
+        return *this * o;
+    }
+    // canonical little-endian limbs must already be < p
+    DR_HD bool is_canonical_raw() const { return !geq_mod(v); }
+
+    // x^e for a little-endian limb exponent (variable time; exponents here are public)
+    DR_HD Fp pow(const uint32_t* e, int nlimbs) const {
+        Fp acc = one();
+        bool started = false;
+        for (int i = nlimbs - 1; i >= 0; i--) {
+            for (int b = 31; b >= 0; b--) {
+                if (started) acc = acc.sqr();
+                if ((e[i] >> b) & 1) {
+                    acc = started ? acc * *this : *this;
+                    started = true;
+                }
+            }
+        }
+        return acc;
+    }
+    // Fermat inverse x^(p-2); 0 -> 0
+    DR_HD Fp inv() const {
+        uint32_t e[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) e[i] = T::mod(i);
+        uint32_t borrow = 2;  // p - 2 with borrow propagation (Fr's low limb is 1)
+        for (int i = 0; i < N && borrow; i++) {
+            uint32_t old = e[i];
+            e[i] = old - borrow;
+            borrow = old < borrow ? 1 : 0;
+        }
+        return pow(e, N);
+    }
+    DR_HD static Fp from_u32(uint32_t x) {
+        Fp r = zero();
+        r.v[0] = x;
+        return r.to_mont();
+    }
+    // conditional select (branch-free): c ? a : b
+    DR_HD static Fp select(bool c, const Fp& a, const Fp& b) {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = c ? a.v[i] : b.v[i];
+        return r;
+    }
+};
+
+typedef Fp<FqTag> Fq;
+typedef Fp<FrTag> Fr;
+typedef Fp<FnTag> Fn;
+
+// Reduce an arbitrary little-endian byte string (len <= 64) into the field, Montgomery form:
+// Horner over 16-byte chunks so every partial operand stays canonical.
+template <class F>
+DR_HD F fp_from_le_bytes_mod(const uint8_t* in, int len) {
+    static_assert(F::N == 8, "8-limb fields only");
+    F two128 = F::zero();
+    two128.v[4] = 1;
+    two128 = two128.to_mont();
+    F acc = F::zero();
+    int nchunks = (len + 15) / 16;
+    for (int c = nchunks - 1; c >= 0; c--) {
+        F chunk = F::zero();
+        for (int b = 0; b < 16; b++) {
+            int idx = 16 * c + b;
+            if (idx < len) chunk.v[b >> 2] |= (uint32_t)in[idx] << (8 * (b & 3));
+        }
+        acc = acc * two128 + chunk.to_mont();
+    }
+    return acc;
+}
+
+// ---- byte codecs used at the C ABI ---------------------------------------------------------
+// Fr: 32-byte little-endian canonical.  Fq: 48-byte big-endian canonical (zcash).
+DR_HD void fr_from_le_bytes_raw(Fr& out, const uint8_t* in) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        out.v[i] = (uint32_t)in[4 * i] | ((uint32_t)in[4 * i + 1] << 8) | ((uint32_t)in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24);
+}
+DR_HD void fr_to_le_bytes_raw(uint8_t* out, const Fr& in) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)in.v[i];
+        out[4 * i + 1] = (uint8_t)(in.v[i] >> 8);
+        out[4 * i + 2] = (uint8_t)(in.v[i] >> 16);
+        out[4 * i + 3] = (uint8_t)(in.v[i] >> 24);
+    }
+}
+DR_HD void fq_from_be_bytes_raw(Fq& out, const uint8_t* in) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint8_t* p = in + 44 - 4 * i;
+        out.v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    }
+}
+DR_HD void fq_to_be_bytes_raw(uint8_t* out, const Fq& in) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint8_t* p = out + 44 - 4 * i;
+        p[0] = (uint8_t)(in.v[i] >> 24);
+        p[1] = (uint8_t)(in.v[i] >> 16);
+        p[2] = (uint8_t)(in.v[i] >> 8);
+        p[3] = (uint8_t)in.v[i];
+    }
+}
+
+}  // namespace dr

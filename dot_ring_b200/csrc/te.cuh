@@ -1,0 +1,305 @@
+// Bandersnatch (twisted Edwards, a = -5) over Fr: group law, codec, subgroup check, Elligator 2.
+//
+// Replaces, for batched use on the device:
+//   dot_ring/curve/native_field/bandersnatch_te.pyx:127-174  (extended add / double)
+//   dot_ring/curve/native_field/bandersnatch_te.pyx:421-477  (Tonelli-Shanks in Fr)
+//   dot_ring/curve/native_field/bandersnatch_te.pyx:480-816  (small simultaneous multiplications)
+//   dot_ring/curve/twisted_edwards/te_affine_point.py:69-316 (affine law, from_mont, x-recover)
+//   dot_ring/curve/twisted_edwards/te_curve.py:48-95         (Elligator 2 map)
+//   dot_ring/curve/point.py:150-214, dot_ring/vrf/codec.py:39-45, dot_ring/curve/curve.py:56-67
+// Points are unique group elements, so the multiplication schedule is ours (fixed 4-bit windows
+// with shared doublings) rather than the reference's GLV + 2-bit joint windows.
+#pragma once
+#include "fp.cuh"
+
+namespace dr {
+
+struct TEAffine {
+    Fr x, y;  // Montgomery
+    DR_HD static TEAffine identity() { return {Fr::zero(), Fr::one()}; }
+    DR_HD bool is_identity() const { return x.is_zero() && y == Fr::one(); }
+    DR_HD bool operator==(const TEAffine& o) const { return x == o.x && y == o.y; }
+};
+
+struct TEExt {
+    Fr X, Y, Z, T;
+    DR_HD static TEExt identity() { return {Fr::zero(), Fr::one(), Fr::one(), Fr::zero()}; }
+    DR_HD static TEExt from_affine(const TEAffine& a) { return {a.x, a.y, Fr::one(), a.x * a.y}; }
+    DR_HD bool is_identity() const { return X.is_zero() && Y == Z; }
+};
+
+DR_HD Fr te_d() {
+    constexpr uint32_t c[8] = DR_TE_D;
+    Fr r;
+    for (int i = 0; i < 8; i++) r.v[i] = c[i];
+    return r;
+}
+DR_HD Fr fr_mul5(const Fr& a) {
+    Fr a2 = a.dbl();
+    return a2.dbl() + a;
+}
+
+// add-2008-hwcd with a = -5:  H = B - a*A = B + 5A
+DR_HD TEExt te_add(const TEExt& p, const TEExt& q) {
+    Fr A = p.X * q.X;
+    Fr B = p.Y * q.Y;
+    Fr C = p.T * te_d() * q.T;
+    Fr D = p.Z * q.Z;
+    Fr E = (p.X + p.Y) * (q.X + q.Y) - A - B;
+    Fr F = D - C;
+    Fr G = D + C;
+    Fr H = B + fr_mul5(A);
+    return {E * F, G * H, F * G, E * H};
+}
+
+// mixed: q affine with precomputed td = d * x * y
+struct TEPre {
+    Fr x, y, td;
+    DR_HD static TEPre from_affine(const TEAffine& a) { return {a.x, a.y, a.x * a.y * te_d()}; }
+};
+DR_HD TEExt te_madd(const TEExt& p, const TEPre& q) {
+    Fr A = p.X * q.x;
+    Fr B = p.Y * q.y;
+    Fr C = p.T * q.td;
+    Fr E = (p.X + p.Y) * (q.x + q.y) - A - B;
+    Fr F = p.Z - C;
+    Fr G = p.Z + C;
+    Fr H = B + fr_mul5(A);
+    return {E * F, G * H, F * G, E * H};
+}
+
+// dbl-2008-hwcd: D = a*A = -5A
+DR_HD TEExt te_dbl(const TEExt& p) {
+    Fr A = p.X.sqr();
+    Fr B = p.Y.sqr();
+    Fr C = p.Z.sqr().dbl();
+    Fr D = fr_mul5(A).neg();
+    Fr E = (p.X + p.Y).sqr() - A - B;
+    Fr G = D + B;
+    Fr F = G - C;
+    Fr H = D - B;
+    return {E * F, G * H, F * G, E * H};
+}
+
+DR_HD TEExt te_neg(const TEExt& p) { return {p.X.neg(), p.Y, p.Z, p.T.neg()}; }
+DR_HD TEAffine te_neg(const TEAffine& p) { return {p.x.neg(), p.y}; }
+
+DR_HD TEAffine te_to_affine(const TEExt& p) {
+    Fr zi = p.Z.inv();
+    return {p.X * zi, p.Y * zi};
+}
+
+DR_HD bool te_ext_eq_affine(const TEExt& p, const TEAffine& a) { return p.X == a.x * p.Z && p.Y == a.y * p.Z; }
+
+DR_HD bool te_on_curve(const TEAffine& a) {
+    Fr x2 = a.x.sqr(), y2 = a.y.sqr();
+    return y2 - fr_mul5(x2) == Fr::one() + te_d() * x2 * y2;
+}
+
+// k * P for a raw little-endian scalar of `nlimbs` limbs (no reduction), fixed 4-bit windows.
+DR_HD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
+    TEExt tab[16];
+    tab[0] = TEExt::identity();
+    tab[1] = TEExt::from_affine(p);
+    for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? te_add(tab[i - 1], tab[1]) : te_dbl(tab[i >> 1]);
+    TEExt acc = TEExt::identity();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+        for (int s = 28; s >= 0; s -= 4) {
+            if (started) {
+                acc = te_dbl(te_dbl(te_dbl(te_dbl(acc))));
+            }
+            uint32_t d = (k[i] >> s) & 15;
+            if (d) {
+                acc = started ? te_add(acc, tab[d]) : tab[d];
+                started = true;
+            }
+        }
+    }
+    return acc;
+}
+
+// sum_i k_i * P_i with shared doublings (Straus), n <= 3, raw 8-limb scalars (< subgroup order).
+DR_HD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int n) {
+    TEExt tab[3][16];
+    for (int j = 0; j < n; j++) {
+        tab[j][0] = TEExt::identity();
+        tab[j][1] = TEExt::from_affine(pts[j]);
+        for (int i = 2; i < 16; i++) tab[j][i] = (i & 1) ? te_add(tab[j][i - 1], tab[j][1]) : te_dbl(tab[j][i >> 1]);
+    }
+    TEExt acc = TEExt::identity();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        for (int s = 28; s >= 0; s -= 4) {
+            if (started) acc = te_dbl(te_dbl(te_dbl(te_dbl(acc))));
+            for (int j = 0; j < n; j++) {
+                uint32_t d = (ks[j][i] >> s) & 15;
+                if (d) {
+                    acc = started ? te_add(acc, tab[j][d]) : tab[j][d];
+                    started = true;
+                }
+            }
+        }
+    }
+    return acc;
+}
+
+DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
+    constexpr uint32_t n[8] = DR_FN_RAW;
+    uint32_t k[8];
+    for (int i = 0; i < 8; i++) k[i] = n[i];
+    return te_mul_raw(p, k, 8).is_identity();
+}
+
+// ---- square roots in Fr (2-adicity 32) ---------------------------------------------------------
+// Returns false when `a` is a non-residue.  Which of the two roots comes back is unspecified; every
+// caller normalises the sign (x-recover orders the candidates, Elligator fixes the parity).
+DR_HD bool fr_sqrt(Fr& out, const Fr& a) {
+    if (a.is_zero()) {
+        out = a;
+        return true;
+    }
+    constexpr uint32_t e_c[8] = DR_FR_TS_QM1_HALF;
+    constexpr uint32_t c_c[8] = DR_FR_TS_C;
+    uint32_t e[8];
+    Fr c;
+    for (int i = 0; i < 8; i++) {
+        e[i] = e_c[i];
+        c.v[i] = c_c[i];
+    }
+    Fr w = a.pow(e, 8);  // a^((q-1)/2)
+    Fr x = a * w;        // a^((q+1)/2)
+    Fr t = x * w;        // a^q
+    int m = 32;
+    Fr one = Fr::one();
+    while (t != one) {
+        int i = 0;
+        Fr t2 = t;
+        while (t2 != one) {
+            t2 = t2.sqr();
+            i++;
+            if (i == m) return false;  // order of t does not divide 2^(m-1): non-residue
+        }
+        Fr b = c;
+        for (int j = 0; j < m - i - 1; j++) b = b.sqr();
+        x = x * b;
+        c = b.sqr();
+        t = t * c;
+        m = i;
+    }
+    out = x;
+    return true;
+}
+
+DR_HD bool fr_is_square(const Fr& a) {
+    if (a.is_zero()) return true;
+    constexpr uint32_t e_c[8] = DR_FR_PM1_HALF;
+    uint32_t e[8];
+    for (int i = 0; i < 8; i++) e[i] = e_c[i];
+    return a.pow(e, 8) == Fr::one();
+}
+
+// canonical-integer comparison helpers on raw (non-Montgomery) limbs
+DR_HD bool raw_gt(const Fr& a, const Fr& b) {
+    for (int i = 7; i >= 0; i--)
+        if (a.v[i] != b.v[i]) return a.v[i] > b.v[i];
+    return false;
+}
+
+// ---- 32-byte point codec (point.py:150-214) ----------------------------------------------------
+DR_HD void te_encode(uint8_t* out32, const TEAffine& p) {
+    Fr xr = p.x.from_mont();
+    Fr nxr = p.x.neg().from_mont();
+    fr_to_le_bytes_raw(out32, p.y.from_mont());
+    if (raw_gt(xr, nxr)) out32[31] |= 0x80;
+}
+
+// Decode without the subgroup check.  false <=> ValueError("Invalid point encoding").
+DR_HD bool te_decode(TEAffine& out, const uint8_t* in32) {
+    uint8_t buf[32];
+    for (int i = 0; i < 32; i++) buf[i] = in32[i];
+    bool sign = (buf[31] >> 7) != 0;
+    buf[31] &= 0x7F;
+    Fr yr;
+    fr_from_le_bytes_raw(yr, buf);
+    if (!yr.is_canonical_raw()) return false;
+    Fr y = yr.to_mont();
+    Fr y2 = y.sqr();
+    Fr lhs = Fr::one() - y2;                   // 1 - y^2
+    Fr rhs = fr_mul5(Fr::one()).neg() - te_d() * y2;  // a - d y^2
+    if (rhs.is_zero()) return false;
+    Fr x;
+    if (!fr_sqrt(x, lhs * rhs.inv())) return false;
+    Fr nx = x.neg();
+    bool x_is_larger = raw_gt(x.from_mont(), nx.from_mont());
+    // candidates ordered (smaller, larger); sign bit selects the larger one
+    if (x_is_larger != sign) x = nx;
+    out = {x, y};
+    return true;
+}
+
+// vrf/codec.py:39-45 `dec_point`: decode + nonidentity prime-subgroup check.
+DR_HD bool te_decode_checked(TEAffine& out, const uint8_t* in32) {
+    if (!te_decode(out, in32)) return false;
+    if (out.is_identity()) return false;
+    return te_in_prime_subgroup(out);
+}
+
+// ---- Elligator 2 (te_curve.py:48-95, te_affine_point.py:262-290) --------------------------------
+DR_HD Fr fr_const(const uint32_t (&c)[8]) {
+    Fr r;
+    for (int i = 0; i < 8; i++) r.v[i] = c[i];
+    return r;
+}
+
+// u (Montgomery) -> twisted Edwards affine point
+DR_HD TEAffine te_map_to_curve_ell2(const Fr& u) {
+    constexpr uint32_t aob_c[8] = DR_ELL2_A_OVER_B;
+    constexpr uint32_t ib2_c[8] = DR_ELL2_INV_B2;
+    constexpr uint32_t b_c[8] = DR_ELL2_B;
+    Fr a_over_b = fr_const(aob_c), inv_b2 = fr_const(ib2_c), mb = fr_const(b_c);
+    Fr one = Fr::one();
+    Fr tv1 = fr_mul5(u.sqr());  // Z = 5
+    if (tv1 == one.neg()) tv1 = Fr::zero();
+    Fr x1 = a_over_b.neg() * (tv1 + one).inv();
+    Fr gx1 = ((x1 + a_over_b) * x1 + inv_b2) * x1;
+    Fr x2 = x1.neg() - a_over_b;
+    Fr gx2 = tv1 * gx1;
+    Fr y;
+    bool e2 = fr_sqrt(y, gx1);
+    Fr x = x1;
+    if (!e2) {
+        x = x2;
+        fr_sqrt(y, gx2);  // exactly one of gx1, gx2 is a square
+    }
+    bool e3 = (y.from_mont().v[0] & 1) != 0;
+    if (e2 != e3) y = y.neg();
+    Fr s = x * mb, t = y * mb;
+    // Montgomery (s, t) -> Edwards (v, w)
+    Fr tv1b = s + one;
+    Fr tv2 = tv1b * t;
+    bool degenerate = tv2.is_zero();
+    Fr tv2i = tv2.inv();  // 0 -> 0
+    Fr v = tv2i * tv1b * s;
+    Fr w = tv2i * t * (s - one);
+    if (degenerate) w = one;
+    return {v, w};
+}
+
+// hash_to_field output bytes (48-byte big-endian each) are reduced mod p on the host or device side:
+DR_HD Fr fr_from_be48_mod(const uint8_t* in48) {
+    uint8_t le[48];
+    for (int i = 0; i < 48; i++) le[i] = in48[47 - i];
+    return fp_from_le_bytes_mod<Fr>(le, 48);
+}
+
+// Elligator2 random-oracle encode: (u0, u1) -> 4 * (map(u0) + map(u1))   (te_affine_point.py:213-222)
+DR_HD TEAffine te_encode_to_curve_from_u(const Fr& u0, const Fr& u1) {
+    TEAffine q0 = te_map_to_curve_ell2(u0);
+    TEAffine q1 = te_map_to_curve_ell2(u1);
+    TEExt s = te_add(TEExt::from_affine(q0), TEExt::from_affine(q1));
+    s = te_dbl(te_dbl(s));
+    return te_to_affine(s);
+}
+
+}  // namespace dr

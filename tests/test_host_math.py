@@ -1,0 +1,169 @@
+"""CPU checks of the product's __host__ __device__ math headers (host-compiled into a test-only
+library) against the oracle: Fq / Fr / Fn arithmetic, G1 group law + zcash codecs, Bandersnatch
+decode / scalar-mul / Elligator2, SHA-512 and SHAKE128.  Mirrors the reference's
+tests/test_curve_ops/test_native_field.py (random add/sub/mul vs Python ints)."""
+
+import ctypes
+import hashlib
+import random
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from oracle import bandersnatch as bs
+from oracle import bls12_381 as bls
+from tests.helpers import load
+
+HERE = Path(__file__).resolve().parent / "host"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = HERE / "libdr_hosttest.so"
+    src = HERE / "hosttest.cpp"
+    hdrs = list((HERE.parents[1] / "dot_ring_b200" / "csrc").glob("*.cuh")) + list((HERE.parents[1] / "dot_ring_b200" / "csrc" / "gen").glob("*"))
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src, *hdrs]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)])
+    return ctypes.CDLL(str(so))
+
+
+def _buf(n):
+    return ctypes.create_string_buffer(n)
+
+
+def test_fq_ops(lib):
+    rng = random.Random(1)
+    P = bls.P
+    vals = [0, 1, 2, P - 1, P - 2, (1 << 380), P >> 1] + [rng.randrange(P) for _ in range(100)]
+    for _ in range(200):
+        a, b = rng.choice(vals), rng.choice(vals)
+        for op, want in ((0, a * b % P), (1, (a + b) % P), (2, (a - b) % P), (5, a * a % P)):
+            out = _buf(48)
+            lib.ht_fq_op(op, a.to_bytes(48, "big"), b.to_bytes(48, "big"), out)
+            assert int.from_bytes(out.raw, "big") == want, (op, a, b)
+    for a in vals[:20]:
+        out = _buf(48)
+        lib.ht_fq_op(3, a.to_bytes(48, "big"), bytes(48), out)
+        assert int.from_bytes(out.raw, "big") == (pow(a, -1, P) if a else 0)
+        sq = a * a % P
+        ok = lib.ht_fq_op(4, sq.to_bytes(48, "big"), bytes(48), out)
+        assert ok and int.from_bytes(out.raw, "big") in (a % P, (-a) % P)
+    assert not lib.ht_fq_op(4, (2).to_bytes(48, "big"), bytes(48), _buf(48)) or pow(2, (P - 1) // 2, P) == 1
+
+
+def test_fr_ops(lib):
+    rng = random.Random(2)
+    P = bs.P
+    vals = [0, 1, 2, P - 1, P - 2, 5, P >> 1] + [rng.randrange(P) for _ in range(100)]
+    for _ in range(200):
+        a, b = rng.choice(vals), rng.choice(vals)
+        for op, want in ((0, a * b % P), (1, (a + b) % P), (2, (a - b) % P), (5, a * a % P)):
+            out = _buf(32)
+            lib.ht_fr_op(op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), out)
+            assert int.from_bytes(out.raw, "little") == want, (op, a, b)
+    for a in vals[:40]:
+        out = _buf(32)
+        lib.ht_fr_op(3, a.to_bytes(32, "little"), bytes(32), out)
+        assert int.from_bytes(out.raw, "little") == (pow(a, -1, P) if a else 0)
+        is_sq = lib.ht_fr_op(6, a.to_bytes(32, "little"), bytes(32), out)
+        assert bool(is_sq) == bs.fr_is_square(a)
+        ok = lib.ht_fr_op(4, a.to_bytes(32, "little"), bytes(32), out)
+        assert bool(ok) == bs.fr_is_square(a)
+        if ok:
+            assert pow(int.from_bytes(out.raw, "little"), 2, P) == a
+
+
+def test_fn_reduction_and_muladd(lib):
+    rng = random.Random(3)
+    for n in (16, 32, 48, 64):
+        for _ in range(20):
+            data = bytes(rng.randrange(256) for _ in range(n))
+            out = _buf(32)
+            lib.ht_fn_from_bytes_mod(data, n, out)
+            assert int.from_bytes(out.raw, "little") == int.from_bytes(data, "little") % bs.N
+    out = _buf(32)
+    lib.ht_fn_from_bytes_mod(b"\xff" * 64, 64, out)
+    assert int.from_bytes(out.raw, "little") == (2**512 - 1) % bs.N
+    for _ in range(20):
+        k, c, x = (rng.randrange(bs.N) for _ in range(3))
+        lib.ht_fn_muladd(k.to_bytes(32, "little"), c.to_bytes(32, "little"), x.to_bytes(32, "little"), out)
+        assert int.from_bytes(out.raw, "little") == (k + c * x) % bs.N
+
+
+def test_g1_group_law_and_codecs(lib):
+    rng = random.Random(4)
+    g = (bls.G1_GEN[0], bls.G1_GEN[1], 1)
+    pts = [bls.g1_mul(g, rng.randrange(bls.R)) for _ in range(6)]
+    for p in pts:
+        ser, comp = bls.g1_serialize(p), bls.g1_compress(p)
+        out96, out48 = _buf(96), _buf(48)
+        assert lib.ht_g1_decode(comp, 48, out96) and out96.raw == ser
+        assert lib.ht_g1_decode(ser, 96, out96) and out96.raw == ser
+        lib.ht_g1_compress(ser, out48)
+        assert out48.raw == comp
+        k = rng.randrange(bls.R)
+        want = bls.g1_serialize(bls.g1_mul(p, k))
+        lib.ht_g1_mul(ser, k.to_bytes(32, "little"), out96)
+        assert out96.raw == want
+        lib.ht_g1_mul_mixed(ser, k.to_bytes(32, "little"), out96)
+        assert out96.raw == want
+    a, b = pts[0], pts[1]
+    inf = bls.g1_serialize(None)
+    for x, y in ((a, b), (a, a), (a, bls.g1_neg(a)), (a, None), (None, a), (None, None)):
+        for mode in (0, 1):
+            out96 = _buf(96)
+            lib.ht_g1_add(bls.g1_serialize(x), bls.g1_serialize(y), mode, out96)
+            assert out96.raw == bls.g1_serialize(bls.g1_add(x, y)), (mode,)
+    assert bls.g1_serialize(None) == inf
+    # malformed encodings are rejected (blst raises -> ValueError in the reference)
+    assert not lib.ht_g1_decode(b"\xff" * 48, 48, _buf(96))
+    assert not lib.ht_g1_decode(bytes(48), 48, _buf(96))
+    bad = bytearray(bls.g1_serialize(a))
+    bad[95] ^= 1
+    assert not lib.ht_g1_decode(bytes(bad), 96, _buf(96))
+    out96 = _buf(96)
+    assert lib.ht_g1_decode(bytes([0xC0]) + bytes(47), 48, out96) and out96.raw == inf
+
+
+def test_bandersnatch_against_reference_goldens(lib):
+    g = load("bandersnatch_reference.json")
+    for e in g["dec_point"]:
+        xy = _buf(64)
+        ok = lib.ht_te_decode(bytes.fromhex(e["raw"]), 1, xy)
+        assert bool(ok) == e["ok"]
+        if ok:
+            assert int.from_bytes(xy.raw[:32], "little") == int(e["x"], 16)
+            assert int.from_bytes(xy.raw[32:], "little") == int(e["y"], 16)
+    for e in g["scalar_mul"]:
+        out = _buf(32)
+        lib.ht_te_mul(bytes.fromhex(e["base"]), int(e["k"], 16).to_bytes(32, "little"), out)
+        assert out.raw.hex() == e["out"]
+    for e in g["encode_to_curve"]:
+        u = bs.expand_message_xmd_sha512(bytes.fromhex(e["alpha"]), bs.SHA512.dst, 96)
+        out = _buf(32)
+        lib.ht_te_ell2(u[:48], u[48:], out)
+        assert out.raw.hex() == e["point"]
+    rng = random.Random(5)
+    pts = [bs.mul(bs.GENERATOR, rng.randrange(bs.N)) for _ in range(3)]
+    ks = [rng.randrange(bs.N) for _ in range(3)]
+    for n in (1, 2, 3):
+        out = _buf(32)
+        lib.ht_te_msm(b"".join(bs.point_to_string(p) for p in pts[:n]), b"".join(k.to_bytes(32, "little") for k in ks[:n]), n, out)
+        assert out.raw == bs.point_to_string(bs.msm(pts[:n], ks[:n]))
+    # a point of small order / outside the subgroup is rejected by the checked decode
+    assert not lib.ht_te_decode(bs.point_to_string((0, bs.P - 1)), 1, _buf(64))
+    assert not lib.ht_te_decode(bs.point_to_string(bs.IDENTITY), 1, _buf(64))
+
+
+def test_hashes(lib):
+    rng = random.Random(6)
+    for n in (0, 1, 55, 111, 112, 113, 127, 128, 129, 167, 168, 169, 335, 336, 1000, 2200):
+        msg = bytes(rng.randrange(256) for _ in range(n))
+        out = _buf(64)
+        lib.ht_sha512(msg, n, out)
+        assert out.raw == hashlib.sha512(msg).digest()
+        for outlen in (48, 200):
+            o2 = _buf(outlen)
+            lib.ht_shake128(msg, n, o2, outlen)
+            assert o2.raw == hashlib.shake_128(msg).digest(outlen)
