@@ -1,0 +1,34 @@
+#!/usr/bin/env bash
+# Build the product library (nvcc, sm_100a) and, with --emul, the CPU emulation of the same kernels
+# used only by the CPU test-suite (tests/host).  Both are built in-tree; .so files are git-ignored.
+set -euo pipefail
+cd "$(dirname "$0")"
+SRC=dot_ring_b200/csrc
+OUT=dot_ring_b200/libdotring_b200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+SOURCES=$(ls $SRC/api_*.cu)
+if [ "${1:-}" = "--emul" ]; then
+  mkdir -p tests/host
+  objs=""
+  for f in $SOURCES; do
+    o=tests/host/.emul_$(basename "$f" .cu).o
+    g++ -O2 -std=c++17 -fPIC -DDR_HOST_EMULATION -x c++ -c "$f" -o "$o" &
+    objs="$objs $o"
+  done
+  wait
+  g++ -shared -o tests/host/libdotring_emul.so $objs -lpthread
+  echo "built tests/host/libdotring_emul.so"
+  exit 0
+fi
+mkdir -p build
+objs=""
+for f in $SOURCES; do
+  o=build/$(basename "$f" .cu).o
+  if [ ! -f "$o" ] || [ -n "$(find $SRC include -newer "$o" \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' -o -name '*.inc' \) | head -1)" ]; then
+    $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA:-} -c "$f" -o "$o" &
+  fi
+  objs="$objs $o"
+done
+wait
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $objs -lcudart
+echo "built $OUT"

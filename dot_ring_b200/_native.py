@@ -1,0 +1,243 @@
+"""ctypes binding of ``libdotring_b200.so`` (C ABI declared in ``include/dot_ring_b200.h``).
+
+The product always loads the CUDA build that sits next to this file and raises if it is missing
+or is not a CUDA build; there is no CPU fallback.  ``Library(path)`` exists so that the CPU
+test-suite can bind the *test-only* emulation build of the same sources (``tests/host``)
+explicitly; nothing in this package ever selects it.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint8, c_uint64, c_void_p
+from pathlib import Path
+
+DR_OK, DR_EINVAL, DR_ECUDA, DR_ENOMEM, DR_ESTATE = 0, -1, -2, -3, -4
+
+_HERE = Path(__file__).resolve().parent
+DEFAULT_LIBRARY = _HERE / "libdotring_b200.so"
+FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"dot_ring_b200 native error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def _u8(buf) -> ctypes.Array:
+    return (c_uint8 * len(buf)).from_buffer_copy(bytes(buf))
+
+
+class Library:
+    """One loaded shared library + typed entry points."""
+
+    def __init__(self, path: os.PathLike | str | None = None, require_cuda: bool = True):
+        path = Path(path) if path is not None else DEFAULT_LIBRARY
+        if not path.exists():
+            raise ImportError(
+                f"{path} is missing: build it with ./build.sh (nvcc, sm_100a). dot_ring_b200 has no CPU fallback."
+            )
+        self.path = path
+        self.lib = ctypes.CDLL(str(path))
+        self._declare()
+        if require_cuda and not self.lib.dr_is_cuda_build():
+            raise ImportError(f"{path} is not a CUDA build; refusing to run the product path on the CPU")
+
+    # ---- prototypes ---------------------------------------------------------------------------
+    def _declare(self) -> None:
+        L = self.lib
+        L.dr_last_error.restype = c_char_p
+        L.dr_version.restype = c_char_p
+        L.dr_is_cuda_build.restype = c_int
+        L.dr_launch_count.restype = c_uint64
+        L.dr_ctx_create.argtypes = [c_int, POINTER(c_void_p)]
+        L.dr_ctx_destroy.argtypes = [c_void_p]
+        L.dr_ctx_destroy.restype = None
+        L.dr_ctx_sync.argtypes = [c_void_p]
+        L.dr_ctx_timer_start.argtypes = [c_void_p]
+        L.dr_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_float)]
+        L.dr_ctx_device_info.argtypes = [c_void_p, c_char_p, c_size_t, POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t)]
+        L.dr_srs_load.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_int, POINTER(c_void_p)]
+        L.dr_srs_destroy.argtypes = [c_void_p]
+        L.dr_srs_destroy.restype = None
+        L.dr_srs_size.argtypes = [c_void_p]
+        L.dr_srs_size.restype = c_size_t
+        L.dr_srs_table_bytes.argtypes = [c_void_p]
+        L.dr_srs_table_bytes.restype = c_size_t
+        L.dr_kzg_commit.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
+        L.dr_kzg_commit_bench.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_uint64, POINTER(c_float), c_void_p]
+        L.dr_g1_compress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
+        L.dr_g1_decompress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+        L.dr_fr_ntt.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_void_p]
+        L.dr_field_op.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]
+        L.dr_microbench.argtypes = [c_void_p, c_int, c_int, POINTER(ctypes.c_double), POINTER(c_float)]
+
+    def check(self, code: int) -> None:
+        if code == DR_OK:
+            return
+        msg = (self.lib.dr_last_error() or b"").decode("utf-8", "replace")
+        if code == DR_EINVAL:
+            raise ValueError(msg)
+        if code == DR_ENOMEM:
+            raise MemoryError(msg)
+        raise NativeError(code, msg)
+
+    @property
+    def is_cuda(self) -> bool:
+        return bool(self.lib.dr_is_cuda_build())
+
+    def launch_count(self) -> int:
+        return int(self.lib.dr_launch_count())
+
+
+_default: Library | None = None
+
+
+def default_library() -> Library:
+    """The CUDA library next to this package (loaded once); raises ImportError when absent."""
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+def set_default_library(lib: Library | None) -> None:
+    """Test hook: inject an explicitly constructed Library (e.g. the tests/host emulation build)."""
+    global _default
+    _default = lib
+
+
+class Context:
+    """One per GPU (dr_ctx)."""
+
+    def __init__(self, device: int = 0, library: Library | None = None):
+        self.library = library or default_library()
+        self.handle = c_void_p()
+        self.library.check(self.library.lib.dr_ctx_create(device, ctypes.byref(self.handle)))
+        self.device = device
+
+    def close(self) -> None:
+        if self.handle:
+            self.library.lib.dr_ctx_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self) -> None:
+        self.library.check(self.library.lib.dr_ctx_sync(self.handle))
+
+    def timer_start(self) -> None:
+        self.library.check(self.library.lib.dr_ctx_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = c_float()
+        self.library.check(self.library.lib.dr_ctx_timer_stop(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def device_info(self) -> dict:
+        name = ctypes.create_string_buffer(128)
+        sm, khz, free, total = c_int(), c_int(), c_size_t(), c_size_t()
+        self.library.check(
+            self.library.lib.dr_ctx_device_info(self.handle, name, 128, ctypes.byref(sm), ctypes.byref(khz), ctypes.byref(free), ctypes.byref(total))
+        )
+        return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": khz.value, "free_bytes": free.value, "total_bytes": total.value}
+
+    # ---- Fr NTT ---------------------------------------------------------------------------------
+    def fr_ntt(self, values: list[int], n: int, omega: int, inverse: bool = False) -> list[int]:
+        """Batched transform of len(values)/n vectors; ints in, ints out (fft.py:87-144 semantics)."""
+        if len(values) % n:
+            raise ValueError("values length must be a multiple of n")
+        batch = len(values) // n
+        buf = ctypes.create_string_buffer(b"".join(int(v).to_bytes(32, "little") for v in values), 32 * len(values))
+        self.library.check(self.library.lib.dr_fr_ntt(self.handle, buf, n, batch, 1 if inverse else 0, int(omega).to_bytes(32, "little")))
+        raw = buf.raw
+        return [int.from_bytes(raw[32 * i : 32 * i + 32], "little") for i in range(len(values))]
+
+    def field_op(self, field: str, op: str, a: list[int], b: list[int] | None = None) -> list[int]:
+        """Element-wise device arithmetic in 'fq' | 'fr' | 'fn' (self-test of the Montgomery kernels)."""
+        fidx = {"fq": 0, "fr": 1, "fn": 2}[field]
+        oidx = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "sqr": 4, "neg": 5}[op]
+        b = b if b is not None else [0] * len(a)
+        size, order = (48, "big") if fidx == 0 else (32, "little")
+        out = ctypes.create_string_buffer(size * len(a))
+        abuf = b"".join(int(x).to_bytes(size, order) for x in a)
+        bbuf = b"".join(int(x).to_bytes(size, order) for x in b)
+        self.library.check(self.library.lib.dr_field_op(self.handle, fidx, oidx, abuf, bbuf, out, len(a)))
+        return [int.from_bytes(out.raw[size * i : size * i + size], order) for i in range(len(a))]
+
+    def microbench(self, kind: str, iters: int) -> tuple[float, float]:
+        """(ops per second over the chip, elapsed ms) for 'imad' | 'imad_wide' | 'fq_mul' | 'fr_mul' | 'g1_madd'."""
+        k = {"imad": 0, "imad_wide": 1, "fq_mul": 2, "fr_mul": 3, "g1_madd": 4}[kind]
+        ops, ms = ctypes.c_double(), c_float()
+        self.library.check(self.library.lib.dr_microbench(self.handle, k, iters, ctypes.byref(ops), ctypes.byref(ms)))
+        return float(ops.value), float(ms.value)
+
+    def g1_compress(self, points_be96: bytes) -> bytes:
+        count = len(points_be96) // 96
+        out = ctypes.create_string_buffer(48 * count)
+        self.library.check(self.library.lib.dr_g1_compress(self.handle, points_be96, count, out))
+        return out.raw
+
+    def g1_decompress(self, points_be48: bytes) -> tuple[bytes, bytes]:
+        count = len(points_be48) // 48
+        out = ctypes.create_string_buffer(96 * count)
+        ok = ctypes.create_string_buffer(count)
+        self.library.check(self.library.lib.dr_g1_decompress(self.handle, points_be48, count, out, ok))
+        return out.raw, ok.raw
+
+
+class NativeSrs:
+    """dr_srs: SRS points + fixed-base window table resident on the device."""
+
+    def __init__(self, ctx: Context, g1_be96: bytes, g2_be192: bytes, window_bits: int = 0):
+        self.ctx = ctx
+        self.handle = c_void_p()
+        n = len(g1_be96) // 96
+        if len(g2_be192) != 384:
+            raise ValueError("expected two 192-byte G2 points")
+        lib = ctx.library
+        lib.check(lib.lib.dr_srs_load(ctx.handle, g1_be96, n, g2_be192, window_bits, ctypes.byref(self.handle)))
+        self.size = n
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.library.lib.dr_srs_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def table_bytes(self) -> int:
+        return int(self.ctx.library.lib.dr_srs_table_bytes(self.handle))
+
+    def commit(self, coeff_vectors: list[list[int]]) -> list[bytes]:
+        """KZG.commit for a batch of equal-length coefficient vectors -> 96-byte uncompressed points."""
+        if not coeff_vectors:
+            return []
+        n = len(coeff_vectors[0])
+        if any(len(v) != n for v in coeff_vectors):
+            raise ValueError("all coefficient vectors in a batch must have the same length")
+        batch = len(coeff_vectors)
+        out = ctypes.create_string_buffer(96 * batch)
+        data = b"".join((int(c) % FR_MODULUS).to_bytes(32, "little") for v in coeff_vectors for c in v)
+        lib = self.ctx.library
+        lib.check(lib.lib.dr_kzg_commit(self.ctx.handle, self.handle, data, n, batch, out))
+        return [out.raw[96 * i : 96 * i + 96] for i in range(batch)]
+
+    def commit_bench(self, n: int, batch: int, iters: int, seed: int = 1) -> tuple[float, bytes]:
+        ms = c_float()
+        first = ctypes.create_string_buffer(96)
+        lib = self.ctx.library
+        lib.check(lib.lib.dr_kzg_commit_bench(self.ctx.handle, self.handle, n, batch, iters, seed, ctypes.byref(ms), first))
+        return float(ms.value), first.raw

@@ -1,0 +1,370 @@
+// C ABI, part 1: context, SRS + fixed-base table, KZG commit, G1 codecs, Fr NTT.
+#include "api_internal.cuh"
+
+namespace dr {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// ---- NTT plans (twiddle tables per (n, omega)) -----------------------------------------------------
+const NttPlan& Ctx::plan(uint32_t n, const Fr& omega_mont) {
+    for (auto& p : plans)
+        if (p->n == n && p->omega == omega_mont) return *p;
+    auto p = std::make_unique<NttPlan>();
+    p->n = n;
+    p->logn = 0;
+    while ((1u << p->logn) < n) p->logn++;
+    p->omega = omega_mont;
+    std::vector<Fr> fwd(n / 2 ? n / 2 : 1), inv(n / 2 ? n / 2 : 1);
+    Fr w = Fr::one(), wi = Fr::one(), omega_inv = omega_mont.inv();
+    for (uint32_t k = 0; k < n / 2; k++) {
+        fwd[k] = w;
+        inv[k] = wi;
+        w = w * omega_mont;
+        wi = wi * omega_inv;
+    }
+    p->tw_fwd.alloc(fwd.size());
+    p->tw_inv.alloc(inv.size());
+    h2d(stream, p->tw_fwd.p, fwd.data(), fwd.size() * sizeof(Fr));
+    h2d(stream, p->tw_inv.p, inv.data(), inv.size() * sizeof(Fr));
+    Fr ninv = Fr::from_u32(n).inv();
+    p->n_inv.alloc(1);
+    h2d(stream, p->n_inv.p, &ninv, sizeof(Fr));
+    stream_sync(stream);
+    plans.push_back(std::move(p));
+    return *plans.back();
+}
+
+void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
+    if (n == 0 || batch == 0) return;
+    if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
+    // enough CTAs to fill the machine: batch * slices >= ~2 waves of 148 SMs x 4 resident CTAs
+    uint32_t slices = 1;
+    const uint32_t target = 148 * 8;
+    if (batch < target) {
+        slices = (target + batch - 1) / batch;
+        uint32_t max_slices = (n + 31) / 32;  // keep >= 32 points per slice
+        if (slices > max_slices) slices = max_slices;
+        if (slices < 1) slices = 1;
+    }
+    ctx->partials.ensure((size_t)batch * slices);
+    const uint32_t threads = COMMIT_THREADS;
+    launch(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
+    launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
+}
+
+}  // namespace dr
+
+using namespace dr;
+
+#define DR_API_BEGIN try {
+#define DR_API_END                                   \
+    }                                                \
+    catch (const Error& e) {                         \
+        return set_error(e.code, e.what());          \
+    }                                                \
+    catch (const std::exception& e) {                \
+        return set_error(DR_ECUDA, e.what());        \
+    }                                                \
+    return DR_OK;
+
+extern "C" {
+
+const char* dr_last_error(void) { return g_last_error.c_str(); }
+const char* dr_version(void) { return "dot_ring_b200 0.1 (sm_100a)"; }
+int dr_is_cuda_build(void) {
+#if defined(DR_HOST_EMULATION)
+    return 0;
+#else
+    return 1;
+#endif
+}
+uint64_t dr_launch_count(void) { return launch_counter(); }
+
+int dr_ctx_create(int device, dr_ctx** out) {
+    DR_API_BEGIN
+    if (!out) throw Error(DR_EINVAL, "null out pointer");
+    auto ctx = std::make_unique<Ctx>();
+    ctx->device = device;
+#if !defined(DR_HOST_EMULATION)
+    int count = 0;
+    DR_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) throw Error(DR_EINVAL, "no such CUDA device");
+    DR_CUDA(cudaSetDevice(device));
+    DR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DR_CUDA(cudaEventCreate(&ctx->ev_start));
+    DR_CUDA(cudaEventCreate(&ctx->ev_stop));
+#else
+    ctx->stream = 0;
+#endif
+    *out = (dr_ctx*)ctx.release();
+    DR_API_END
+}
+
+void dr_ctx_destroy(dr_ctx* c) {
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx) return;
+#if !defined(DR_HOST_EMULATION)
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+#endif
+    ctx->plans.clear();
+    ctx->release_scratch();
+#if !defined(DR_HOST_EMULATION)
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaStreamDestroy(ctx->stream);
+#endif
+    delete ctx;
+}
+
+int dr_ctx_sync(dr_ctx* c) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    ctx->activate();
+    stream_sync(ctx->stream);
+    DR_API_END
+}
+
+int dr_ctx_timer_start(dr_ctx* c) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    ctx->activate();
+#if !defined(DR_HOST_EMULATION)
+    DR_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+#else
+    ctx->t_start = std::chrono::steady_clock::now();
+#endif
+    DR_API_END
+}
+
+int dr_ctx_timer_stop(dr_ctx* c, float* ms_out) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    ctx->activate();
+#if !defined(DR_HOST_EMULATION)
+    DR_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    DR_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    DR_CUDA(cudaEventElapsedTime(ms_out, ctx->ev_start, ctx->ev_stop));
+#else
+    *ms_out = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->t_start).count();
+#endif
+    DR_API_END
+}
+
+int dr_ctx_device_info(dr_ctx* c, char* name_buf, size_t name_len, int* sm_count, int* sm_clock_khz, size_t* free_bytes, size_t* total_bytes) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    ctx->activate();
+#if !defined(DR_HOST_EMULATION)
+    cudaDeviceProp prop;
+    DR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    if (name_buf && name_len) snprintf(name_buf, name_len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (sm_clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *sm_clock_khz = khz;
+    }
+    size_t f = 0, t = 0;
+    DR_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+#else
+    if (name_buf && name_len) snprintf(name_buf, name_len, "cpu-emulation");
+    if (sm_count) *sm_count = 0;
+    if (sm_clock_khz) *sm_clock_khz = 0;
+    if (free_bytes) *free_bytes = 0;
+    if (total_bytes) *total_bytes = 0;
+#endif
+    DR_API_END
+}
+
+// ---------------------------------------------------------------------------------------- SRS
+int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g2_be192, int window_bits, dr_srs** out) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !g1_be96 || !g2_be192 || !out || n_g1 == 0) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    uint32_t cbits = window_bits <= 0 ? 12 : (uint32_t)window_bits;
+    if (cbits < 2 || cbits > 15) throw Error(DR_EINVAL, "window_bits must be in [2, 15]");
+    auto srs = std::make_unique<Srs>();
+    srs->ctx = ctx;
+    srs->n = (uint32_t)n_g1;
+    memcpy(srs->g1_0_be96, g1_be96, 96);
+    memcpy(srs->g2_be192, g2_be192, 384);
+    srs->geom = make_geom(cbits, srs->n);
+    if (srs->geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
+    DevBuf<uint8_t> raw(n_g1 * 96);
+    DevBuf<uint32_t> bad(1);
+    dev_zero(ctx->stream, bad.p, 4);
+    h2d(ctx->stream, raw.p, g1_be96, n_g1 * 96);
+    srs->points.alloc(n_g1);
+    launch(ctx->stream, Dim3((srs->n + 127) / 128), 128, 0, SrsLoadBody(), (const uint8_t*)raw.p, srs->points.p, srs->n, bad.p);
+    uint32_t bad_h = 0;
+    d2h(ctx->stream, &bad_h, bad.p, 4);
+    stream_sync(ctx->stream);
+    if (bad_h) throw Error(DR_EINVAL, "invalid BLS12-381 G1 encoding in SRS");
+    // fixed-base table
+    srs->table.alloc(srs->geom.total_entries());
+    uint32_t chunks = srs->geom.H >= 512 ? srs->geom.H / 256 : 1;  // <= 256 serial additions per thread
+    size_t nthreads = (size_t)srs->n * chunks;
+    const uint32_t tb = 64;
+    Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
+    if (srs->geom.W <= 32)
+        launch(ctx->stream, grid, tb, 0, TableBuildBody<32>(), (const G1Affine*)srs->points.p, srs->table.p, srs->geom, chunks);
+    else
+        launch(ctx->stream, grid, tb, 0, TableBuildBody<64>(), (const G1Affine*)srs->points.p, srs->table.p, srs->geom, chunks);
+    stream_sync(ctx->stream);
+    *out = (dr_srs*)srs.release();
+    DR_API_END
+}
+
+void dr_srs_destroy(dr_srs* s) { delete (Srs*)s; }
+size_t dr_srs_size(const dr_srs* s) { return s ? ((const Srs*)s)->n : 0; }
+size_t dr_srs_table_bytes(const dr_srs* s) { return s ? ((const Srs*)s)->geom.total_entries() * sizeof(G1Affine) : 0; }
+
+int dr_kzg_commit(dr_ctx* c, dr_srs* s, const uint8_t* coeffs_le32, size_t n, size_t batch, uint8_t* out_be96) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    Srs* srs = (Srs*)s;
+    if (!ctx || !srs || !out_be96 || (!coeffs_le32 && n * batch)) throw Error(DR_EINVAL, "bad argument");
+    if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
+    ctx->activate();
+    if (batch == 0) return DR_OK;
+    if (n == 0) {  // empty polynomial commits to infinity
+        for (size_t b = 0; b < batch; b++) {
+            memset(out_be96 + 96 * b, 0, 96);
+            out_be96[96 * b] = 0x40;
+        }
+        return DR_OK;
+    }
+    size_t total = n * batch;
+    DevBuf<uint8_t> raw(total * 32);
+    DevBuf<Fr> sc(total);
+    DevBuf<G1Affine> res(batch);
+    DevBuf<uint8_t> enc(batch * 96);
+    h2d(ctx->stream, raw.p, coeffs_le32, total * 32);
+    launch(ctx->stream, Dim3((uint32_t)((total + 255) / 256)), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, sc.p, total, (uint32_t*)nullptr);
+    commit_device(ctx, srs, sc.p, n, (uint32_t)n, (uint32_t)batch, res.p);
+    launch(ctx->stream, Dim3((uint32_t)((batch + 63) / 64)), 64, 0, G1EncodeBody(), (const G1Affine*)res.p, (uint32_t)batch, enc.p, (uint8_t*)nullptr);
+    d2h(ctx->stream, out_be96, enc.p, batch * 96);
+    stream_sync(ctx->stream);
+    DR_API_END
+}
+
+// splitmix64-based deterministic scalars generated on the device side of the ABI (host fills, uploads once)
+static uint64_t splitmix64(uint64_t& x) {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+int dr_kzg_commit_bench(dr_ctx* c, dr_srs* s, size_t n, size_t batch, int iters, uint64_t seed, float* ms_per_iter, uint8_t* out_first_be96) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    Srs* srs = (Srs*)s;
+    if (!ctx || !srs || n == 0 || batch == 0 || iters <= 0 || n > srs->n) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    size_t total = n * batch;
+    std::vector<uint8_t> host(total * 32);
+    uint64_t st = seed;
+    for (size_t i = 0; i < total; i++) {
+        uint64_t w[4] = {splitmix64(st), splitmix64(st), splitmix64(st), splitmix64(st) >> 2};  // < 2^254 < r
+        memcpy(&host[32 * i], w, 32);
+    }
+    DevBuf<uint8_t> raw(total * 32);
+    DevBuf<Fr> sc(total);
+    DevBuf<G1Affine> res(batch);
+    h2d(ctx->stream, raw.p, host.data(), total * 32);
+    launch(ctx->stream, Dim3((uint32_t)((total + 255) / 256)), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, sc.p, total, (uint32_t*)nullptr);
+    commit_device(ctx, srs, sc.p, n, (uint32_t)n, (uint32_t)batch, res.p);  // warm-up
+    stream_sync(ctx->stream);
+    float ms = 0;
+    dr_ctx_timer_start(c);
+    for (int it = 0; it < iters; it++) commit_device(ctx, srs, sc.p, n, (uint32_t)n, (uint32_t)batch, res.p);
+    dr_ctx_timer_stop(c, &ms);
+    if (ms_per_iter) *ms_per_iter = ms / iters;
+    if (out_first_be96) {
+        DevBuf<uint8_t> enc(96);
+        launch(ctx->stream, Dim3(1), 64, 0, G1EncodeBody(), (const G1Affine*)res.p, 1u, enc.p, (uint8_t*)nullptr);
+        d2h(ctx->stream, out_first_be96, enc.p, 96);
+        stream_sync(ctx->stream);
+    }
+    DR_API_END
+}
+
+// ------------------------------------------------------------------------------------- G1 codecs
+int dr_g1_compress(dr_ctx* c, const uint8_t* in_be96, size_t count, uint8_t* out_be48) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || (count && (!in_be96 || !out_be48))) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    if (!count) return DR_OK;
+    DevBuf<uint8_t> raw(count * 96), ok(count), enc(count * 48);
+    DevBuf<G1Affine> pts(count);
+    h2d(ctx->stream, raw.p, in_be96, count * 96);
+    uint32_t blocks = (uint32_t)((count + 63) / 64);
+    launch(ctx->stream, Dim3(blocks), 64, 0, G1DecodeBody(), (const uint8_t*)raw.p, 96u, (uint32_t)count, pts.p, ok.p);
+    launch(ctx->stream, Dim3(blocks), 64, 0, G1EncodeBody(), (const G1Affine*)pts.p, (uint32_t)count, (uint8_t*)nullptr, enc.p);
+    std::vector<uint8_t> okh(count);
+    d2h(ctx->stream, okh.data(), ok.p, count);
+    d2h(ctx->stream, out_be48, enc.p, count * 48);
+    stream_sync(ctx->stream);
+    for (size_t i = 0; i < count; i++)
+        if (!okh[i]) throw Error(DR_EINVAL, "invalid BLS12-381 G1 encoding");
+    DR_API_END
+}
+
+int dr_g1_decompress(dr_ctx* c, const uint8_t* in_be48, size_t count, uint8_t* out_be96, uint8_t* ok_out) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || (count && (!in_be48 || !out_be96 || !ok_out))) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    if (!count) return DR_OK;
+    DevBuf<uint8_t> raw(count * 48), ok(count), enc(count * 96);
+    DevBuf<G1Affine> pts(count);
+    h2d(ctx->stream, raw.p, in_be48, count * 48);
+    uint32_t blocks = (uint32_t)((count + 63) / 64);
+    launch(ctx->stream, Dim3(blocks), 64, 0, G1DecodeBody(), (const uint8_t*)raw.p, 48u, (uint32_t)count, pts.p, ok.p);
+    launch(ctx->stream, Dim3(blocks), 64, 0, G1EncodeBody(), (const G1Affine*)pts.p, (uint32_t)count, enc.p, (uint8_t*)nullptr);
+    d2h(ctx->stream, ok_out, ok.p, count);
+    d2h(ctx->stream, out_be96, enc.p, count * 96);
+    stream_sync(ctx->stream);
+    DR_API_END
+}
+
+// ---------------------------------------------------------------------------------------- NTT
+int dr_fr_ntt(dr_ctx* c, uint8_t* data_le32, size_t n, size_t batch, int inverse, const uint8_t omega_le32[32]) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !data_le32 || !omega_le32) throw Error(DR_EINVAL, "bad argument");
+    if (n < 2 || n > 4096 || (n & (n - 1))) throw Error(DR_EINVAL, "n must be a power of two in [2, 4096]");
+    ctx->activate();
+    if (!batch) return DR_OK;
+    Fr om;
+    fr_from_le_bytes_raw(om, omega_le32);
+    if (!om.is_canonical_raw()) throw Error(DR_EINVAL, "omega is not canonical");
+    om = om.to_mont();
+    const NttPlan& plan = ctx->plan((uint32_t)n, om);
+    size_t total = n * batch;
+    DevBuf<uint8_t> raw(total * 32);
+    DevBuf<Fr> buf(total);
+    h2d(ctx->stream, raw.p, data_le32, total * 32);
+    uint32_t blocks = (uint32_t)((total + 255) / 256);
+    launch(ctx->stream, Dim3(blocks), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, buf.p, total, (uint32_t*)nullptr);
+    uint32_t threads = n / 2 < 256 ? (uint32_t)(n / 2 < 32 ? 32 : n / 2) : 256;
+    launch(ctx->stream, Dim3((uint32_t)batch), threads, ntt_smem_bytes((uint32_t)n), NttPlainBody(), (const Fr*)buf.p, buf.p, (uint32_t)n, plan.logn,
+           (const Fr*)(inverse ? plan.tw_inv.p : plan.tw_fwd.p), (const Fr*)(inverse ? plan.n_inv.p : nullptr));
+    launch(ctx->stream, Dim3(blocks), 256, 0, FrFromMontBody(), (const Fr*)buf.p, raw.p, total);
+    d2h(ctx->stream, data_le32, raw.p, total * 32);
+    stream_sync(ctx->stream);
+    DR_API_END
+}
+
+}  // extern "C"

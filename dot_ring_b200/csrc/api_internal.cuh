@@ -1,0 +1,62 @@
+// Internal host-side state shared by the api_*.cu translation units.
+#pragma once
+#include <chrono>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dot_ring_b200.h"
+#include "fp.cuh"
+#include "g1.cuh"
+#include "hash.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "rt.cuh"
+#include "te.cuh"
+
+namespace dr {
+
+constexpr uint32_t COMMIT_THREADS = 128;
+
+int set_error(int code, const std::string& msg);
+
+struct NttPlan {
+    uint32_t n = 0, logn = 0;
+    Fr omega;
+    DevBuf<Fr> tw_fwd, tw_inv, n_inv;
+};
+
+struct Ctx {
+    int device = 0;
+    Stream stream{};
+#if !defined(DR_HOST_EMULATION)
+    cudaEvent_t ev_start{}, ev_stop{};
+#else
+    std::chrono::steady_clock::time_point t_start;
+#endif
+    std::vector<std::unique_ptr<NttPlan>> plans;
+    DevBuf<G1> partials;
+
+    void activate() {
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaSetDevice(device));
+#endif
+    }
+    const NttPlan& plan(uint32_t n, const Fr& omega_mont);
+    void release_scratch() { partials.release(); }
+};
+
+struct Srs {
+    Ctx* ctx = nullptr;
+    uint32_t n = 0;
+    DevBuf<G1Affine> points;  // Montgomery affine
+    DevBuf<G1Affine> table;   // fixed-base window table
+    TableGeom geom{};
+    uint8_t g1_0_be96[96];
+    uint8_t g2_be192[384];
+};
+
+// scalars: `batch` vectors of n Montgomery Fr, vector b at scalars + b*stride.  Result: affine points.
+void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine);
+
+}  // namespace dr

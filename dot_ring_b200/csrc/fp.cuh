@@ -18,9 +18,13 @@
 #if defined(__CUDACC__)
 #define DR_HD __host__ __device__ __forceinline__
 #define DR_D __device__ __forceinline__
+// large, rarely executed helpers (inversions, exponentiations, exceptional group-law cases) stay out of
+// line on the device: it keeps the hot loops inside the instruction cache and the build time sane
+#define DR_HD_COLD inline __host__ __device__ __noinline__
 #else
 #define DR_HD inline
 #define DR_D inline
+#define DR_HD_COLD inline
 #endif
 
 namespace dr {
@@ -95,7 +99,7 @@ struct FnTag {  // Bandersnatch prime-subgroup order (VRF scalar arithmetic)
 };
 
 template <class T>
-struct Fp {
+struct alignas(16) Fp {
     static constexpr int N = T::N;
     uint32_t v[N];
 
@@ -264,10 +268,12 @@ struct Fp {
     DR_HD bool is_canonical_raw() const { return !geq_mod(v); }
 
     // x^e for a little-endian limb exponent (variable time; exponents here are public)
-    DR_HD Fp pow(const uint32_t* e, int nlimbs) const {
+    DR_HD_COLD Fp pow(const uint32_t* e, int nlimbs) const {
         Fp acc = one();
         bool started = false;
+#pragma unroll 1
         for (int i = nlimbs - 1; i >= 0; i--) {
+#pragma unroll 1
             for (int b = 31; b >= 0; b--) {
                 if (started) acc = acc.sqr();
                 if ((e[i] >> b) & 1) {
@@ -279,7 +285,7 @@ struct Fp {
         return acc;
     }
     // Fermat inverse x^(p-2); 0 -> 0
-    DR_HD Fp inv() const {
+    DR_HD_COLD Fp inv() const {
         uint32_t e[N];
 #pragma unroll
         for (int i = 0; i < N; i++) e[i] = T::mod(i);

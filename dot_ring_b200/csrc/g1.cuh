@@ -28,7 +28,7 @@ struct G1 {  // XYZZ
     }
 };
 
-DR_HD G1 g1_dbl_affine(const G1Affine& a) {
+DR_HD_COLD G1 g1_dbl_affine(const G1Affine& a) {
     if (a.is_inf() || a.y.is_zero()) return G1::inf();
     Fq U = a.y.dbl();
     Fq V = U.sqr();
@@ -44,7 +44,7 @@ DR_HD G1 g1_dbl_affine(const G1Affine& a) {
     return r;
 }
 
-DR_HD G1 g1_dbl(const G1& p) {
+DR_HD_COLD G1 g1_dbl(const G1& p) {
     if (p.is_inf() || p.Y.is_zero()) return G1::inf();
     Fq U = p.Y.dbl();
     Fq V = U.sqr();
@@ -92,7 +92,7 @@ DR_HD void g1_madd(G1& acc, const G1Affine& a, bool neg = false) {
     acc.ZZZ = acc.ZZZ * PPP;
 }
 
-DR_HD void g1_add(G1& acc, const G1& b) {
+DR_HD_COLD void g1_add(G1& acc, const G1& b) {
     if (b.is_inf()) return;
     if (acc.is_inf()) {
         acc = b;
@@ -126,7 +126,7 @@ DR_HD G1 g1_neg(const G1& p) {
     return r;
 }
 
-DR_HD G1Affine g1_to_affine(const G1& p) {
+DR_HD_COLD G1Affine g1_to_affine(const G1& p) {
     if (p.is_inf()) return G1Affine::inf();
     Fq t = (p.ZZ * p.ZZZ).inv();
     Fq zz_inv = t * p.ZZZ;
@@ -176,7 +176,7 @@ DR_HD void g1_compress(uint8_t* out48, const G1Affine& a) {
 }
 
 // sqrt in Fq: p = 3 mod 4, candidate a^((p+1)/4)
-DR_HD bool fq_sqrt(Fq& out, const Fq& a) {
+DR_HD_COLD bool fq_sqrt(Fq& out, const Fq& a) {
     // (p+1)/4 little-endian limbs
     constexpr uint32_t e[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
                                 0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};
@@ -190,7 +190,7 @@ DR_HD bool fq_sqrt(Fq& out, const Fq& a) {
 // Decode 48-byte compressed or 96-byte uncompressed zcash G1.  Returns false on a malformed
 // encoding (blst raises; the reference turns that into ValueError("invalid BLS12-381 G1 encoding")).
 // No subgroup check, matching blst's P1_Affine(bytes) constructor.
-DR_HD bool g1_decode(G1Affine& out, const uint8_t* in, int len) {
+DR_HD_COLD bool g1_decode(G1Affine& out, const uint8_t* in, int len) {
     if (len != 48 && len != 96) return false;
     uint8_t flags = in[0];
     bool compressed = (flags & 0x80) != 0;

@@ -1,0 +1,277 @@
+// KZG commitments over the fixed G1 SRS: fixed-base window tables in HBM + batched commit kernel.
+//
+// The reference commits with blst's single-threaded Pippenger over the SRS prefix
+// (dot_ring/ring_proof/pcs/kzg.py:152-175, `mult_pippenger(srs.blst_g1_memory[:len], coeffs)`),
+// seven times per proof (4 witness columns, quotient, two openings; proof_builder.py:38-142).
+// Here every one of those MSMs uses the same bases, so the bases are expanded ONCE per SRS into a
+// table  T[i][w][d-1] = d * 2^(c*w) * [tau^i]_1   (d = 1 .. 2^(c-1), affine, Montgomery)
+// that lives in HBM (c = 12: 6145 * 22 * 2048 * 96 B = 26.6 GB of the 180 GB), and a commitment is
+// just  sum_i sum_w  +-T[i][w][|digit_w(k_i)|]  : W mixed additions per coefficient, no buckets, no
+// sort, no doublings, perfectly balanced across threads.  The group element is identical to what
+// Pippenger returns, so the commitment bytes are identical.
+#pragma once
+#include "g1.cuh"
+#include "rt.cuh"
+
+namespace dr {
+
+struct TableGeom {
+    uint32_t c;        // window bits
+    uint32_t W;        // windows = ceil(256 / c)
+    uint32_t H;        // entries per (i, w) = 2^(c-1)
+    uint32_t n_points; // SRS points covered
+    DR_HD size_t entry(uint32_t i, uint32_t w, uint32_t d) const { return (((size_t)i * W + w) << (c - 1)) + (d - 1); }
+    size_t total_entries() const { return ((size_t)n_points * W) << (c - 1); }
+};
+inline TableGeom make_geom(uint32_t c, uint32_t n_points) {
+    TableGeom g;
+    g.c = c;
+    g.W = (256 + c - 1) / c;
+    g.H = 1u << (c - 1);
+    g.n_points = n_points;
+    return g;
+}
+
+// ---- SRS ingestion: 96-byte big-endian uncompressed points -> Montgomery affine --------------------
+struct SrsLoadBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* in, G1Affine* out, uint32_t n, uint32_t* bad) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < n) {
+                G1Affine a;
+                if (!g1_decode(a, in + 96 * (size_t)i, 96) || a.is_inf()) {
+                    *bad = 1;
+                    a = G1Affine::inf();
+                }
+                out[i] = a;
+            }
+        }
+    }
+};
+
+// ---- table construction -------------------------------------------------------------------------
+// Thread (i, q): SRS point i, digit range d in [q*L + 1, (q+1)*L], all W windows in lockstep so that
+// each step's W affine additions share one field inversion (Montgomery's trick).
+template <int MAXW>
+struct TableBuildBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* srs, G1Affine* table, TableGeom g, uint32_t chunks) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t gid = ctx.bx * ctx.nthreads + t;
+            uint32_t i = gid / chunks, q = gid % chunks;
+            if (i < g.n_points) {
+                const uint32_t W = g.W;
+                const uint32_t L = g.H / chunks;
+                const uint32_t d0 = q * L + 1;
+                Fq bx[MAXW], by[MAXW], ex[MAXW], ey[MAXW], den[MAXW], pre[MAXW];
+                // 1. window bases B_w = 2^(c*w) * P_i
+                {
+                    G1 cur = G1::from_affine(srs[i]);
+                    G1 proj[MAXW];
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        proj[w] = cur;
+                        if (w + 1 < W)
+#pragma unroll 1
+                            for (uint32_t k = 0; k < g.c; k++) cur = g1_dbl(cur);
+                    }
+                    // batch normalise: x = X / ZZ, y = Y / ZZZ
+                    Fq acc = Fq::one();
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        pre[w] = acc;
+                        den[w] = proj[w].ZZ * proj[w].ZZZ;
+                        acc = acc * den[w];
+                    }
+                    Fq inv = acc.inv();
+#pragma unroll 1
+                    for (int w = (int)W - 1; w >= 0; w--) {
+                        Fq di = inv * pre[w];
+                        inv = inv * den[w];
+                        bx[w] = proj[w].X * (di * proj[w].ZZZ);
+                        by[w] = proj[w].Y * (di * proj[w].ZZ);
+                    }
+                }
+                // 2. chunk start E_w = d0 * B_w
+                if (d0 == 1) {
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        ex[w] = bx[w];
+                        ey[w] = by[w];
+                    }
+                } else {
+                    G1 proj[MAXW];
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        G1Affine b{bx[w], by[w]};
+                        G1 acc = G1::inf();
+#pragma unroll 1
+                        for (int bit = 31; bit >= 0; bit--) {
+                            acc = g1_dbl(acc);
+                            if ((d0 >> bit) & 1) g1_madd(acc, b);
+                        }
+                        proj[w] = acc;
+                    }
+                    Fq acc = Fq::one();
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        pre[w] = acc;
+                        den[w] = proj[w].ZZ * proj[w].ZZZ;
+                        acc = acc * den[w];
+                    }
+                    Fq inv = acc.inv();
+#pragma unroll 1
+                    for (int w = (int)W - 1; w >= 0; w--) {
+                        Fq di = inv * pre[w];
+                        inv = inv * den[w];
+                        ex[w] = proj[w].X * (di * proj[w].ZZZ);
+                        ey[w] = proj[w].Y * (di * proj[w].ZZ);
+                    }
+                }
+#pragma unroll 1
+                for (uint32_t w = 0; w < W; w++) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
+                // 3. E_w += B_w, one shared inversion per step
+#pragma unroll 1
+                for (uint32_t d = d0 + 1; d < d0 + L; d++) {
+                    Fq acc = Fq::one();
+#pragma unroll 1
+                    for (uint32_t w = 0; w < W; w++) {
+                        pre[w] = acc;
+                        // E == B only for d == 2 (then the chord degenerates to the tangent); E == -B never
+                        den[w] = (d == 2) ? ey[w].dbl() : bx[w] - ex[w];
+                        acc = acc * den[w];
+                    }
+                    Fq inv = acc.inv();
+#pragma unroll 1
+                    for (int w = (int)W - 1; w >= 0; w--) {
+                        Fq di = inv * pre[w];
+                        inv = inv * den[w];
+                        Fq num;
+                        if (d == 2) {
+                            Fq xx = ex[w].sqr();
+                            num = xx.dbl() + xx;
+                        } else {
+                            num = by[w] - ey[w];
+                        }
+                        Fq lam = num * di;
+                        Fq x3 = lam.sqr() - ex[w] - bx[w];
+                        Fq y3 = lam * (ex[w] - x3) - ey[w];
+                        ex[w] = x3;
+                        ey[w] = y3;
+                        table[g.entry(i, w, d)] = G1Affine{x3, y3};
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ---- signed-digit recoding -------------------------------------------------------------------------
+// k: canonical little-endian limbs (< 2^255).  Returns digit w in [-(H-1), H]; carry is threaded.
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) {
+    uint32_t bit = w * c;
+    uint32_t limb = bit >> 5, off = bit & 31;
+    uint64_t two = (limb < 8 ? (uint64_t)k[limb] : 0) | ((limb + 1 < 8 ? (uint64_t)k[limb + 1] : 0) << 32);
+    uint32_t raw = (uint32_t)(two >> off) & ((1u << c) - 1);
+    uint32_t d = raw + carry;
+    uint32_t H = 1u << (c - 1);
+    if (d > H) {
+        carry = 1;
+        return (int)d - (int)(1u << c);
+    }
+    carry = 0;
+    return (int)d;
+}
+
+// ---- batched commit ----------------------------------------------------------------------------------
+// grid = (slices, batch).  MSM `by` uses scalars[by * scalar_stride + i] (Montgomery Fr), i < n, against
+// SRS points 0..n-1.  Each block accumulates its slice of points and tree-reduces to one XYZZ partial.
+struct CommitBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, const Fr* scalars, size_t scalar_stride, uint32_t n, G1* partials) const {
+        G1* sm = (G1*)ctx.smem;
+        const uint32_t slices = ctx.gx;
+        const uint32_t per = (n + slices - 1) / slices;
+        const uint32_t lo = ctx.bx * per;
+        const uint32_t hi = (lo + per < n) ? lo + per : n;
+        const Fr* sc = scalars + (size_t)ctx.by * scalar_stride;
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+#pragma unroll 1
+            for (uint32_t i = lo + t; i < hi; i += ctx.nthreads) {
+                Fr kc = sc[i].from_mont();
+                uint32_t carry = 0;
+                int d_next = msm_digit(kc.v, 0, g.c, carry);
+                G1Affine pt_next = G1Affine::inf();
+                if (d_next) pt_next = table[g.entry(i, 0, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+#pragma unroll 1
+                for (uint32_t w = 0; w < g.W; w++) {
+                    int d = d_next;
+                    G1Affine pt = pt_next;
+                    if (w + 1 < g.W) {
+                        d_next = msm_digit(kc.v, w + 1, g.c, carry);
+                        if (d_next) pt_next = table[g.entry(i, w + 1, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+                    }
+                    if (d) g1_madd(acc, pt, d < 0);
+                }
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) partials[(size_t)ctx.by * slices + ctx.bx] = sm[0];
+        }
+    }
+};
+
+// Sum `slices` partials per MSM and normalise to affine.  One thread per MSM.
+struct CommitFinishBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1* partials, uint32_t slices, uint32_t batch, G1Affine* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t m = ctx.bx * ctx.nthreads + t;
+            if (m < batch) {
+                G1 acc = partials[(size_t)m * slices];
+                for (uint32_t s = 1; s < slices; s++) g1_add(acc, partials[(size_t)m * slices + s]);
+                out[m] = g1_to_affine(acc);
+            }
+        }
+    }
+};
+
+// affine (Montgomery) -> 96-byte uncompressed and/or 48-byte compressed zcash bytes
+struct G1EncodeBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* in, uint32_t count, uint8_t* out96, uint8_t* out48) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t m = ctx.bx * ctx.nthreads + t;
+            if (m < count) {
+                G1Affine a = in[m];
+                if (out96) g1_serialize(out96 + 96 * (size_t)m, a);
+                if (out48) g1_compress(out48 + 48 * (size_t)m, a);
+            }
+        }
+    }
+};
+
+// 48-byte compressed / 96-byte uncompressed -> affine Montgomery; ok[m] = 0 on a malformed encoding
+struct G1DecodeBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* in, uint32_t len, uint32_t count, G1Affine* out, uint8_t* ok) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t m = ctx.bx * ctx.nthreads + t;
+            if (m < count) {
+                G1Affine a;
+                bool good = g1_decode(a, in + (size_t)len * m, (int)len);
+                if (!good) a = G1Affine::inf();
+                out[m] = a;
+                ok[m] = good ? 1 : 0;
+            }
+        }
+    }
+};
+
+}  // namespace dr

@@ -1,0 +1,106 @@
+// Fr NTT in shared memory, one CTA per transform (n <= 4096 elements).
+//
+// Replaces dot_ring/ring_proof/polynomial/ntt.pyx:116-163 + bls12_381_scalar.c:333-356
+// (bit-reverse gather, log2 n radix-2 DIT rounds, optional scale) behind
+// dot_ring/ring_proof/polynomial/fft.py:87-144 (inverse_fft / evaluate_poly_fft).  Input and
+// output are in natural order like the reference; the transform is exact field arithmetic, so the
+// butterfly schedule is free.
+//
+// The working set lives in shared memory in limb-planar layout (sm[limb * n + index]) so that
+// unit-stride butterflies are bank-conflict free with 32-bit accesses.  Loading and storing go
+// through functors, which lets callers fuse the witness-column synthesis, the coset pre-twist of
+// the 4x low-degree extension and the 1/n scaling into the transform instead of materialising
+// intermediate vectors in HBM.
+#pragma once
+#include "fp.cuh"
+#include "rt.cuh"
+
+namespace dr {
+
+DR_HD uint32_t bit_reverse(uint32_t x, uint32_t bits) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+
+DR_HD Fr sm_load(const uint32_t* sm, uint32_t n, uint32_t i) {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = sm[l * n + i];
+    return r;
+}
+DR_HD void sm_store(uint32_t* sm, uint32_t n, uint32_t i, const Fr& x) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) sm[l * n + i] = x.v[l];
+}
+
+// tw[k] = w^k (Montgomery), k < n/2, for the n-th root of unity w of this transform.
+// loader(k): k-th input in natural order.  storer(k, value): k-th output in natural order.
+template <class Loader, class Storer>
+DR_HD void ntt_block(const BlockCtx& ctx, uint32_t n, uint32_t logn, const Fr* tw, const Loader& loader, const Storer& storer) {
+    uint32_t* sm = (uint32_t*)ctx.smem;
+    DR_STRIDE_LOOP(e, n, ctx) { sm_store(sm, n, e, loader(bit_reverse(e, logn))); }
+    DR_BLOCK_SYNC();
+    for (uint32_t s = 1; s <= logn; s++) {
+        uint32_t half = 1u << (s - 1);
+        DR_STRIDE_LOOP(b, n >> 1, ctx) {
+            uint32_t j = b & (half - 1);
+            uint32_t i = ((b >> (s - 1)) << s) + j;
+            Fr u = sm_load(sm, n, i);
+            Fr v = sm_load(sm, n, i + half);
+            if (j) v = v * tw[j << (logn - s)];
+            sm_store(sm, n, i, u + v);
+            sm_store(sm, n, i + half, u - v);
+        }
+        DR_BLOCK_SYNC();
+    }
+    DR_STRIDE_LOOP(e, n, ctx) { storer(e, sm_load(sm, n, e)); }
+}
+
+inline size_t ntt_smem_bytes(uint32_t n) { return (size_t)n * 32; }
+
+// ---- plain batched transform (C ABI dr_fr_ntt; ring-root fixed columns) -------------------------
+struct NttPlainBody {
+    // grid.x = transform index.  scale may be null.  in/out may alias.
+    DR_HD void operator()(const BlockCtx& ctx, const Fr* in, Fr* out, uint32_t n, uint32_t logn, const Fr* tw, const Fr* scale) const {
+        const Fr* src = in + (size_t)ctx.bx * n;
+        Fr* dst = out + (size_t)ctx.bx * n;
+        bool has_scale = scale != nullptr;
+        Fr sc = has_scale ? *scale : Fr::one();
+        ntt_block(
+            ctx, n, logn, tw, [&](uint32_t k) { return src[k]; },
+            [&](uint32_t k, const Fr& v) { dst[k] = has_scale ? v * sc : v; });
+    }
+};
+
+// canonical little-endian bytes <-> Montgomery limbs, elementwise
+struct FrToMontBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* in, Fr* out, size_t count, uint32_t* bad_flag) const {
+        DR_THREAD_LOOP(t, ctx) {
+            size_t i = (size_t)ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                Fr r;
+                fr_from_le_bytes_raw(r, in + 32 * i);
+                if (!r.is_canonical_raw()) {
+                    // reduce once or more: value < 2^256 < 3r
+                    if (bad_flag) *bad_flag = 1;
+                    while (!r.is_canonical_raw()) Fr::sub_mod_inplace(r.v);
+                }
+                out[i] = r.to_mont();
+            }
+        }
+    }
+};
+struct FrFromMontBody {
+    DR_HD void operator()(const BlockCtx& ctx, const Fr* in, uint8_t* out, size_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            size_t i = (size_t)ctx.bx * ctx.nthreads + t;
+            if (i < count) fr_to_le_bytes_raw(out + 32 * i, in[i].from_mont());
+        }
+    }
+};
+
+}  // namespace dr

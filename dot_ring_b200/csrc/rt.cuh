@@ -1,0 +1,188 @@
+// Minimal runtime layer: device memory, streams and kernel launch.
+//
+// Every kernel in this library is written as a functor whose operator() takes a BlockCtx and runs
+// "phases": DR_STRIDE_LOOP / DR_THREAD_LOOP bodies separated by DR_BLOCK_SYNC(), with all
+// cross-thread state in shared memory.  Compiled by nvcc (the product) a phase loop is the usual
+// threadIdx-strided loop and the sync is __syncthreads().  Compiled by g++ with
+// -DDR_HOST_EMULATION (tests/host only, never loaded by the dot_ring_b200 package) the same bodies
+// run block after block, thread after thread, on the CPU, which lets the CPU test-suite exercise
+// the exact kernel logic (indexing, phase structure, transcripts) without a GPU.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dot_ring_b200.h"
+#include "fp.cuh"
+
+#if !defined(DR_HOST_EMULATION)
+#include <cuda_runtime.h>
+#endif
+
+namespace dr {
+
+struct BlockCtx {
+    uint32_t bx, by, bz;
+    uint32_t gx, gy, gz;
+    uint32_t nthreads;
+    uint8_t* smem;
+};
+
+#if defined(__CUDA_ARCH__)
+#define DR_THREAD_LOOP(t, ctx) for (uint32_t t = threadIdx.x, _dr_once = 1; _dr_once; _dr_once = 0)
+#define DR_STRIDE_LOOP(i, n, ctx) for (uint32_t i = threadIdx.x; i < (uint32_t)(n); i += blockDim.x)
+#define DR_BLOCK_SYNC() __syncthreads()
+#else
+#define DR_THREAD_LOOP(t, ctx) for (uint32_t t = 0; t < (ctx).nthreads; t++)
+#define DR_STRIDE_LOOP(i, n, ctx) for (uint32_t i = 0; i < (uint32_t)(n); i++)
+#define DR_BLOCK_SYNC() ((void)0)
+#endif
+
+struct Dim3 {
+    uint32_t x, y, z;
+    Dim3(uint32_t x_ = 1, uint32_t y_ = 1, uint32_t z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#if !defined(DR_HOST_EMULATION)
+// ------------------------------------------------------------------ CUDA build
+typedef cudaStream_t Stream;
+
+inline void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw Error(DR_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define DR_CUDA(x) ::dr::cuda_check((x), #x)
+
+template <class Body, class... Args>
+__global__ void kernel_entry(Body body, Args... args) {
+    extern __shared__ __align__(16) uint8_t dr_smem[];
+    BlockCtx ctx{blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, gridDim.z, blockDim.x, dr_smem};
+    body(ctx, args...);
+}
+
+// launch counter (bench.py reports it as gpu_launches)
+inline uint64_t& launch_counter() {
+    static uint64_t c = 0;
+    return c;
+}
+
+template <class Body, class... Args>
+inline void launch(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+    auto kern = kernel_entry<Body, Args...>;
+    if (smem > 48 * 1024) DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(grid.x, grid.y, grid.z), threads, smem, s>>>(body, args...);
+    DR_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+inline void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) throw Error(DR_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return p;
+}
+inline void dev_free(void* p) {
+    if (p) cudaFree(p);
+}
+inline void h2d(Stream s, void* dst, const void* src, size_t bytes) {
+    if (bytes) DR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+}
+inline void d2h(Stream s, void* dst, const void* src, size_t bytes) {
+    if (bytes) DR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+}
+inline void d2d(Stream s, void* dst, const void* src, size_t bytes) {
+    if (bytes) DR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+}
+inline void dev_zero(Stream s, void* dst, size_t bytes) {
+    if (bytes) DR_CUDA(cudaMemsetAsync(dst, 0, bytes, s));
+}
+inline void stream_sync(Stream s) { DR_CUDA(cudaStreamSynchronize(s)); }
+inline void* host_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    DR_CUDA(cudaMallocHost(&p, bytes ? bytes : 16));
+    return p;
+}
+inline void host_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+#else
+// ------------------------------------------------------------------ host emulation (tests only)
+typedef int Stream;
+inline uint64_t& launch_counter() {
+    static uint64_t c = 0;
+    return c;
+}
+template <class Body, class... Args>
+inline void launch(Stream, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
+    std::vector<uint8_t> sm(smem + 16);
+    for (uint32_t z = 0; z < grid.z; z++)
+        for (uint32_t y = 0; y < grid.y; y++)
+            for (uint32_t x = 0; x < grid.x; x++) {
+                BlockCtx ctx{x, y, z, grid.x, grid.y, grid.z, threads, sm.data()};
+                body(ctx, args...);
+            }
+    launch_counter()++;
+}
+inline void* dev_alloc(size_t bytes) {
+    void* p = calloc(bytes ? bytes : 16, 1);
+    if (!p) throw Error(DR_ENOMEM, "calloc failed");
+    return p;
+}
+inline void dev_free(void* p) { free(p); }
+inline void h2d(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+inline void d2h(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+inline void d2d(Stream, void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); }
+inline void dev_zero(Stream, void* dst, size_t bytes) { memset(dst, 0, bytes); }
+inline void stream_sync(Stream) {}
+inline void* host_alloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 16); }
+inline void host_free_pinned(void* p) { free(p); }
+#endif
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        p = (T*)dev_alloc(count * sizeof(T));
+        n = count;
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+    void release() {
+        dev_free(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace dr

@@ -97,7 +97,7 @@ DR_HD bool te_on_curve(const TEAffine& a) {
 }
 
 // k * P for a raw little-endian scalar of `nlimbs` limbs (no reduction), fixed 4-bit windows.
-DR_HD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
+DR_HD_COLD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
     TEExt tab[16];
     tab[0] = TEExt::identity();
     tab[1] = TEExt::from_affine(p);
@@ -120,7 +120,7 @@ DR_HD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
 }
 
 // sum_i k_i * P_i with shared doublings (Straus), n <= 3, raw 8-limb scalars (< subgroup order).
-DR_HD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int n) {
+DR_HD_COLD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int n) {
     TEExt tab[3][16];
     for (int j = 0; j < n; j++) {
         tab[j][0] = TEExt::identity();
@@ -154,7 +154,7 @@ DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
 // ---- square roots in Fr (2-adicity 32) ---------------------------------------------------------
 // Returns false when `a` is a non-residue.  Which of the two roots comes back is unspecified; every
 // caller normalises the sign (x-recover orders the candidates, Elligator fixes the parity).
-DR_HD bool fr_sqrt(Fr& out, const Fr& a) {
+DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
     if (a.is_zero()) {
         out = a;
         return true;
@@ -191,7 +191,7 @@ DR_HD bool fr_sqrt(Fr& out, const Fr& a) {
     return true;
 }
 
-DR_HD bool fr_is_square(const Fr& a) {
+DR_HD_COLD bool fr_is_square(const Fr& a) {
     if (a.is_zero()) return true;
     constexpr uint32_t e_c[8] = DR_FR_PM1_HALF;
     uint32_t e[8];
@@ -215,7 +215,7 @@ DR_HD void te_encode(uint8_t* out32, const TEAffine& p) {
 }
 
 // Decode without the subgroup check.  false <=> ValueError("Invalid point encoding").
-DR_HD bool te_decode(TEAffine& out, const uint8_t* in32) {
+DR_HD_COLD bool te_decode(TEAffine& out, const uint8_t* in32) {
     uint8_t buf[32];
     for (int i = 0; i < 32; i++) buf[i] = in32[i];
     bool sign = (buf[31] >> 7) != 0;
@@ -253,7 +253,7 @@ DR_HD Fr fr_const(const uint32_t (&c)[8]) {
 }
 
 // u (Montgomery) -> twisted Edwards affine point
-DR_HD TEAffine te_map_to_curve_ell2(const Fr& u) {
+DR_HD_COLD TEAffine te_map_to_curve_ell2(const Fr& u) {
     constexpr uint32_t aob_c[8] = DR_ELL2_A_OVER_B;
     constexpr uint32_t ib2_c[8] = DR_ELL2_INV_B2;
     constexpr uint32_t b_c[8] = DR_ELL2_B;

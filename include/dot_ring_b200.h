@@ -1,0 +1,100 @@
+/* dot_ring_b200 -- C ABI of the B200-native ring-proof engine.
+ *
+ * This is the drop-in boundary for the hot path of Chainscore/dot-ring.  The
+ * reference has no FFI of its own for this path: it crosses from Python into Cython
+ * (dot_ring/ring_proof/polynomial/ntt.pyx, dot_ring/curve/native_field/bandersnatch_te.pyx) and into
+ * the SWIG bindings of blst (dot_ring/ring_proof/pcs/kzg.py).  Each entry point below names the
+ * reference interface it replaces (file:line in the reference tree).  INTEGRATION.md shows the ctypes
+ * stubs a dot-ring maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every byte buffer; handles own device memory.
+ *   - encodings are the reference's wire encodings: Fr 32-byte little-endian canonical; G1 96-byte
+ *     uncompressed / 48-byte compressed zcash big-endian; Bandersnatch points 32 bytes
+ *     (y little-endian, x-sign in bit 7 of the last byte).
+ *   - return value 0 on success, negative error code otherwise; dr_last_error() gives the message
+ *     (thread-local).  DR_EINVAL corresponds to the reference raising ValueError.  A cryptographically
+ *     invalid proof is a verdict (0/1 in an output array), never an error.
+ *   - one dr_ctx per GPU; calls on one ctx are serialised by the caller; calls are synchronous at the
+ *     ABI and asynchronous inside (one CUDA stream per ctx).
+ */
+#ifndef DOT_RING_B200_H
+#define DOT_RING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_OK 0
+#define DR_EINVAL (-1) /* malformed encoding / bad argument (reference: ValueError) */
+#define DR_ECUDA (-2)  /* CUDA runtime failure */
+#define DR_ENOMEM (-3)
+#define DR_ESTATE (-4) /* handle used in the wrong state */
+
+typedef struct dr_ctx dr_ctx;
+typedef struct dr_srs dr_srs;
+typedef struct dr_ring dr_ring;
+
+const char* dr_last_error(void);
+const char* dr_version(void);
+/* 1 when built for the GPU (nvcc, sm_100a); 0 for the CPU emulation build used only by tests/host. */
+int dr_is_cuda_build(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int dr_ctx_create(int device, dr_ctx** out);
+void dr_ctx_destroy(dr_ctx* ctx);
+int dr_ctx_sync(dr_ctx* ctx);
+/* Device-side timing with CUDA events on the ctx stream (bench.py): start, then stop -> ms. */
+int dr_ctx_timer_start(dr_ctx* ctx);
+int dr_ctx_timer_stop(dr_ctx* ctx, float* ms_out);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+uint64_t dr_launch_count(void);
+/* Device properties for reports: name into buf, returns SM count (0 in emulation). */
+int dr_ctx_device_info(dr_ctx* ctx, char* name_buf, size_t name_len, int* sm_count, int* sm_clock_khz, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- SRS + KZG commit ------------------------------------------------------------------------
+ * Replaces dot_ring/ring_proof/pcs/srs.py:98-148 (SRS, `blst.P1_Affines.as_memory`) and
+ * dot_ring/ring_proof/pcs/kzg.py:152-175 (`KZG.commit` -> `blst.P1_Affines.mult_pippenger`).
+ * g1_be96: n_g1 uncompressed points [tau^i]_1; g2_be192: [1]_2 and [tau]_2 (srs.py:57-88 layout).
+ * window_bits selects the fixed-base table (0 = default 12; table bytes = n_g1*ceil(256/c)*2^(c-1)*96).
+ */
+int dr_srs_load(dr_ctx* ctx, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g2_be192, int window_bits, dr_srs** out);
+void dr_srs_destroy(dr_srs* srs);
+size_t dr_srs_size(const dr_srs* srs);
+size_t dr_srs_table_bytes(const dr_srs* srs);
+/* `batch` polynomials of n coefficients each (coefficient j of polynomial b at coeffs_le32 + 32*(b*n+j));
+ * values >= r are reduced (kzg.py passes unreduced quotient coefficients, ops.py:215-220); all-zero ->
+ * infinity (kzg.py:167-168).  Output: batch x 96-byte uncompressed commitments. */
+int dr_kzg_commit(dr_ctx* ctx, dr_srs* srs, const uint8_t* coeffs_le32, size_t n, size_t batch, uint8_t* out_be96);
+/* Same with operands already resident on the device (Montgomery limbs); used for roofline timing. */
+int dr_kzg_commit_bench(dr_ctx* ctx, dr_srs* srs, size_t n, size_t batch, int iters, uint64_t seed, float* ms_per_iter, uint8_t* out_first_be96);
+
+/* ---- G1 codecs -------------------------------------------------------------------------------
+ * Replaces kzg.py:121-144 (`compress_g1`, `serialize_g1_uncompressed`, `decompress_g1`).
+ * ok[i] = 0 marks a malformed encoding (reference: ValueError("invalid BLS12-381 G1 encoding")). */
+int dr_g1_compress(dr_ctx* ctx, const uint8_t* in_be96, size_t count, uint8_t* out_be48);
+int dr_g1_decompress(dr_ctx* ctx, const uint8_t* in_be48, size_t count, uint8_t* out_be96, uint8_t* ok);
+
+/* ---- Fr NTT ------------------------------------------------------------------------------------
+ * Replaces `BlsScalarNTTPlan.transform/transform_scaled` (ring_proof/polynomial/ntt.pyx:104-163) behind
+ * `inverse_fft` / `evaluate_poly_fft` (ring_proof/polynomial/fft.py:87-144): natural order in and out,
+ * out[k] = scale * sum_j in[j] * omega^(j*k).  inverse != 0 uses omega^-1 and scale 1/n.
+ * data_le32: batch x n elements, transformed in place.  n is a power of two, 2 <= n <= 4096. */
+int dr_fr_ntt(dr_ctx* ctx, uint8_t* data_le32, size_t n, size_t batch, int inverse, const uint8_t omega_le32[32]);
+
+/* ---- arithmetic-layer self test + integer-pipe ceilings ----------------------------------------
+ * dr_field_op: element-wise Montgomery arithmetic on the device (reference equivalent:
+ * dot_ring/curve/native_field/scalar.pyx:12-165 `Scalar`, tested by tests/test_curve_ops/test_native_field.py).
+ * field: 0 = BLS12-381 Fq (48-byte big-endian), 1 = Fr, 2 = Bandersnatch scalar field (32-byte
+ * little-endian).  op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 sqr(a), 5 neg(a).
+ * dr_microbench: whole-chip ops/s of kind 0 IMAD, 1 IMAD.WIDE, 2 Fq mul, 3 Fr mul, 4 G1 mixed add. */
+int dr_field_op(dr_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count);
+int dr_microbench(dr_ctx* ctx, int kind, int iters, double* ops_per_s, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOT_RING_B200_H */
