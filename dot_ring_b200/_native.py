@@ -75,6 +75,16 @@ class Library:
         L.dr_field_op.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]
         L.dr_microbench.argtypes = [c_void_p, c_int, c_int, POINTER(ctypes.c_double), POINTER(c_float)]
 
+        L.dr_ring_create.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(c_void_p)]
+        L.dr_ring_destroy.argtypes = [c_void_p]
+        L.dr_ring_destroy.restype = None
+        L.dr_ring_root.argtypes = [c_void_p, c_void_p]
+        L.dr_ring_fixed_commitments.argtypes = [c_void_p, c_void_p]
+        L.dr_ring_points.argtypes = [c_void_p, c_void_p, c_size_t]
+        L.dr_ring_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 10
+        L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
+        L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
+
     def check(self, code: int) -> None:
         if code == DR_OK:
             return
@@ -241,3 +251,121 @@ class NativeSrs:
         lib = self.ctx.library
         lib.check(lib.lib.dr_kzg_commit_bench(self.ctx.handle, self.handle, n, batch, iters, seed, ctypes.byref(ms), first))
         return float(ms.value), first.raw
+
+
+class RingParamsStruct(ctypes.Structure):
+    """dr_ring_params (include/dot_ring_b200.h)."""
+
+    _fields_ = [
+        ("domain_size", ctypes.c_uint32),
+        ("max_ring_size", ctypes.c_uint32),
+        ("padding_rows", ctypes.c_uint32),
+        ("suite_id_len", ctypes.c_uint32),
+        ("h2c_dst_len", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
+        ("omega", c_uint8 * 32),
+        ("radix_omega", c_uint8 * 32),
+        ("seed", c_uint8 * 64),
+        ("blinding_base", c_uint8 * 64),
+        ("padding_point", c_uint8 * 64),
+        ("generator", c_uint8 * 64),
+        ("suite_id", c_uint8 * 32),
+        ("h2c_dst", c_uint8 * 64),
+    ]
+
+
+def _fill(arr, data: bytes) -> None:
+    for i, b in enumerate(data):
+        arr[i] = b
+
+
+def _xy(pt) -> bytes:
+    return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
+
+
+class NativeRing:
+    """dr_ring: decoded keys, fixed columns (coefficients + 4x LDE), ring root, transcript prefix."""
+
+    def __init__(self, srs: NativeSrs, keys: list[bytes], *, domain_size: int, max_ring_size: int, padding_rows: int, omega: int, radix_omega: int,
+                 seed, blinding_base, padding_point, generator, suite_id: bytes, h2c_dst: bytes):
+        self.srs = srs
+        self.ctx = srs.ctx
+        p = RingParamsStruct()
+        p.domain_size, p.max_ring_size, p.padding_rows = domain_size, max_ring_size, padding_rows
+        p.suite_id_len, p.h2c_dst_len = len(suite_id), len(h2c_dst)
+        _fill(p.omega, int(omega).to_bytes(32, "little"))
+        _fill(p.radix_omega, int(radix_omega).to_bytes(32, "little"))
+        _fill(p.seed, _xy(seed))
+        _fill(p.blinding_base, _xy(blinding_base))
+        _fill(p.padding_point, _xy(padding_point))
+        _fill(p.generator, _xy(generator))
+        _fill(p.suite_id, suite_id)
+        _fill(p.h2c_dst, h2c_dst)
+        for key in keys:
+            if len(key) != 32:
+                raise ValueError("ring keys must be 32 bytes")
+        self.handle = c_void_p()
+        self.domain_size = domain_size
+        lib = self.ctx.library
+        lib.check(lib.lib.dr_ring_create(self.ctx.handle, srs.handle, ctypes.byref(p), b"".join(keys), len(keys), ctypes.byref(self.handle)))
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.library.lib.dr_ring_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def root(self) -> bytes:
+        out = ctypes.create_string_buffer(144)
+        self.ctx.library.check(self.ctx.library.lib.dr_ring_root(self.handle, out))
+        return out.raw
+
+    def fixed_commitments(self) -> bytes:
+        out = ctypes.create_string_buffer(288)
+        self.ctx.library.check(self.ctx.library.lib.dr_ring_fixed_commitments(self.handle, out))
+        return out.raw
+
+    def points(self) -> list[tuple[int, int]]:
+        n = self.domain_size
+        out = ctypes.create_string_buffer(64 * n)
+        self.ctx.library.check(self.ctx.library.lib.dr_ring_points(self.handle, out, n))
+        raw = out.raw
+        return [(int.from_bytes(raw[64 * i : 64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32 : 64 * i + 64], "little")) for i in range(n)]
+
+    def prove_batch(self, alphas: list[bytes], ads: list[bytes], secret_keys: list[bytes], producer_index: list[int], zk_rows: list[int] | None = None):
+        """-> (list of 784-byte proofs, list of status words)."""
+        n = len(alphas)
+        if not (len(ads) == len(secret_keys) == len(producer_index) == n):
+            raise ValueError("batch inputs must have equal length")
+        blob = bytearray()
+        a_off, a_len, d_off, d_len = [], [], [], []
+        for a, d in zip(alphas, ads):
+            a_off.append(len(blob)); a_len.append(len(a)); blob += a
+            d_off.append(len(blob)); d_len.append(len(d)); blob += d
+        U32 = ctypes.c_uint32 * max(n, 1)
+        proofs = ctypes.create_string_buffer(784 * max(n, 1))
+        status = U32()
+        zk = None
+        if zk_rows is not None:
+            if len(zk_rows) != 12 * n:
+                raise ValueError("zk_rows must hold 12 field elements per proof")
+            zk = b"".join(int(v).to_bytes(32, "little") for v in zk_rows)
+        lib = self.ctx.library
+        lib.check(
+            lib.lib.dr_ring_prove_batch(
+                self.ctx.handle, self.handle, n, bytes(blob) if blob else None, U32(*a_off), U32(*a_len), U32(*d_off), U32(*d_len),
+                b"".join(secret_keys), U32(*producer_index), zk, proofs, status,
+            )
+        )
+        raw = proofs.raw
+        return [raw[784 * i : 784 * i + 784] for i in range(n)], [int(status[i]) for i in range(n)]
+
+    def prove_phase_ms(self) -> list[float]:
+        arr = (c_float * 6)()
+        self.ctx.library.check(self.ctx.library.lib.dr_ring_prove_phase_ms(self.ctx.handle, ctypes.byref(arr)))
+        return [float(x) for x in arr]

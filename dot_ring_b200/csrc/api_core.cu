@@ -39,6 +39,39 @@ const NttPlan& Ctx::plan(uint32_t n, const Fr& omega_mont) {
     return *plans.back();
 }
 
+void PhaseTimer::mark(Ctx* ctx, int phase) {
+    size_t i = phase_of.size();
+    phase_of.push_back(phase);
+#if !defined(DR_HOST_EMULATION)
+    if (events.size() <= i) {
+        cudaEvent_t e;
+        DR_CUDA(cudaEventCreate(&e));
+        events.push_back(e);
+    }
+    DR_CUDA(cudaEventRecord(events[i], ctx->stream));
+#else
+    (void)ctx;
+    if (stamps.size() <= i) stamps.resize(i + 1);
+    stamps[i] = std::chrono::steady_clock::now();
+#endif
+}
+
+void PhaseTimer::collect(Ctx* ctx) {
+    (void)ctx;
+    for (size_t i = 0; i + 1 < phase_of.size(); i++) {
+        int ph = phase_of[i];
+        if (ph < 0 || ph >= NPH) continue;
+        float ms = 0;
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaEventElapsedTime(&ms, events[i], events[i + 1]));
+#else
+        ms = std::chrono::duration<float, std::milli>(stamps[i + 1] - stamps[i]).count();
+#endif
+        total[ph] += ms;
+    }
+    phase_of.clear();
+}
+
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
     if (n == 0 || batch == 0) return;
     if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");

@@ -26,6 +26,26 @@ struct NttPlan {
     DevBuf<Fr> tw_fwd, tw_inv, n_inv;
 };
 
+struct Ctx;
+
+// Accumulates device time per pipeline phase with events recorded between the launches.
+struct PhaseTimer {
+    static constexpr int NPH = 6;
+    float total[NPH] = {0, 0, 0, 0, 0, 0};
+    std::vector<int> phase_of;  // phase that starts at mark i (-1 = end marker)
+#if !defined(DR_HOST_EMULATION)
+    std::vector<cudaEvent_t> events;
+#else
+    std::vector<std::chrono::steady_clock::time_point> stamps;
+#endif
+    void reset() {
+        for (float& t : total) t = 0;
+        phase_of.clear();
+    }
+    void mark(Ctx* ctx, int phase);
+    void collect(Ctx* ctx);
+};
+
 struct Ctx {
     int device = 0;
     Stream stream{};
@@ -36,6 +56,9 @@ struct Ctx {
 #endif
     std::vector<std::unique_ptr<NttPlan>> plans;
     DevBuf<G1> partials;
+    PhaseTimer phases;
+    std::shared_ptr<void> prove_scratch;
+    size_t prove_chunk = 0;
 
     void activate() {
 #if !defined(DR_HOST_EMULATION)
@@ -43,7 +66,10 @@ struct Ctx {
 #endif
     }
     const NttPlan& plan(uint32_t n, const Fr& omega_mont);
-    void release_scratch() { partials.release(); }
+    void release_scratch() {
+        partials.release();
+        prove_scratch.reset();
+    }
 };
 
 struct Srs {

@@ -1,0 +1,382 @@
+// C ABI, part 3: ring set-up (key ingestion, fixed columns, ring root) and batched Ring VRF proving.
+#include "api_internal.cuh"
+#include "ring.cuh"
+
+namespace dr {
+
+struct Ring {
+    Ctx* ctx = nullptr;
+    Srs* srs = nullptr;
+    RingDev dev{};
+    DevBuf<TEAffine> nm;
+    DevBuf<Fr> fixed_coef, fixed_lde, w4, w4inv;
+    DevBuf<Shake128> prefix;
+    G1Affine commitments[3];
+    uint8_t commit_be96[288];
+    uint8_t root144[144];
+    TEAffine padding;
+};
+
+static Fr fr_from_param(const uint8_t* b) {
+    Fr r;
+    fr_from_le_bytes_raw(r, b);
+    if (!r.is_canonical_raw()) throw Error(DR_EINVAL, "field element is not canonical");
+    return r.to_mont();
+}
+static TEAffine te_from_param(const uint8_t* xy) {
+    TEAffine p{fr_from_param(xy), fr_from_param(xy + 32)};
+    if (!te_on_curve(p)) throw Error(DR_EINVAL, "auxiliary point is not on the curve");
+    return p;
+}
+
+struct ProveScratch {
+    size_t cap = 0;
+    uint32_t N = 0;
+    DevBuf<ProofState> st;
+    DevBuf<ProveInput> in;
+    DevBuf<Fr> wit_coef, lde, agg, cagg, quot, aggopen, lin;
+    DevBuf<G1Affine> res;
+    DevBuf<uint8_t> out, zraw;
+    DevBuf<uint32_t> status;
+    void ensure(size_t n, uint32_t N_) {
+        if (n <= cap && N_ == N) return;
+        cap = n;
+        N = N_;
+        size_t q = 3 * (size_t)N + 1;
+        st.alloc(n);
+        in.alloc(n);
+        wit_coef.alloc(n * 4 * N);
+        lde.alloc(n * 16 * N);
+        agg.alloc(n * 4 * N);
+        cagg.alloc(n * 4 * N);
+        quot.alloc(n * q);
+        aggopen.alloc(n * q);
+        lin.alloc(n * N);
+        res.alloc(n * 4);
+        out.alloc(n * 784);
+        zraw.alloc(n * 12 * 32);
+        status.alloc(n);
+    }
+};
+
+static ProveScratch& scratch_for(Ctx* ctx) {
+    if (!ctx->prove_scratch) ctx->prove_scratch = std::shared_ptr<void>(new ProveScratch(), [](void* p) { delete (ProveScratch*)p; });
+    return *(ProveScratch*)ctx->prove_scratch.get();
+}
+
+}  // namespace dr
+
+using namespace dr;
+
+#define DR_API_BEGIN try {
+#define DR_API_END                            \
+    }                                         \
+    catch (const Error& e) {                  \
+        return set_error(e.code, e.what());   \
+    }                                         \
+    catch (const std::exception& e) {         \
+        return set_error(DR_ECUDA, e.what()); \
+    }                                         \
+    return DR_OK;
+
+extern "C" {
+
+int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_t* keys32, size_t n_keys, dr_ring** out) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    Srs* srs = (Srs*)s;
+    if (!ctx || !srs || !prm || !out || (n_keys && !keys32)) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    const uint32_t N = prm->domain_size;
+    if (N < 512 || N > 4096 || (N & (N - 1))) throw Error(DR_EINVAL, "domain_size must be a power of two in [512, 4096]");
+    if (prm->padding_rows != 4) throw Error(DR_EINVAL, "padding_rows must be 4 to match the 3 hidden rows");
+    if (prm->max_ring_size + SCALAR_BITS + 4 > N) throw Error(DR_EINVAL, "max_ring_size exceeds supported size for this domain");
+    if (n_keys > prm->max_ring_size) throw Error(DR_EINVAL, "ring size exceeds max supported size");
+    if (3 * (size_t)N + 1 > srs->n) throw Error(DR_EINVAL, "SRS too small for this domain (needs 3N+1 G1 points)");
+    if (prm->suite_id_len > 32 || prm->h2c_dst_len > 64) throw Error(DR_EINVAL, "suite id / DST too long");
+
+    auto ring = std::make_unique<Ring>();
+    ring->ctx = ctx;
+    ring->srs = srs;
+    RingDev& d = ring->dev;
+    d.N = N;
+    d.logN = 0;
+    while ((1u << d.logN) < N) d.logN++;
+    d.max_ring = prm->max_ring_size;
+    d.last = N - 4;
+    d.omega = fr_from_param(prm->omega);
+    Fr w4 = fr_from_param(prm->radix_omega);
+    // sanity: w4^4 == omega, omega^N == 1, omega^(N/2) != 1
+    if (w4.sqr().sqr() != d.omega) throw Error(DR_EINVAL, "radix_omega^4 != omega");
+    {
+        Fr t = d.omega;
+        for (uint32_t i = 0; i + 1 < d.logN; i++) t = t.sqr();
+        if (t == Fr::one() || t.sqr() != Fr::one()) throw Error(DR_EINVAL, "omega is not a primitive N-th root of unity");
+    }
+    d.seed = te_from_param(prm->seed);
+    d.blinding_base = te_from_param(prm->blinding_base);
+    d.generator = te_from_param(prm->generator);
+    ring->padding = te_from_param(prm->padding_point);
+    d.suite_id_len = prm->suite_id_len;
+    memcpy(d.suite_id, prm->suite_id, 32);
+    d.dst_len = prm->h2c_dst_len;
+    memcpy(d.dst, prm->h2c_dst, 64);
+    d.n_inv = Fr::from_u32(N).inv();
+    d.quarter = Fr::from_u32(4).inv();
+
+    // ---- domain tables (host, portable arithmetic; uploaded once) ----
+    const NttPlan& plan = ctx->plan(N, d.omega);
+    d.tw_fwd = plan.tw_fwd.p;
+    d.tw_inv = plan.tw_inv.p;
+    std::vector<Fr> hw4(4 * N), hw4i(4 * N);
+    {
+        Fr a = Fr::one(), b = Fr::one(), w4i = w4.inv();
+        for (uint32_t k = 0; k < 4 * N; k++) {
+            hw4[k] = a;
+            hw4i[k] = b;
+            a = a * w4;
+            b = b * w4i;
+        }
+        if (a != Fr::one()) throw Error(DR_EINVAL, "radix_omega is not a 4N-th root of unity");
+    }
+    ring->w4.alloc(4 * N);
+    ring->w4inv.alloc(4 * N);
+    h2d(ctx->stream, ring->w4.p, hw4.data(), 4 * N * sizeof(Fr));
+    h2d(ctx->stream, ring->w4inv.p, hw4i.data(), 4 * N * sizeof(Fr));
+    d.w4 = ring->w4.p;
+    d.w4inv = ring->w4inv.p;
+    d.w_last = hw4[4 * (N - 4)];
+    {
+        // (X - w^(N-1))(X - w^(N-2))(X - w^(N-3))
+        Fr r1 = hw4[4 * (N - 1)], r2 = hw4[4 * (N - 2)], r3 = hw4[4 * (N - 3)];
+        d.tail[3] = Fr::one();
+        d.tail[2] = (r1 + r2 + r3).neg();
+        d.tail[1] = r1 * r2 + r1 * r3 + r2 * r3;
+        d.tail[0] = (r1 * r2 * r3).neg();
+    }
+
+    // ---- public vector PK || padding || 2^i B || zeros (members.py:36-53) ----
+    ring->nm.alloc(N);
+    {
+        std::vector<TEAffine> host(N);
+        for (uint32_t i = 0; i < d.max_ring; i++) host[i] = ring->padding;
+        TEExt cur = TEExt::from_affine(d.blinding_base);
+        for (uint32_t i = d.max_ring; i < N - 4; i++) {
+            host[i] = te_to_affine(cur);
+            cur = te_dbl(cur);
+        }
+        for (uint32_t i = N - 4; i < N; i++) host[i] = TEAffine{Fr::zero(), Fr::zero()};
+        h2d(ctx->stream, ring->nm.p, host.data(), N * sizeof(TEAffine));
+        if (n_keys) {
+            DevBuf<uint8_t> kraw(n_keys * 32);
+            h2d(ctx->stream, kraw.p, keys32, n_keys * 32);
+            launch(ctx->stream, Dim3((uint32_t)((n_keys + 63) / 64)), 64, 0, KeyDecodeBody(), (const uint8_t*)kraw.p, (uint32_t)n_keys, ring->padding, ring->nm.p);
+            stream_sync(ctx->stream);
+        }
+    }
+    d.nm = ring->nm.p;
+
+    // ---- fixed columns: evaluations -> coefficients -> commitments ----
+    ring->fixed_coef.alloc(3 * N);
+    launch(ctx->stream, Dim3((N + 127) / 128), 128, 0, FixedColumnsBody(), (const TEAffine*)ring->nm.p, N, d.max_ring, ring->fixed_coef.p);
+    uint32_t ntt_threads = N / 2 < 256 ? N / 2 : 256;
+    launch(ctx->stream, Dim3(3), ntt_threads, ntt_smem_bytes(N), NttPlainBody(), (const Fr*)ring->fixed_coef.p, ring->fixed_coef.p, N, d.logN, (const Fr*)plan.tw_inv.p,
+           (const Fr*)plan.n_inv.p);
+    d.fixed_coef = ring->fixed_coef.p;
+    DevBuf<G1Affine> cm(3);
+    commit_device(ctx, srs, ring->fixed_coef.p, N, N, 3, cm.p);
+    DevBuf<uint8_t> enc96(288), enc48(144);
+    launch(ctx->stream, Dim3(1), 64, 0, G1EncodeBody(), (const G1Affine*)cm.p, 3u, enc96.p, enc48.p);
+    d2h(ctx->stream, ring->commitments, cm.p, 3 * sizeof(G1Affine));
+    d2h(ctx->stream, ring->commit_be96, enc96.p, 288);
+    d2h(ctx->stream, ring->root144, enc48.p, 144);
+
+    // ---- 4x LDE of px, py, s, L_0, L_{N-4} and (x - w^(N-4)) on the 4N domain ----
+    ring->fixed_lde.alloc(6 * 4 * (size_t)N);
+    {
+        DevBuf<Fr> coef5(5 * (size_t)N);
+        d2d(ctx->stream, coef5.p, ring->fixed_coef.p, 3 * N * sizeof(Fr));
+        std::vector<Fr> lag(2 * (size_t)N);
+        Fr cur0 = d.n_inv, curl = d.n_inv;
+        Fr inv_xl = hw4i[4 * (N - 4)];  // w^-(N-4)
+        for (uint32_t k = 0; k < N; k++) {
+            lag[k] = cur0;  // L_0 = (1/N) sum X^k
+            lag[N + k] = curl;
+            curl = curl * inv_xl;
+        }
+        h2d(ctx->stream, coef5.p + 3 * (size_t)N, lag.data(), 2 * N * sizeof(Fr));
+        launch(ctx->stream, Dim3(20), ntt_threads, ntt_smem_bytes(N), PlainLdeBody(), N, d.logN, (const Fr*)plan.tw_fwd.p, (const Fr*)ring->w4.p, (const Fr*)coef5.p,
+               ring->fixed_lde.p);
+        launch(ctx->stream, Dim3((4 * N + 127) / 128), 128, 0, NotLastBody(), N, (const Fr*)ring->w4.p, d.w_last, ring->fixed_lde.p + 5 * 4 * (size_t)N);
+        stream_sync(ctx->stream);
+    }
+    d.fixed_lde = ring->fixed_lde.p;
+
+    // ---- verifier-key transcript prefix (root.py:54-71, phases.py:72-74) ----
+    {
+        Shake128 tr;
+        tr.init();
+        tr.absorb(d.suite_id, d.suite_id_len);
+        tr.absorb_be32(d.suite_id_len);
+        shake_absorb_label(tr, "vk", 2);
+        tr.absorb(srs->g1_0_be96, 96);
+        tr.absorb(srs->g2_be192, 384);
+        tr.absorb(ring->commit_be96, 288);
+        tr.absorb_be32(96 + 384 + 288);
+        ring->prefix.alloc(1);
+        h2d(ctx->stream, ring->prefix.p, &tr, sizeof(Shake128));
+        stream_sync(ctx->stream);
+    }
+    *out = (dr_ring*)ring.release();
+    DR_API_END
+}
+
+void dr_ring_destroy(dr_ring* r) { delete (Ring*)r; }
+
+int dr_ring_root(dr_ring* r, uint8_t root144[144]) {
+    DR_API_BEGIN
+    if (!r || !root144) throw Error(DR_EINVAL, "bad argument");
+    memcpy(root144, ((Ring*)r)->root144, 144);
+    DR_API_END
+}
+
+int dr_ring_fixed_commitments(dr_ring* r, uint8_t out288[288]) {
+    DR_API_BEGIN
+    if (!r || !out288) throw Error(DR_EINVAL, "bad argument");
+    memcpy(out288, ((Ring*)r)->commit_be96, 288);
+    DR_API_END
+}
+
+int dr_ring_points(dr_ring* r, uint8_t* out_xy64, size_t n_points) {
+    DR_API_BEGIN
+    Ring* ring = (Ring*)r;
+    if (!ring || !out_xy64 || n_points > ring->dev.N) throw Error(DR_EINVAL, "bad argument");
+    ring->ctx->activate();
+    std::vector<TEAffine> host(n_points);
+    d2h(ring->ctx->stream, host.data(), ring->nm.p, n_points * sizeof(TEAffine));
+    stream_sync(ring->ctx->stream);
+    for (size_t i = 0; i < n_points; i++) {
+        fr_to_le_bytes_raw(out_xy64 + 64 * i, host[i].x.from_mont());
+        fr_to_le_bytes_raw(out_xy64 + 64 * i + 32, host[i].y.from_mont());
+    }
+    DR_API_END
+}
+
+int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, const uint32_t* alpha_off, const uint32_t* alpha_len, const uint32_t* ad_off,
+                        const uint32_t* ad_len, const uint8_t* secret_keys32, const uint32_t* producer_index, const uint8_t* zk_rows, uint8_t* proofs784,
+                        uint32_t* status) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    Ring* ring = (Ring*)r;
+    if (!ctx || !ring || (n && (!alpha_off || !alpha_len || !ad_off || !ad_len || !secret_keys32 || !producer_index || !proofs784 || !status)))
+        throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    if (!n) return DR_OK;
+    const RingDev& rg = ring->dev;
+    const uint32_t N = rg.N;
+    const uint32_t qlen = 3 * N + 1;
+    size_t blob_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t e1 = (size_t)alpha_off[i] + alpha_len[i], e2 = (size_t)ad_off[i] + ad_len[i];
+        if (e1 > blob_len) blob_len = e1;
+        if (e2 > blob_len) blob_len = e2;
+    }
+    if (blob_len && !blob) throw Error(DR_EINVAL, "null blob");
+    DevBuf<uint8_t> dblob(blob_len ? blob_len : 1);
+    h2d(ctx->stream, dblob.p, blob, blob_len);
+
+    const size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 1024;
+    ProveScratch& sc = scratch_for(ctx);
+    sc.ensure(n < chunk_cap ? n : chunk_cap, N);
+    PhaseTimer& pt = ctx->phases;
+    pt.reset();
+    const uint32_t ntt_threads = N / 2 < 256 ? N / 2 : 256;
+    const size_t ntt_smem = ntt_smem_bytes(N);
+    std::vector<ProveInput> hin;
+
+    for (size_t base = 0; base < n; base += sc.cap) {
+        const uint32_t m = (uint32_t)((n - base < sc.cap) ? n - base : sc.cap);
+        hin.assign(m, ProveInput{});
+        for (uint32_t i = 0; i < m; i++) {
+            ProveInput& pi = hin[i];
+            pi.alpha_off = alpha_off[base + i];
+            pi.alpha_len = alpha_len[base + i];
+            pi.ad_off = ad_off[base + i];
+            pi.ad_len = ad_len[base + i];
+            pi.k = producer_index[base + i];
+            memcpy(pi.sk, secret_keys32 + 32 * (base + i), 32);
+        }
+        h2d(ctx->stream, sc.in.p, hin.data(), m * sizeof(ProveInput));
+        const uint32_t tb = 64, pb = (m + tb - 1) / tb;
+
+        pt.mark(ctx, 0);
+        // zk rows (Montgomery) into the state, then Pedersen + witness
+        if (zk_rows) {
+            h2d(ctx->stream, sc.zraw.p, zk_rows + (size_t)base * 12 * 32, (size_t)m * 12 * 32);
+            launch(ctx->stream, Dim3((m * 12 + 127) / 128), 128, 0, ZkRowsBody(), (const uint8_t*)sc.zraw.p, sc.st.p, m);
+        } else {
+            launch(ctx->stream, Dim3((m * 12 + 127) / 128), 128, 0, ZkRowsBody(), (const uint8_t*)nullptr, sc.st.p, m);
+        }
+        launch(ctx->stream, Dim3(pb), tb, 0, PedersenProveBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
+        launch(ctx->stream, Dim3(pb), tb, 0, WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
+        pt.mark(ctx, 1);
+        launch(ctx->stream, Dim3(4, m), ntt_threads, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+        pt.mark(ctx, 2);
+        commit_device(ctx, ring->srs, sc.wit_coef.p, N, N, 4 * m, sc.res.p);
+        // column order (b, accx, accy, accip) -> payload slots (0, 2, 3, 1)
+        launch(ctx->stream, Dim3((4 * m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 4u, 0x01030200u, sc.st.p, m);
+        pt.mark(ctx, 5);
+        launch(ctx->stream, Dim3(pb), tb, 0, Transcript1Body(), sc.st.p, m);
+        pt.mark(ctx, 3);
+        launch(ctx->stream, Dim3(16, m), ntt_threads, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
+        launch(ctx->stream, Dim3((4 * N + 127) / 128, m), 128, 0, ConstraintBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.lde.p, sc.agg.p);
+        launch(ctx->stream, Dim3(4, m), ntt_threads, ntt_smem, QuotientInttBody(), rg, sc.agg.p);
+        launch(ctx->stream, Dim3((N + 127) / 128, m), 128, 0, QuotientCombineBody(), rg, (const Fr*)sc.agg.p, sc.cagg.p);
+        launch(ctx->stream, Dim3((qlen + 127) / 128, m), 128, 0, QuotientFoldBody(), rg, (const Fr*)sc.cagg.p, sc.quot.p, qlen);
+        pt.mark(ctx, 2);
+        commit_device(ctx, ring->srs, sc.quot.p, qlen, qlen, m, sc.res.p);
+        launch(ctx->stream, Dim3((m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 1u, 0x04u, sc.st.p, m);
+        pt.mark(ctx, 5);
+        launch(ctx->stream, Dim3(pb), tb, 0, Transcript2Body(), sc.st.p, m);
+        pt.mark(ctx, 4);
+        launch(ctx->stream, Dim3(7, m), 128, 128 * sizeof(Fr), EvalBody(), rg, sc.st.p, (const Fr*)sc.wit_coef.p);
+        launch(ctx->stream, Dim3((N + 127) / 128, m), 128, 0, LinPolyBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.wit_coef.p, sc.lin.p);
+        launch(ctx->stream, Dim3(1, m), 128, 128 * sizeof(Fr), LinEvalBody(), rg, sc.st.p, (const Fr*)sc.lin.p);
+        pt.mark(ctx, 5);
+        launch(ctx->stream, Dim3(pb), tb, 0, Transcript3Body(), sc.st.p, m);
+        pt.mark(ctx, 4);
+        launch(ctx->stream, Dim3((qlen + 127) / 128, m), 128, 0, AggOpenBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.wit_coef.p, (const Fr*)sc.quot.p, qlen, sc.aggopen.p);
+        launch(ctx->stream, Dim3(2, m), 256, 257 * sizeof(Fr), OpenQuotientsBody(), rg, (const ProofState*)sc.st.p, sc.aggopen.p, qlen, sc.lin.p);
+        pt.mark(ctx, 2);
+        commit_device(ctx, ring->srs, sc.aggopen.p, qlen, 3 * N, m, sc.res.p);
+        launch(ctx->stream, Dim3((m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 1u, 0x05u, sc.st.p, m);
+        commit_device(ctx, ring->srs, sc.lin.p, N, N - 1, m, sc.res.p);
+        launch(ctx->stream, Dim3((m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 1u, 0x06u, sc.st.p, m);
+        pt.mark(ctx, 5);
+        launch(ctx->stream, Dim3(pb), tb, 0, FinalizeBody(), (const ProofState*)sc.st.p, m, sc.out.p, sc.status.p);
+        pt.mark(ctx, -1);
+        d2h(ctx->stream, proofs784 + 784 * base, sc.out.p, (size_t)m * 784);
+        d2h(ctx->stream, status + base, sc.status.p, (size_t)m * sizeof(uint32_t));
+        stream_sync(ctx->stream);
+        pt.collect(ctx);
+    }
+    DR_API_END
+}
+
+int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !out) throw Error(DR_EINVAL, "bad argument");
+    for (int i = 0; i < 6; i++) out[i] = ctx->phases.total[i];
+    DR_API_END
+}
+
+int dr_ctx_set_prove_chunk(dr_ctx* c, size_t chunk) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx) throw Error(DR_EINVAL, "bad argument");
+    ctx->prove_chunk = chunk;
+    DR_API_END
+}
+
+}  // extern "C"

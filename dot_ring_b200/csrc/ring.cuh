@@ -1,0 +1,832 @@
+// Ring-proof prover kernels (batched over proofs).
+//
+// Device restatement of the reference prover pipeline:
+//   dot_ring/ring_proof/columns/columns.py:111-167       witness columns b / acc_x / acc_y / acc_ip
+//   dot_ring/ring_proof/constraints/constraints.py:43-151 4x LDE + constraints c1..c7
+//   dot_ring/ring_proof/proof_builder.py:38-315           aggregation, quotient, linearisation, openings
+//   dot_ring/ring_proof/polynomial/ops.py:170-224         Horner, divide by X^N - 1
+//   dot_ring/ring_proof/pcs/utils.py:27-35                synthetic division
+//   dot_ring/ring_proof/transcript/{transcript,phases}.py Fiat-Shamir (SHAKE128)
+//   dot_ring/vrf/pedersen/vrf.py:86-126                   Pedersen VRF prove (SHA-512 transcripts)
+// One proof is one row of every buffer; the 4N ("radix") domain is handled as four cosets of the
+// N-domain (point 4i+j = w4^j * w^i is stored at [j*N + i]) so every transform is an N-point NTT
+// that fits one CTA's shared memory, and the shifted row access i+4 (mod 4N) of the constraints
+// becomes i+1 (mod N) inside a coset.
+#pragma once
+#include "g1.cuh"
+#include "hash.cuh"
+#include "ntt.cuh"
+#include "rt.cuh"
+#include "te.cuh"
+
+namespace dr {
+
+constexpr uint32_t SCALAR_BITS = 253;
+
+// Per-ring constants and device tables, passed to kernels by value.
+struct RingDev {
+    uint32_t N, logN, max_ring, last;  // last = N - 4 (last accumulator row)
+    const TEAffine* nm;                // [N]   PK || padding || 2^i B || 4 x (0,0)
+    const Fr* fixed_coef;              // [3][N]   px, py, s  coefficients
+    const Fr* fixed_lde;               // [6][4N]  px, py, s, L_0, L_last, (x - w^last): coset layout
+    const Fr* tw_fwd;                  // [N/2] w^k
+    const Fr* tw_inv;                  // [N/2] w^-k
+    const Fr* w4;                      // [4N]  w4^k
+    const Fr* w4inv;                   // [4N]  w4^-k
+    Fr n_inv;                          // 1/N
+    Fr quarter;                        // 1/4
+    Fr omega;                          // w
+    Fr w_last;                         // w^(N-4)
+    Fr tail[4];                        // coefficients of (X - w^(N-1))(X - w^(N-2))(X - w^(N-3))
+    TEAffine seed, blinding_base, generator;
+    uint32_t suite_id_len;
+    uint8_t suite_id[32];
+    uint32_t dst_len;
+    uint8_t dst[64];  // hash-to-curve DST (without the trailing length byte)
+};
+
+// Per-proof state (one element of an array in HBM).
+struct ProofState {
+    uint32_t k;         // producer index
+    uint32_t status;    // 0 ok; 1 = producer key does not match secret key / ring row
+    uint32_t t[8];      // Pedersen blinding factor, raw limbs
+    Fr zk[12];          // blinding rows: b, accx, accy, accip (3 each), Montgomery
+    TEAffine a0;        // seed + PK_k
+    TEAffine s[SCALAR_BITS];  // accumulator after bit row j
+    TEAffine relation;  // PK_k + t*B  (== Pedersen blinded key)
+    Shake128 tr;        // ring transcript
+    Fr alpha[7], zeta, nu[8];
+    Fr evals[7];        // px, py, s, b, accip, accx, accy at zeta
+    Fr lzw;             // L(zeta * w)
+    G1Affine commits[7];  // C_b, C_accip, C_accx, C_accy, C_q, Phi_zeta, Phi_zeta_w
+    uint8_t pedersen[192];
+};
+
+struct ProveInput {  // host-packed per proof
+    uint32_t alpha_off, alpha_len, ad_off, ad_len;
+    uint32_t k;
+    uint32_t pad;
+    uint8_t sk[32];
+};
+
+// column index convention inside the prover buffers
+enum { COL_B = 0, COL_ACCX = 1, COL_ACCY = 2, COL_ACCIP = 3 };
+
+// ---- small helpers ---------------------------------------------------------------------------------
+DR_HD void shake_absorb_label(Shake128& s, const char* label, uint32_t len) {
+    s.absorb((const uint8_t*)label, len);
+    s.absorb_be32(len);
+}
+DR_HD void shake_absorb_labeled_begin(Shake128& s, const char* label, uint32_t len) { shake_absorb_label(s, label, len); }
+// challenge squeeze: 48 bytes big-endian mod r -> Montgomery Fr
+DR_HD Fr shake_challenge_value(const Shake128& s) {
+    uint8_t out[48];
+    s.squeeze_snapshot(out, 48);
+    return fr_from_be48_mod(out);
+}
+// transcript.py:109-136: prefix = label | be32(len) | "challenge"; after each squeeze absorb footer 00 00 00 09
+DR_HD void shake_challenges(Shake128& s, const char* label, uint32_t len, Fr* out, int n) {
+    for (int i = 0; i < n; i++) {
+        shake_absorb_label(s, label, len);
+        s.absorb((const uint8_t*)"challenge", 9);
+        out[i] = shake_challenge_value(s);
+        s.absorb_be32(9);
+    }
+}
+DR_HD void shake_absorb_fr(Shake128& s, const Fr& x_mont) {
+    uint8_t b[32];
+    fr_to_le_bytes_raw(b, x_mont.from_mont());
+    s.absorb(b, 32);
+}
+DR_HD void shake_absorb_g1(Shake128& s, const G1Affine& p) {
+    uint8_t b[96];
+    g1_serialize(b, p);
+    s.absorb(b, 96);
+}
+
+// SHA-512 counter-mode squeeze of the VRF transcript (primitives.py:165-174): seed = H(absorbed),
+// block c = H(seed | le64(c)).  `st` already holds the absorbed bytes.
+DR_HD void vrf_squeeze(const Sha512& st, uint8_t* out, uint32_t size) {
+    Sha512 h = st;
+    uint8_t seed[64];
+    h.final(seed);
+    uint32_t done = 0;
+    for (uint64_t c = 0; done < size; c++) {
+        Sha512 b;
+        b.init();
+        b.update(seed, 64);
+        uint8_t ctr[8];
+        for (int i = 0; i < 8; i++) ctr[i] = (uint8_t)(c >> (8 * i));
+        b.update(ctr, 8);
+        uint8_t blk[64];
+        b.final(blk);
+        for (uint32_t i = 0; i < 64 && done < size; i++) out[done++] = blk[i];
+    }
+}
+DR_HD void fn_to_le_bytes(uint8_t* out, const Fn& x_mont) {
+    Fn x = x_mont.from_mont();
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(x.v[i] >> (8 * b));
+}
+// primitives.py:66-82 `nonce`
+DR_HD Fn vrf_nonce(const Sha512& t, const Fn& secret) {
+    Sha512 te = t;
+    te.update_byte(0x10);
+    uint8_t sb[32];
+    fn_to_le_bytes(sb, secret);
+    te.update(sb, 32);
+    uint8_t secret_hash[64];
+    vrf_squeeze(te, secret_hash, 64);
+    Sha512 tn = t;
+    tn.update_byte(0x11);
+    tn.update(secret_hash, 64);
+    uint8_t wide[48];
+    vrf_squeeze(tn, wide, 48);
+    return fp_from_le_bytes_mod<Fn>(wide, 48);
+}
+DR_HD void fn_raw_limbs(uint32_t* out, const Fn& x_mont) {
+    Fn x = x_mont.from_mont();
+    for (int i = 0; i < 8; i++) out[i] = x.v[i];
+}
+DR_HD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {
+    uint32_t kr[8];
+    fn_raw_limbs(kr, k);
+    return te_to_affine(te_mul_raw(p, kr, 8));
+}
+DR_HD void sha_absorb_point(Sha512& s, const TEAffine& p) {
+    uint8_t b[32];
+    te_encode(b, p);
+    s.update(b, 32);
+}
+
+// expand_message_xmd(SHA-512) for 96 output bytes (curve.py:145-185; Z_pad = 48 bytes for this suite)
+DR_HD void h2c_uniform_bytes(const RingDev& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
+    uint8_t dst_prime_len = (uint8_t)rg.dst_len;
+    Sha512 h;
+    h.init();
+    uint8_t zero[48];
+    for (int i = 0; i < 48; i++) zero[i] = 0;
+    h.update(zero, 48);
+    h.update(msg, msg_len);
+    uint8_t lib[3] = {0, 96, 0};
+    h.update(lib, 3);
+    h.update(rg.dst, rg.dst_len);
+    h.update_byte(dst_prime_len);
+    uint8_t b0[64];
+    h.final(b0);
+    uint8_t prev[64];
+    for (int blk = 1; blk <= 2; blk++) {
+        Sha512 g;
+        g.init();
+        uint8_t x[64];
+        for (int i = 0; i < 64; i++) x[i] = blk == 1 ? b0[i] : (uint8_t)(b0[i] ^ prev[i]);
+        g.update(x, 64);
+        g.update_byte((uint8_t)blk);
+        g.update(rg.dst, rg.dst_len);
+        g.update_byte(dst_prime_len);
+        g.final(prev);
+        for (int i = 0; i < 64 && 64 * (blk - 1) + i < 96; i++) out96[64 * (blk - 1) + i] = prev[i];
+    }
+}
+DR_HD TEAffine vrf_encode_to_curve(const RingDev& rg, const uint8_t* msg, uint32_t msg_len) {
+    uint8_t u[96];
+    h2c_uniform_bytes(rg, msg, msg_len, u);
+    return te_encode_to_curve_from_u(fr_from_be48_mod(u), fr_from_be48_mod(u + 48));
+}
+
+// ---- A. Pedersen VRF prove (pedersen/vrf.py:86-126), one thread per proof -------------------------------
+struct PedersenProveBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProveInput* in, const uint8_t* blob, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                const ProveInput& pi = in[p];
+                ProofState& ps = st[p];
+                Fn x = fp_from_le_bytes_mod<Fn>(pi.sk, 32);
+                TEAffine pk = te_mul_fn(rg.generator, x);
+                TEAffine input = vrf_encode_to_curve(rg, blob + pi.alpha_off, pi.alpha_len);
+                TEAffine output = te_mul_fn(input, x);
+                // vrf_transcript (primitives.py:102-144) with one I/O pair
+                Sha512 tr;
+                tr.init();
+                tr.update(rg.suite_id, rg.suite_id_len);
+                tr.update_byte(0x02);
+                uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+                tr.update(le, 8);
+                sha_absorb_point(tr, input);
+                sha_absorb_point(tr, output);
+                for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(pi.ad_len >> (8 * i)) : 0;
+                tr.update(le, 8);
+                tr.update(blob + pi.ad_off, pi.ad_len);
+                // blinding factor
+                Sha512 tb = tr;
+                tb.update_byte(0x12);
+                Fn b = vrf_nonce(tb, x);
+                TEAffine bb = te_mul_fn(rg.blinding_base, b);
+                TEAffine blinded = te_to_affine(te_add(TEExt::from_affine(pk), TEExt::from_affine(bb)));
+                sha_absorb_point(tr, blinded);
+                Fn k = vrf_nonce(tr, x);
+                Fn kb = vrf_nonce(tr, b);
+                TEAffine kg = te_mul_fn(rg.generator, k);
+                TEAffine kbb = te_mul_fn(rg.blinding_base, kb);
+                TEAffine R = te_to_affine(te_add(TEExt::from_affine(kg), TEExt::from_affine(kbb)));
+                TEAffine ok = te_mul_fn(input, k);
+                Sha512 tc = tr;
+                tc.update_byte(0x40);
+                sha_absorb_point(tc, R);
+                sha_absorb_point(tc, ok);
+                uint8_t cb[16];
+                vrf_squeeze(tc, cb, 16);
+                Fn c = fp_from_le_bytes_mod<Fn>(cb, 16);
+                Fn s = k + c * x;
+                Fn sb = kb + c * b;
+                te_encode(ps.pedersen, output);
+                te_encode(ps.pedersen + 32, blinded);
+                te_encode(ps.pedersen + 64, R);
+                te_encode(ps.pedersen + 96, ok);
+                fn_to_le_bytes(ps.pedersen + 128, s);
+                fn_to_le_bytes(ps.pedersen + 160, sb);
+                fn_raw_limbs(ps.t, b);
+                ps.k = pi.k;
+                ps.relation = blinded;
+                // producer_key must be pk(sk) and sit at row k of the ring (vrf/ring/vrf.py:196-197, members.py:71-81)
+                ps.status = (pi.k < rg.max_ring && rg.nm[pi.k] == pk) ? 0u : 1u;
+            }
+        }
+    }
+};
+
+// ---- B. witness accumulators (columns.py:127-146), one thread per proof -----------------------------------
+// acc_0 = seed; the only rows that change it are row k (adds PK_k) and the 253 bit rows (add 2^j * B when
+// bit j of the blinding factor is set).  The chain is walked in extended coordinates twice around ONE
+// field inversion (Montgomery's trick over the 254 Z coordinates) to obtain the affine values the
+// reference computes with one inversion per addition.
+struct WitnessBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, ProofState* st, uint32_t count, const Shake128* prefix) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                ProofState& ps = st[p];
+                uint32_t k = ps.k < rg.max_ring ? ps.k : 0;
+                const TEExt a0 = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(rg.nm[k]));
+                // walk 1: stash Z_j in s[j].x and the prefix product Z_a0 * prod_{i<j} Z_i in s[j].y
+                TEExt acc = a0;
+                Fr prefix_prod = a0.Z;
+#pragma unroll 1
+                for (uint32_t j = 0; j < SCALAR_BITS; j++) {
+                    if ((ps.t[j >> 5] >> (j & 31)) & 1) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
+                    ps.s[j].x = acc.Z;
+                    ps.s[j].y = prefix_prod;
+                    prefix_prod = prefix_prod * acc.Z;
+                }
+                Fr inv_run = prefix_prod.inv();
+                // backward sweep: s[j].y <- 1 / Z_j
+#pragma unroll 1
+                for (int j = (int)SCALAR_BITS - 1; j >= 0; j--) {
+                    Fr zj = ps.s[j].x;
+                    ps.s[j].y = inv_run * ps.s[j].y;
+                    inv_run = inv_run * zj;
+                }
+                ps.a0 = {a0.X * inv_run, a0.Y * inv_run};  // inv_run == 1 / Z_a0
+                // walk 2: affine accumulator values
+                acc = a0;
+#pragma unroll 1
+                for (uint32_t j = 0; j < SCALAR_BITS; j++) {
+                    if ((ps.t[j >> 5] >> (j & 31)) & 1) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
+                    Fr zi = ps.s[j].y;
+                    ps.s[j] = {acc.X * zi, acc.Y * zi};
+                }
+                // the accumulator must end at seed + relation (proof_builder.py:66-69)
+                TEExt chk = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(ps.relation));
+                if (!te_ext_eq_affine(chk, ps.s[SCALAR_BITS - 1])) ps.status |= 2u;
+                // transcript: copy the ring prefix, absorb the instance (phases.py:18-26)
+                ps.tr = *prefix;
+                shake_absorb_label(ps.tr, "instance", 8);
+                shake_absorb_fr(ps.tr, ps.relation.x);
+                shake_absorb_fr(ps.tr, ps.relation.y);
+                ps.tr.absorb_be32(64);
+            }
+        }
+    }
+};
+
+// Column synthesis (columns.py:111-146 + 43-53): value of witness column `col` at row `row`.
+DR_HD Fr witness_eval(const RingDev& rg, const ProofState& ps, uint32_t col, uint32_t row) {
+    const uint32_t N = rg.N;
+    if (row >= N - 3) return ps.zk[3 * col + (row - (N - 3))];
+    if (col == COL_B) {
+        if (row < rg.max_ring) return row == ps.k ? Fr::one() : Fr::zero();
+        uint32_t j = row - rg.max_ring;
+        if (j < SCALAR_BITS && ((ps.t[j >> 5] >> (j & 31)) & 1)) return Fr::one();
+        return Fr::zero();
+    }
+    if (col == COL_ACCIP) return row > ps.k ? Fr::one() : Fr::zero();
+    const TEAffine* pt;
+    if (row <= ps.k)
+        pt = &rg.seed;
+    else if (row <= rg.max_ring)
+        pt = &ps.a0;
+    else
+        pt = &ps.s[row - rg.max_ring - 1];
+    return col == COL_ACCX ? pt->x : pt->y;
+}
+
+// ---- C. witness interpolation: grid (4 columns, proofs) ------------------------------------------------
+struct WitnessInttBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, Fr* wit_coef) const {
+        const ProofState& ps = st[ctx.by];
+        uint32_t col = ctx.bx;
+        Fr* dst = wit_coef + ((size_t)ctx.by * 4 + col) * rg.N;
+        Fr ninv = rg.n_inv;
+        ntt_block(
+            ctx, rg.N, rg.logN, rg.tw_inv, [&](uint32_t r) { return witness_eval(rg, ps, col, r); }, [&](uint32_t k, const Fr& v) { dst[k] = v * ninv; });
+    }
+};
+
+// ---- E. transcript phase 1: committed columns -> 7 alphas (phases.py:18-26) ------------------------------
+struct Transcript1Body {
+    DR_HD void operator()(const BlockCtx& ctx, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                ProofState& ps = st[p];
+                shake_absorb_label(ps.tr, "committed_cols", 14);
+                for (int i = 0; i < 4; i++) shake_absorb_g1(ps.tr, ps.commits[i]);
+                ps.tr.absorb_be32(4 * 96);
+                shake_challenges(ps.tr, "constraints_aggregation", 23, ps.alpha, 7);
+            }
+        }
+    }
+};
+
+// ---- F. 4x low-degree extension of the witness columns: grid (16 = 4 cosets x 4 columns, proofs) ---------
+struct WitnessLdeBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const Fr* wit_coef, Fr* lde) const {
+        uint32_t col = ctx.bx & 3, j = ctx.bx >> 2;
+        const Fr* src = wit_coef + ((size_t)ctx.by * 4 + col) * rg.N;
+        Fr* dst = lde + (((size_t)ctx.by * 4 + col) * 4 + j) * rg.N;
+        const uint32_t mask = 4 * rg.N - 1;
+        ntt_block(
+            ctx, rg.N, rg.logN, rg.tw_fwd, [&](uint32_t k) { return j ? src[k] * rg.w4[(j * k) & mask] : src[k]; }, [&](uint32_t i, const Fr& v) { dst[i] = v; });
+    }
+};
+
+// Plain coset LDE of `count` coefficient vectors (ring set-up: px, py, s, L_0, L_last): grid (4*count)
+struct PlainLdeBody {
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t N, uint32_t logN, const Fr* tw_fwd, const Fr* w4, const Fr* coef, Fr* lde) const {
+        uint32_t v = ctx.bx >> 2, j = ctx.bx & 3;
+        const Fr* src = coef + (size_t)v * N;
+        Fr* dst = lde + ((size_t)v * 4 + j) * N;
+        const uint32_t mask = 4 * N - 1;
+        ntt_block(
+            ctx, N, logN, tw_fwd, [&](uint32_t k) { return j ? src[k] * w4[(j * k) & mask] : src[k]; }, [&](uint32_t i, const Fr& val) { dst[i] = val; });
+    }
+};
+
+// ---- G. constraints c1..c7 and their alpha-aggregation on the 4N domain (constraints.py:64-151,
+//         proof_builder.py:165-179): grid (ceil(4N / threads), proofs) ----------------------------------------
+struct ConstraintBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, const Fr* lde, Fr* agg) const {
+        const ProofState& ps = st[ctx.by];
+        const uint32_t N = rg.N, N4 = 4 * rg.N;
+        const Fr* w = lde + (size_t)ctx.by * 4 * N4;
+        const Fr *b4 = w + COL_B * N4, *ax4 = w + COL_ACCX * N4, *ay4 = w + COL_ACCY * N4, *aip4 = w + COL_ACCIP * N4;
+        const Fr *px4 = rg.fixed_lde, *py4 = rg.fixed_lde + N4, *s4 = rg.fixed_lde + 2 * N4, *l0 = rg.fixed_lde + 3 * N4, *ln = rg.fixed_lde + 4 * N4,
+                 *nl = rg.fixed_lde + 5 * N4;
+        Fr* out = agg + (size_t)ctx.by * N4;
+        const TEAffine rps = ps.s[SCALAR_BITS - 1];  // result + seed
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < N4) {
+                uint32_t j = p / N, i = p - j * N;
+                uint32_t q = j * N + ((i + 1) & (N - 1));  // row shifted by 4 in the 4N domain
+                Fr one = Fr::one();
+                Fr x1 = ax4[p], y1 = ay4[p], x2 = px4[p], y2 = py4[p], x3 = ax4[q], y3 = ay4[q];
+                Fr bi = b4[p], nli = nl[p], aip = aip4[p];
+                Fr omb = one - bi;
+                Fr x1y1 = x1 * y1, y2x2 = y2 * x2;
+                Fr c1 = (aip4[q] - aip - bi * s4[p]) * nli;
+                Fr xt = x3 * (y1 * y2 - fr_mul5(x1 * x2)) - (x1y1 + y2x2);
+                Fr c2 = (bi * xt + omb * (x3 - x1)) * nli;
+                Fr yt = y3 * (x1 * y2 - x2 * y1) - (x1y1 - y2x2);
+                Fr c3 = (bi * yt + omb * (y3 - y1)) * nli;
+                Fr c4 = bi * omb;
+                Fr l0i = l0[p], lni = ln[p];
+                Fr c5 = (x1 - rg.seed.x) * l0i + (x1 - rps.x) * lni;
+                Fr c6 = (y1 - rg.seed.y) * l0i + (y1 - rps.y) * lni;
+                Fr c7 = aip * l0i + (aip - one) * lni;
+                out[p] = c1 * ps.alpha[0] + c2 * ps.alpha[1] + c3 * ps.alpha[2] + c4 * ps.alpha[3] + c5 * ps.alpha[4] + c6 * ps.alpha[5] + c7 * ps.alpha[6];
+            }
+        }
+    }
+};
+
+// ---- H. inverse transform of the aggregated constraint, coset by coset: grid (4, proofs) ------------------
+// After this kernel agg[j*N + k0] holds  w4^(-j*k0) * (1/N) * sum_i E[4i+j] w^(-i*k0).
+struct QuotientInttBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, Fr* agg) const {
+        uint32_t j = ctx.bx;
+        Fr* buf = agg + ((size_t)ctx.by * 4 + j) * rg.N;
+        const uint32_t mask = 4 * rg.N - 1;
+        Fr ninv = rg.n_inv;
+        ntt_block(
+            ctx, rg.N, rg.logN, rg.tw_inv, [&](uint32_t i) { return buf[i]; },
+            [&](uint32_t k0, const Fr& v) {
+                Fr r = v * ninv;
+                buf[k0] = j ? r * rg.w4inv[(j * k0) & mask] : r;
+            });
+    }
+};
+
+// ---- I. 4-point combine across cosets -> coefficients c[0..4N) of the aggregated polynomial ---------------
+// c[k0 + N*m] = 1/4 * sum_j i4^(-j*m) * D_j[k0],  i4 = w4^N (primitive 4th root of unity).
+struct QuotientCombineBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const Fr* agg, Fr* cagg) const {
+        const uint32_t N = rg.N;
+        const Fr* src = agg + (size_t)ctx.by * 4 * N;
+        Fr* dst = cagg + (size_t)ctx.by * 4 * N;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t k0 = ctx.bx * ctx.nthreads + t;
+            if (k0 < N) {
+                Fr d0 = src[k0], d1 = src[N + k0], d2 = src[2 * N + k0], d3 = src[3 * N + k0];
+                Fr i4inv = rg.w4inv[N];  // i4^-1
+                Fr s02 = d0 + d2, m02 = d0 - d2, s13 = d1 + d3, m13 = (d1 - d3) * i4inv;
+                // m = 0: d0+d1+d2+d3 ; m = 1: d0 + i^-1 d1 - d2 - i^-1 d3 ; m = 2: d0-d1+d2-d3 ; m = 3: d0 - i^-1 d1 - d2 + i^-1 d3
+                dst[k0] = (s02 + s13) * rg.quarter;
+                dst[N + k0] = (m02 + m13) * rg.quarter;
+                dst[2 * N + k0] = (s02 - s13) * rg.quarter;
+                dst[3 * N + k0] = (m02 - m13) * rg.quarter;
+            }
+        }
+    }
+};
+
+// ---- J. multiply by the tail-vanishing cubic and divide by X^N - 1 (proof_builder.py:181-195,
+//         ops.py:207-224): q[j] = sum_{i>=1, iN+j<=4N+3} e[iN+j],  e = c * tail.  grid (ceil((3N+1)/threads), proofs)
+struct QuotientFoldBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const Fr* cagg, Fr* quot, uint32_t qstride) const {
+        const uint32_t N = rg.N, N4 = 4 * rg.N;
+        const Fr* c = cagg + (size_t)ctx.by * N4;
+        Fr* q = quot + (size_t)ctx.by * qstride;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t j = ctx.bx * ctx.nthreads + t;
+            if (j < qstride) {
+                Fr acc = Fr::zero();
+                for (uint32_t idx = N + j; idx < N4 + 4; idx += N) {
+                    // e[idx] = sum_{tt=0..3} tail[tt] * c[idx - tt]
+                    for (uint32_t tt = 0; tt < 4; tt++) {
+                        if (idx >= tt && idx - tt < N4) acc = acc + rg.tail[tt] * c[idx - tt];
+                    }
+                }
+                q[j] = acc;
+            }
+        }
+    }
+};
+
+// ---- transcript phase 2: quotient commitment -> zeta (phases.py:29-32) ---------------------------------------
+struct Transcript2Body {
+    DR_HD void operator()(const BlockCtx& ctx, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                ProofState& ps = st[p];
+                shake_absorb_label(ps.tr, "quotient", 8);
+                shake_absorb_g1(ps.tr, ps.commits[4]);
+                ps.tr.absorb_be32(96);
+                shake_challenges(ps.tr, "evaluation_point", 16, &ps.zeta, 1);
+            }
+        }
+    }
+};
+
+// Parallel Horner: value of poly (n coefficients, n a multiple of nthreads or padded by the caller) at x.
+// All threads of the block cooperate; result valid for every thread after the call (read from smem[0]).
+DR_HD Fr block_poly_eval(const BlockCtx& ctx, const Fr* poly, uint32_t n, const Fr& x, Fr* sm) {
+    const uint32_t T = ctx.nthreads;
+    const uint32_t L = (n + T - 1) / T;
+    DR_THREAD_LOOP(t, ctx) {
+        uint32_t lo = t * L, hi = lo + L < n ? lo + L : n;
+        Fr acc = Fr::zero();
+        if (lo < n) {
+#pragma unroll 1
+            for (uint32_t k = hi; k > lo; k--) acc = acc * x + poly[k - 1];
+            // times x^lo
+            Fr pw = Fr::one(), base = x;
+            uint32_t e = lo;
+#pragma unroll 1
+            while (e) {
+                if (e & 1) pw = pw * base;
+                base = base.sqr();
+                e >>= 1;
+            }
+            acc = acc * pw;
+        }
+        sm[t] = acc;
+    }
+    DR_BLOCK_SYNC();
+    for (uint32_t stride = T >> 1; stride > 0; stride >>= 1) {
+        DR_STRIDE_LOOP(t, stride, ctx) { sm[t] = sm[t] + sm[t + stride]; }
+        DR_BLOCK_SYNC();
+    }
+    Fr r = sm[0];
+    DR_BLOCK_SYNC();
+    return r;
+}
+
+// ---- K. evaluations at zeta (proof_builder.py:243-267): grid (7, proofs) ----------------------------------------
+// slot order = payload order: px, py, s, b, accip, accx, accy
+struct EvalBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, ProofState* st, const Fr* wit_coef) const {
+        ProofState& ps = st[ctx.by];
+        uint32_t slot = ctx.bx;
+        const Fr* poly;
+        const Fr* wc = wit_coef + (size_t)ctx.by * 4 * rg.N;
+        switch (slot) {
+            case 0: poly = rg.fixed_coef; break;
+            case 1: poly = rg.fixed_coef + rg.N; break;
+            case 2: poly = rg.fixed_coef + 2 * rg.N; break;
+            case 3: poly = wc + COL_B * rg.N; break;
+            case 4: poly = wc + COL_ACCIP * rg.N; break;
+            case 5: poly = wc + COL_ACCX * rg.N; break;
+            default: poly = wc + COL_ACCY * rg.N; break;
+        }
+        Fr v = block_poly_eval(ctx, poly, rg.N, ps.zeta, (Fr*)ctx.smem);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) ps.evals[slot] = v;
+        }
+    }
+};
+
+// ---- linearisation polynomial (proof_builder.py:197-241): grid (ceil(N/threads), proofs) --------------------------
+DR_HD void lin_factors(const RingDev& rg, const ProofState& ps, Fr& f_ip, Fr& f_x, Fr& f_y) {
+    Fr one = Fr::one();
+    Fr st = ps.zeta - rg.w_last;
+    Fr b = ps.evals[3], x1 = ps.evals[5], y1 = ps.evals[6], x2 = ps.evals[0], y2 = ps.evals[1];
+    Fr omb = one - b;
+    Fr fx = (b * (y1 * y2 - fr_mul5(x1 * x2)) + omb) * st;
+    Fr fy = (b * (x1 * y2 - x2 * y1) + omb) * st;
+    f_ip = st * ps.alpha[0];
+    f_x = fx * ps.alpha[1];
+    f_y = fy * ps.alpha[2];
+}
+struct LinPolyBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, const Fr* wit_coef, Fr* lin) const {
+        const ProofState& ps = st[ctx.by];
+        const Fr* wc = wit_coef + (size_t)ctx.by * 4 * rg.N;
+        Fr* dst = lin + (size_t)ctx.by * rg.N;
+        Fr f_ip, f_x, f_y;
+        lin_factors(rg, ps, f_ip, f_x, f_y);
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t k = ctx.bx * ctx.nthreads + t;
+            if (k < rg.N) dst[k] = wc[COL_ACCIP * rg.N + k] * f_ip + wc[COL_ACCX * rg.N + k] * f_x + wc[COL_ACCY * rg.N + k] * f_y;
+        }
+    }
+};
+// L(zeta * w): grid (1, proofs)
+struct LinEvalBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, ProofState* st, const Fr* lin) const {
+        ProofState& ps = st[ctx.by];
+        Fr zw = ps.zeta * rg.omega;
+        Fr v = block_poly_eval(ctx, lin + (size_t)ctx.by * rg.N, rg.N, zw, (Fr*)ctx.smem);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) ps.lzw = v;
+        }
+    }
+};
+
+// ---- transcript phase 3 (phases.py:35-43) -------------------------------------------------------------------------
+struct Transcript3Body {
+    DR_HD void operator()(const BlockCtx& ctx, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                ProofState& ps = st[p];
+                shake_absorb_label(ps.tr, "register_evaluations", 20);
+                for (int i = 0; i < 7; i++) shake_absorb_fr(ps.tr, ps.evals[i]);
+                ps.tr.absorb_be32(7 * 32);
+                shake_absorb_label(ps.tr, "shifted_linearization_evaluation", 32);
+                shake_absorb_fr(ps.tr, ps.lzw);
+                ps.tr.absorb_be32(32);
+                shake_challenges(ps.tr, "kzg_aggregation", 15, ps.nu, 8);
+            }
+        }
+    }
+};
+
+// ---- M. aggregated opening polynomial (proof_builder.py:288-315): grid (ceil((3N+1)/threads), proofs) ------------
+struct AggOpenBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, const Fr* wit_coef, const Fr* quot, uint32_t qstride, Fr* aggopen) const {
+        const ProofState& ps = st[ctx.by];
+        const uint32_t N = rg.N;
+        const Fr* wc = wit_coef + (size_t)ctx.by * 4 * N;
+        const Fr* q = quot + (size_t)ctx.by * qstride;
+        Fr* dst = aggopen + (size_t)ctx.by * qstride;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t k = ctx.bx * ctx.nthreads + t;
+            if (k < 3 * N + 1) {
+                Fr acc = q[k] * ps.nu[7];
+                if (k < N) {
+                    acc = acc + rg.fixed_coef[k] * ps.nu[0] + rg.fixed_coef[N + k] * ps.nu[1] + rg.fixed_coef[2 * N + k] * ps.nu[2] +
+                          wc[COL_B * N + k] * ps.nu[3] + wc[COL_ACCIP * N + k] * ps.nu[4] + wc[COL_ACCX * N + k] * ps.nu[5] + wc[COL_ACCY * N + k] * ps.nu[6];
+                }
+                dst[k] = acc;
+            }
+        }
+    }
+};
+
+// ---- N. synthetic division by (X - x) (pcs/utils.py:27-35): in place, poly[i] <- q[i], one block per polynomial.
+// r_i = sum_{k>=i} a_k x^(k-i);  q_i = r_{i+1}, q_{n-1} = 0.
+DR_HD void block_synthetic_div(const BlockCtx& ctx, Fr* poly, uint32_t n, const Fr& x, Fr* sm) {
+    const uint32_t T = ctx.nthreads;
+    const uint32_t L = (n + T - 1) / T;
+    // pass 1: suffix sums local to each chunk, written in place
+    DR_THREAD_LOOP(t, ctx) {
+        uint32_t lo = t * L, hi = lo + L < n ? lo + L : n;
+        Fr acc = Fr::zero();
+        if (lo < n) {
+#pragma unroll 1
+            for (uint32_t k = hi; k > lo; k--) {
+                acc = acc * x + poly[k - 1];
+                poly[k - 1] = acc;
+            }
+        }
+        sm[t] = acc;  // local suffix at the chunk start
+    }
+    DR_BLOCK_SYNC();
+    // pass 2: full suffix at each chunk start, serial over chunks: R_t = S_t + x^(len_t) * R_{t+1}
+    DR_THREAD_LOOP(t, ctx) {
+        if (t == 0) {
+            Fr xl = Fr::one(), base = x;
+            uint32_t e = L;
+#pragma unroll 1
+            while (e) {
+                if (e & 1) xl = xl * base;
+                base = base.sqr();
+                e >>= 1;
+            }
+            uint32_t nchunks = (n + L - 1) / L;
+            Fr carry = Fr::zero();  // R_{t+1}
+#pragma unroll 1
+            for (int c = (int)nchunks - 1; c >= 0; c--) {
+                Fr s = sm[c];
+                uint32_t len = ((uint32_t)c + 1) * L <= n ? L : n - (uint32_t)c * L;
+                Fr mult = xl;
+                if (len != L) {  // last (short) chunk
+                    mult = Fr::one();
+                    Fr b2 = x;
+                    uint32_t e2 = len;
+#pragma unroll 1
+                    while (e2) {
+                        if (e2 & 1) mult = mult * b2;
+                        b2 = b2.sqr();
+                        e2 >>= 1;
+                    }
+                }
+                sm[c] = carry;  // what chunk c needs: R_{c+1}
+                carry = s + mult * carry;
+            }
+        }
+    }
+    DR_BLOCK_SYNC();
+    // pass 3: r_i = local_i + x^(hi - i) * R_{t+1}
+    DR_THREAD_LOOP(t, ctx) {
+        uint32_t lo = t * L, hi = lo + L < n ? lo + L : n;
+        if (lo < n) {
+            Fr carry = sm[t];
+            Fr pw = x;  // x^(hi - (hi-1))
+#pragma unroll 1
+            for (uint32_t k = hi; k > lo; k--) {
+                poly[k - 1] = poly[k - 1] + pw * carry;
+                pw = pw * x;
+            }
+        }
+    }
+    DR_BLOCK_SYNC();
+    // pass 4: shift down by one: q_i = r_{i+1}.  Chunk boundaries need the neighbour's first element.
+    DR_THREAD_LOOP(t, ctx) {
+        uint32_t lo = t * L;
+        sm[t] = lo < n ? poly[lo] : Fr::zero();  // r at chunk start
+    }
+    DR_BLOCK_SYNC();
+    DR_THREAD_LOOP(t, ctx) {
+        uint32_t lo = t * L, hi = lo + L < n ? lo + L : n;
+        if (lo < n) {
+            for (uint32_t k = lo; k + 1 < hi; k++) poly[k] = poly[k + 1];
+            poly[hi - 1] = (hi < n) ? sm[t + 1] : Fr::zero();
+        }
+    }
+    DR_BLOCK_SYNC();
+}
+struct OpenQuotientsBody {
+    // grid (2, proofs): bx = 0 -> aggregated poly at zeta (3N+1 coefficients), bx = 1 -> L at zeta*w (N)
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, Fr* aggopen, uint32_t qstride, Fr* lin) const {
+        const ProofState& ps = st[ctx.by];
+        if (ctx.bx == 0) {
+            block_synthetic_div(ctx, aggopen + (size_t)ctx.by * qstride, 3 * rg.N + 1, ps.zeta, (Fr*)ctx.smem);
+        } else {
+            Fr zw = ps.zeta * rg.omega;
+            block_synthetic_div(ctx, lin + (size_t)ctx.by * rg.N, rg.N, zw, (Fr*)ctx.smem);
+        }
+    }
+};
+
+// ---- P. proof assembly (vrf/ring/vrf.py:51-58, proof_payload.py:68-91): 784 bytes per proof ----------------------
+struct FinalizeBody {
+    DR_HD void operator()(const BlockCtx& ctx, const ProofState* st, uint32_t count, uint8_t* out, uint32_t* status) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                const ProofState& ps = st[p];
+                uint8_t* o = out + 784 * (size_t)p;
+                for (int i = 0; i < 192; i++) o[i] = ps.pedersen[i];
+                o += 192;
+                for (int i = 0; i < 4; i++) g1_compress(o + 48 * i, ps.commits[i]);
+                o += 192;
+                for (int i = 0; i < 7; i++) fr_to_le_bytes_raw(o + 32 * i, ps.evals[i].from_mont());
+                o += 224;
+                g1_compress(o, ps.commits[4]);
+                fr_to_le_bytes_raw(o + 48, ps.lzw.from_mont());
+                g1_compress(o + 80, ps.commits[5]);
+                g1_compress(o + 128, ps.commits[6]);
+                status[p] = ps.status;
+            }
+        }
+    }
+};
+
+// scatter commit results (one per proof) into ProofState::commits[slot]
+struct StoreCommitBody {
+    // slot for result c of a proof = byte c of `slot_map`
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* res, uint32_t per_proof, uint32_t slot_map, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t idx = ctx.bx * ctx.nthreads + t;
+            if (idx < count * per_proof) {
+                uint32_t p = idx / per_proof, c = idx % per_proof;
+                st[p].commits[(slot_map >> (8 * c)) & 0xff] = res[idx];
+            }
+        }
+    }
+};
+
+// blinding rows: n x 12 canonical 32-byte values -> Montgomery in ProofState::zk (null -> zeros)
+struct ZkRowsBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* raw, ProofState* st, uint32_t count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t idx = ctx.bx * ctx.nthreads + t;
+            if (idx < count * 12) {
+                Fr v = Fr::zero();
+                if (raw) {
+                    fr_from_le_bytes_raw(v, raw + 32 * (size_t)idx);
+                    while (!v.is_canonical_raw()) Fr::sub_mod_inplace(v.v);
+                    v = v.to_mont();
+                }
+                st[idx / 12].zk[idx % 12] = v;
+            }
+        }
+    }
+};
+
+// ---- ring set-up helpers ----------------------------------------------------------------------------------------
+// keys (32 bytes each) -> nm[i]; undecodable / identity / out-of-subgroup keys become the padding point
+// (members.py:36-41,61-69).
+struct KeyDecodeBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* keys, uint32_t n_keys, TEAffine padding, TEAffine* nm) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < n_keys) {
+                TEAffine p;
+                if (!te_decode_checked(p, keys + 32 * (size_t)i)) p = padding;
+                nm[i] = p;
+            }
+        }
+    }
+};
+// column evaluations for the fixed columns: out[0][i] = nm[i].x, out[1][i] = nm[i].y, out[2][i] = i < max_ring
+struct FixedColumnsBody {
+    DR_HD void operator()(const BlockCtx& ctx, const TEAffine* nm, uint32_t N, uint32_t max_ring, Fr* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < N) {
+                out[i] = nm[i].x;
+                out[N + i] = nm[i].y;
+                out[2 * N + i] = i < max_ring ? Fr::one() : Fr::zero();
+            }
+        }
+    }
+};
+// notlast[j*N + i] = w4^(4i + j) - w^(N-4)
+struct NotLastBody {
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t N, const Fr* w4, Fr w_last, Fr* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < 4 * N) {
+                uint32_t j = p / N, i = p - j * N;
+                out[p] = w4[4 * i + j] - w_last;
+            }
+        }
+    }
+};
+
+}  // namespace dr

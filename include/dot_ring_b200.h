@@ -85,6 +85,57 @@ int dr_g1_decompress(dr_ctx* ctx, const uint8_t* in_be48, size_t count, uint8_t*
  * data_le32: batch x n elements, transformed in place.  n is a power of two, 2 <= n <= 4096. */
 int dr_fr_ntt(dr_ctx* ctx, uint8_t* data_le32, size_t n, size_t batch, int inverse, const uint8_t omega_le32[32]);
 
+/* ---- ring: key ingestion, fixed columns, ring root ---------------------------------------------------
+ * Replaces `Ring.__init__` (dot_ring/vrf/ring/members.py:22-55: per-key decode + subgroup check, padding,
+ * blinding-base powers) and `RingRoot.from_ring` (dot_ring/vrf/ring/root.py:21-44,133-173: three
+ * iNTT(N) + three KZG commits) plus the per-ring constants the prover re-derives on every call in the
+ * reference (constraints.py:43-62: 4x LDE of px, py, s, L_0, L_{N-4}).
+ * All field elements are 32-byte little-endian canonical; points are affine (x | y). */
+typedef struct dr_ring_params {
+    uint32_t domain_size;      /* N (params.py:119) */
+    uint32_t max_ring_size;    /* params.py:120 */
+    uint32_t padding_rows;     /* must be 4 (params.py:196-197) */
+    uint32_t suite_id_len;
+    uint32_t h2c_dst_len;
+    uint32_t reserved;
+    uint8_t omega[32];         /* params.omega: primitive N-th root of unity */
+    uint8_t radix_omega[32];   /* params.radix_omega: primitive 4N-th root (sqrt-extended for 4N > 2048) */
+    uint8_t seed[64];          /* accumulator_base */
+    uint8_t blinding_base[64];
+    uint8_t padding_point[64];
+    uint8_t generator[64];
+    uint8_t suite_id[32];      /* e.g. "Bandersnatch-SHA512-ELL2-v1" */
+    uint8_t h2c_dst[64];       /* hash-to-curve DST, e.g. suite_id | 0x60 */
+} dr_ring_params;
+
+int dr_ring_create(dr_ctx* ctx, dr_srs* srs, const dr_ring_params* params, const uint8_t* keys32, size_t n_keys, dr_ring** out);
+void dr_ring_destroy(dr_ring* ring);
+/* 144-byte ring root = compress(C_px) | compress(C_py) | compress(C_s)  (root.py:74-87). */
+int dr_ring_root(dr_ring* ring, uint8_t root144[144]);
+/* Uncompressed fixed commitments (3 x 96 bytes) as absorbed by the verifier key (root.py:54-71). */
+int dr_ring_fixed_commitments(dr_ring* ring, uint8_t out288[288]);
+/* `Ring.nm_points` (members.py:55): N affine points, x | y little-endian (64 bytes each). */
+int dr_ring_points(dr_ring* ring, uint8_t* out_xy64, size_t n_points);
+
+/* ---- Ring VRF prove, batched -----------------------------------------------------------------------
+ * Replaces `RingVRF[Bandersnatch].prove` (dot_ring/vrf/ring/vrf.py:185-209) = `PedersenVRF.prove`
+ * (vrf/pedersen/vrf.py:86-126) + `RingProofBuilder.build` (ring_proof/proof_builder.py:38-142) for n
+ * independent (alpha, ad, secret key, producer index) items against one ring.
+ *   blob / offsets: item i has alpha = blob[alpha_off[i] .. +alpha_len[i]) and ad likewise;
+ *   secret_keys32: n x 32-byte little-endian scalars; producer_index[i]: row of pk(sk_i) in the ring;
+ *   zk_rows: n x 12 x 32 bytes replacing the reference's `secrets.randbelow` draws in column order
+ *            b, acc_x, acc_y, acc_ip (columns.py:43-53,153-161), or NULL for test_vectors=True (zeros);
+ *   proofs784: n x 784 bytes (192-byte Pedersen part | 592-byte ring payload);
+ *   status[i]: 0 ok, non-zero when sk_i does not own ring row producer_index[i] (reference: ValueError). */
+int dr_ring_prove_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* blob, const uint32_t* alpha_off, const uint32_t* alpha_len,
+                        const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* secret_keys32, const uint32_t* producer_index,
+                        const uint8_t* zk_rows, uint8_t* proofs784, uint32_t* status);
+/* Per-phase device time of the last dr_ring_prove_batch on this ctx (ms): [0] pedersen+witness, [1] interpolate,
+ * [2] commits (all MSMs), [3] LDE+constraints+quotient, [4] evaluations+openings polys, [5] transcripts+assembly. */
+int dr_ring_prove_phase_ms(dr_ctx* ctx, float out[6]);
+/* Proofs processed per internal pass (bounds device scratch: about 1 KiB * domain_size per proof). 0 = default 1024. */
+int dr_ctx_set_prove_chunk(dr_ctx* ctx, size_t chunk);
+
 /* ---- arithmetic-layer self test + integer-pipe ceilings ----------------------------------------
  * dr_field_op: element-wise Montgomery arithmetic on the device (reference equivalent:
  * dot_ring/curve/native_field/scalar.pyx:12-165 `Scalar`, tested by tests/test_curve_ops/test_native_field.py).
