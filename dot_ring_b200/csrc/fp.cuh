@@ -325,6 +325,7 @@ DR_HD F fp_from_le_bytes_mod(const uint8_t* in, int len) {
     two128 = two128.to_mont();
     F acc = F::zero();
     int nchunks = (len + 15) / 16;
+#pragma unroll 1
     for (int c = nchunks - 1; c >= 0; c--) {
         F chunk = F::zero();
         for (int b = 0; b < 16; b++) {

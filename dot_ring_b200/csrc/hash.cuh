@@ -55,7 +55,7 @@ struct Sha512 {
         return k[i];
     }
 
-    DR_HD void compress(const uint8_t* p) {
+    DR_HD_COLD void compress(const uint8_t* p) {
         uint64_t w[16];
         for (int i = 0; i < 16; i++) {
             uint64_t x = 0;
@@ -63,6 +63,7 @@ struct Sha512 {
             w[i] = x;
         }
         uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll 4
         for (int i = 0; i < 80; i++) {
             uint64_t wi;
             if (i < 16) {
@@ -101,6 +102,7 @@ struct Sha512 {
 
     DR_HD void update(const uint8_t* data, uint32_t len) {
         total += len;
+#pragma unroll 1
         for (uint32_t i = 0; i < len; i++) {
             buf[fill++] = data[i];
             if (fill == 128) {
@@ -140,7 +142,7 @@ struct Shake128 {
         pos = 0;
     }
 
-    DR_HD static void permute(uint64_t* a) {
+    DR_HD_COLD static void permute(uint64_t* a) {
         constexpr uint64_t rc[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
                                      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
                                      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
@@ -149,6 +151,7 @@ struct Shake128 {
                                      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
         constexpr int rotc[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
         constexpr int piln[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+#pragma unroll 1
         for (int round = 0; round < 24; round++) {
             uint64_t bc[5];
             for (int i = 0; i < 5; i++) bc[i] = a[i] ^ a[i + 5] ^ a[i + 10] ^ a[i + 15] ^ a[i + 20];
@@ -172,6 +175,7 @@ struct Shake128 {
     }
 
     DR_HD void absorb(const uint8_t* data, uint32_t len) {
+#pragma unroll 1
         for (uint32_t i = 0; i < len; i++) {
             st[pos >> 3] ^= (uint64_t)data[i] << (8 * (pos & 7));
             pos++;

@@ -85,7 +85,7 @@ DR_HD Fr shake_challenge_value(const Shake128& s) {
     return fr_from_be48_mod(out);
 }
 // transcript.py:109-136: prefix = label | be32(len) | "challenge"; after each squeeze absorb footer 00 00 00 09
-DR_HD void shake_challenges(Shake128& s, const char* label, uint32_t len, Fr* out, int n) {
+DR_HD_COLD void shake_challenges(Shake128& s, const char* label, uint32_t len, Fr* out, int n) {
     for (int i = 0; i < n; i++) {
         shake_absorb_label(s, label, len);
         s.absorb((const uint8_t*)"challenge", 9);
@@ -106,7 +106,7 @@ DR_HD void shake_absorb_g1(Shake128& s, const G1Affine& p) {
 
 // SHA-512 counter-mode squeeze of the VRF transcript (primitives.py:165-174): seed = H(absorbed),
 // block c = H(seed | le64(c)).  `st` already holds the absorbed bytes.
-DR_HD void vrf_squeeze(const Sha512& st, uint8_t* out, uint32_t size) {
+DR_HD_COLD void vrf_squeeze(const Sha512& st, uint8_t* out, uint32_t size) {
     Sha512 h = st;
     uint8_t seed[64];
     h.final(seed);
@@ -129,7 +129,7 @@ DR_HD void fn_to_le_bytes(uint8_t* out, const Fn& x_mont) {
         for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(x.v[i] >> (8 * b));
 }
 // primitives.py:66-82 `nonce`
-DR_HD Fn vrf_nonce(const Sha512& t, const Fn& secret) {
+DR_HD_COLD Fn vrf_nonce(const Sha512& t, const Fn& secret) {
     Sha512 te = t;
     te.update_byte(0x10);
     uint8_t sb[32];
@@ -148,7 +148,7 @@ DR_HD void fn_raw_limbs(uint32_t* out, const Fn& x_mont) {
     Fn x = x_mont.from_mont();
     for (int i = 0; i < 8; i++) out[i] = x.v[i];
 }
-DR_HD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {
+DR_HD_COLD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {
     uint32_t kr[8];
     fn_raw_limbs(kr, k);
     return te_to_affine(te_mul_raw(p, kr, 8));
@@ -160,7 +160,7 @@ DR_HD void sha_absorb_point(Sha512& s, const TEAffine& p) {
 }
 
 // expand_message_xmd(SHA-512) for 96 output bytes (curve.py:145-185; Z_pad = 48 bytes for this suite)
-DR_HD void h2c_uniform_bytes(const RingDev& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
+DR_HD_COLD void h2c_uniform_bytes(const RingDev& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
     uint8_t dst_prime_len = (uint8_t)rg.dst_len;
     Sha512 h;
     h.init();

@@ -101,10 +101,13 @@ DR_HD_COLD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
     TEExt tab[16];
     tab[0] = TEExt::identity();
     tab[1] = TEExt::from_affine(p);
+#pragma unroll 1
     for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? te_add(tab[i - 1], tab[1]) : te_dbl(tab[i >> 1]);
     TEExt acc = TEExt::identity();
     bool started = false;
+#pragma unroll 1
     for (int i = nlimbs - 1; i >= 0; i--) {
+#pragma unroll 1
         for (int s = 28; s >= 0; s -= 4) {
             if (started) {
                 acc = te_dbl(te_dbl(te_dbl(te_dbl(acc))));
@@ -122,16 +125,21 @@ DR_HD_COLD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
 // sum_i k_i * P_i with shared doublings (Straus), n <= 3, raw 8-limb scalars (< subgroup order).
 DR_HD_COLD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int n) {
     TEExt tab[3][16];
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         tab[j][0] = TEExt::identity();
         tab[j][1] = TEExt::from_affine(pts[j]);
+#pragma unroll 1
         for (int i = 2; i < 16; i++) tab[j][i] = (i & 1) ? te_add(tab[j][i - 1], tab[j][1]) : te_dbl(tab[j][i >> 1]);
     }
     TEExt acc = TEExt::identity();
     bool started = false;
+#pragma unroll 1
     for (int i = 7; i >= 0; i--) {
+#pragma unroll 1
         for (int s = 28; s >= 0; s -= 4) {
             if (started) acc = te_dbl(te_dbl(te_dbl(te_dbl(acc))));
+#pragma unroll 1
             for (int j = 0; j < n; j++) {
                 uint32_t d = (ks[j][i] >> s) & 15;
                 if (d) {
@@ -163,6 +171,7 @@ DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
     constexpr uint32_t c_c[8] = DR_FR_TS_C;
     uint32_t e[8];
     Fr c;
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         e[i] = e_c[i];
         c.v[i] = c_c[i];
@@ -172,15 +181,18 @@ DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
     Fr t = x * w;        // a^q
     int m = 32;
     Fr one = Fr::one();
+#pragma unroll 1
     while (t != one) {
         int i = 0;
         Fr t2 = t;
+#pragma unroll 1
         while (t2 != one) {
             t2 = t2.sqr();
             i++;
             if (i == m) return false;  // order of t does not divide 2^(m-1): non-residue
         }
         Fr b = c;
+#pragma unroll 1
         for (int j = 0; j < m - i - 1; j++) b = b.sqr();
         x = x * b;
         c = b.sqr();
