@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark: Ring VRF proofs/s at ring size 1023 (domain 2^11), batched on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...   # reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]; seeding of the reference's own tests/benchmark/bench_ring_proof.py:
+47-77,140-152): one 1023-key ring, signer at index 3, per step a batch of `--batch` proofs with
+alpha = "bench-batch-input" | le64(j), ad = "bench-batch-ad" | le64(j) and 12 blinding rows per proof from
+random.Random(0).  Every rank proves its own batch per step (weak scaling, no data-path collective);
+`value` = proofs of all ranks / max-over-ranks device time; `e2e` = the same through the public Python API
+with host buffers (H2D of the inputs and D2H of the 784-byte proofs inside the timed region).
+
+A number printed by this script under a profiler is not a bench value.
+"""
+
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FR = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+RING_SIZE = 1023
+SIGNER_INDEX = 3
+MSM_SIZES = (2048, 2048, 2048, 2048, 6145, 6144, 2047)  # per proof at N = 2048
+
+
+def seed_bytes(*parts) -> bytes:
+    h = hashlib.sha256()
+    for part in parts:
+        if isinstance(part, bytes):
+            h.update(part)
+        elif isinstance(part, int):
+            h.update(part.to_bytes(8, "little"))
+        else:
+            h.update(part.encode())
+        h.update(b"\0")
+    return h.digest()
+
+
+def le64(i: int) -> bytes:
+    return i.to_bytes(8, "little")
+
+
+def canonical_fq_mul_per_msm(n: int) -> int:
+    """Pippenger, signed c-bit windows: min_c ceil(255/c) * (n*10 + 2^c*14) Fq multiplications."""
+    return min(-(-255 // c) * (n * 10 + (1 << c) * 14) for c in range(2, 21))
+
+
+CANONICAL_IMAD_PER_PROOF = sum(canonical_fq_mul_per_msm(n) for n in MSM_SIZES) * 600  # 600 IMAD per 12-limb Montgomery mul
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples: list[dict] = []
+        self._stop = threading.Event()
+
+    def run(self) -> None:
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5
+                ).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 7:
+                    self.samples.append({"sm": float(f[0]), "max": float(f[1]), "power": float(f[2]), "reasons": f[3:7]})
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(s["sm"] for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i, r in enumerate(s["reasons"]) if r.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0]["max"], "power_w_max": max(s["power"] for s in self.samples), "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    """One process per GPU; torch.distributed (NCCL) is plumbing for the barrier and the max-over-ranks only."""
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return rank, local, 1, None
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, local, world, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def reduce_max(dist, local, values: list[float]) -> list[float]:
+    if dist is None:
+        return values
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def reduce_sum(dist, local, values: list[float]) -> list[float]:
+    if dist is None:
+        return values
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()]
+
+
+# -------------------------------------------------------------------------------------------------- ours
+def run_ours(args) -> None:
+    rank, local, world, dist = dist_setup(args.gpus)
+    os.environ["DOT_RING_B200_DEVICE"] = str(local)
+    from dot_ring_b200 import Bandersnatch, Ring, RingProofParams, RingRoot, RingVRF
+    from dot_ring_b200 import engine as eng_mod
+
+    t0 = time.perf_counter()
+    eng = eng_mod.Engine(local, window_bits=args.window_bits)
+    eng_mod.set_default_engine(eng, local)
+    _ = eng.srs
+    eng.ctx.sync()
+    table_s = time.perf_counter() - t0
+    info = eng.ctx.device_info()
+
+    # synthetic ring: keys derived with the product's own key derivation (no oracle on this path)
+    t0 = time.perf_counter()
+    seeds = [seed_bytes("batch-signer", 0, 0) if i == SIGNER_INDEX else seed_bytes("ring-member", 0, i) for i in range(RING_SIZE)]
+    from dot_ring_b200.transcript import secret_scalar_from_seed
+
+    sks = [secret_scalar_from_seed(Bandersnatch, s).to_bytes(32, "little") for s in seeds]
+    keys = Bandersnatch.public_keys_from_secrets(sks)
+    sk, pk = sks[SIGNER_INDEX], keys[SIGNER_INDEX]
+    params = RingProofParams.from_ring_size(RING_SIZE)
+    ring = Ring(keys, params, eng)
+    root = RingRoot.from_ring(ring, params)
+    root_bytes = root.encode()
+    ring_s = time.perf_counter() - t0
+
+    batch = args.batch
+    rng = random.Random(rank)
+
+    def inputs(step: int):
+        base = (rank * 1_000_000 + step) * batch
+        return (
+            [b"bench-batch-input" + le64(base + j) for j in range(batch)],
+            [b"bench-batch-ad" + le64(base + j) for j in range(batch)],
+            [rng.randrange(FR) for _ in range(12 * batch)],
+        )
+
+    launches0 = eng.ctx.library.launch_count()
+    for w in range(args.warmup):
+        a, d, zk = inputs(-1 - w)
+        RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
+    launches_warm = eng.ctx.library.launch_count()
+
+    prepared = [inputs(s) for s in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier(dist, local)
+    eng.ctx.sync()
+    dev_ms, phases = 0.0, [0.0] * 6
+    t_start = time.perf_counter()
+    last = None
+    for a, d, zk in prepared:
+        last = RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
+        ph = ring.native.prove_phase_ms()
+        dev_ms += sum(ph)
+        phases = [x + y for x, y in zip(phases, ph)]
+    eng.ctx.sync()
+    barrier(dist, local)
+    wall_s = time.perf_counter() - t_start
+    clocks = sampler.stop()
+    launches = eng.ctx.library.launch_count() - launches_warm
+
+    # integer-pipe ceiling measured live on this GPU (dependent-free mad.lo.u32, all SMs)
+    imad_peak, _ = eng.ctx.microbench("imad", 20000)
+    imad_wide_peak, _ = eng.ctx.microbench("imad_wide", 20000)
+
+    mx = reduce_max(dist, local, [dev_ms, wall_s])
+    proofs_total = batch * args.steps * world
+    value = proofs_total / (mx[0] * 1e-3)
+    e2e = proofs_total / mx[1]
+    commit_ms = phases[2]
+    achieved = CANONICAL_IMAD_PER_PROOF * batch * args.steps / (commit_ms * 1e-3)
+    executed = (sum(MSM_SIZES) * (-(-256 // args.window_bits)) * 10 * 600) * batch * args.steps / (commit_ms * 1e-3)
+    table_traffic = sum(MSM_SIZES) * (-(-256 // args.window_bits)) * 96 * batch * args.steps  # algorithmic table bytes read
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "ring_vrf_proofs_per_s",
+        "value": value,
+        "unit": "proofs/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": mx[0] / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u32 limbs (381-bit Fq / 255-bit Fr Montgomery)",
+        "data": "synthetic",
+        "config": {
+            "workload": f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {batch} proofs per GPU per step (BASELINE configs[1])",
+            "batch_per_gpu": batch,
+            "window_bits": args.window_bits,
+            "table_gb": round(eng.srs.table_bytes / 1e9, 2),
+            "l2": "per-step working set (window table + ~8 GB scratch) is far larger than the 126 MB L2; no flush needed",
+            "parity": "ring root sha256 " + hashlib.sha256(root_bytes).hexdigest()[:16],
+        },
+        "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": batch * (12 * 32 + 32 + 4 * 5 + 25 + 22), "d2h_bytes_per_step": batch * (784 + 4), "ms_per_step": mx[1] * 1e3 / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "kernel_entry<CommitBody> (fixed-base KZG commit)",
+            "bound": "int32 pipe (IMAD); not hbm / tensor: the path is 381-bit modular arithmetic",
+            "achieved": achieved / 1e12,
+            "peak": imad_peak / 1e12,
+            "unit": "T IMAD/s (canonical Pippenger count, SURVEY.md 8d: 4.674 G IMAD per proof)",
+            "frac": achieved / imad_peak,
+            "executed": executed / 1e12,
+            "executed_frac": executed / imad_peak,
+            "peak_source": "measured live: dependent-free mad.lo.u32 on all SMs (dr_microbench); IMAD.WIDE measured " + f"{imad_wide_peak / 1e12:.2f} T/s",
+            "traffic": None,
+            "algorithmic_table_bytes": table_traffic,
+            "hbm_gbs_for_table_reads": table_traffic / (commit_ms * 1e-3) / 1e9,
+            "kernel_share_of_step": commit_ms / sum(phases),
+        },
+        "phase_ms_per_step": {k: v / args.steps for k, v in zip(["pedersen+witness", "interpolate", "commit(msm)", "lde+constraints+quotient", "evals+openings", "transcripts+assembly"], phases)},
+        "setup": {"srs_table_s": table_s, "ring_s": ring_s, "device": info["name"], "sm_count": info["sm_count"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single()
+    print(json.dumps(line), flush=True)
+    if last:
+        sys.stderr.write(f"[bench] last proof sha256 {hashlib.sha256(last[-1]).hexdigest()[:16]}\n")
+
+
+# ------------------------------------------------------------------------------------ CPU baseline (oracle)
+def _oracle_ring():
+    from oracle import bandersnatch as bs
+    from oracle import ring_proof as rp
+    from oracle import transcript as tr
+
+    pk, sk = tr.secret_from_seed(bs.SHA512, seed_bytes("batch-signer", 0, 0))
+    keys = [pk if i == SIGNER_INDEX else tr.secret_from_seed(bs.SHA512, seed_bytes("ring-member", 0, i))[0] for i in range(RING_SIZE)]
+    params = rp.Params.from_ring_size(RING_SIZE)
+    ring = rp.Ring(keys, params)
+    root = rp.RingRoot.from_ring(ring, params)
+    return pk, sk, ring, root
+
+
+def _oracle_prove_n(args):
+    """Worker: build the ring once, then time `count` proofs."""
+    count, start = args
+    from oracle import fr as ofr
+    from oracle import vrf as ovrf
+
+    pk, sk, ring, root = _oracle_ring()
+    rng = random.Random(start)
+    t0 = time.perf_counter()
+    for j in range(count):
+        zk = [rng.randrange(ofr.R) for _ in range(12)]
+        ovrf.ring_prove(b"bench-batch-input" + le64(start + j), b"bench-batch-ad" + le64(start + j), sk, pk, ring, root, zk_rows=zk)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single() -> dict:
+    from oracle import backend_name
+
+    dt = _oracle_prove_n((1, 0))
+    return {
+        "value": 1.0 / dt,
+        "unit": "proofs/s",
+        "cores": 1,
+        "kind": "port",
+        "sample": f"1 proof, ring {RING_SIZE} / domain 2048, oracle port ({backend_name()}), ring set-up excluded",
+    }
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+
+    from oracle import backend_name
+
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, args.ref_workers or cores))
+    total_steps = args.steps + args.warmup
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        times = list(ex.map(_oracle_prove_n, [(total_steps, 1000 * w) for w in range(workers)]))
+    # every worker proves one proof per step; warm-up steps are part of each worker's loop, so scale them out
+    per_worker_s = [t * args.steps / total_steps for t in times]
+    wall = max(per_worker_s)
+    value = workers * args.steps / wall
+    line = {
+        "impl": "reference",
+        "metric": "ring_vrf_proofs_per_s",
+        "value": value,
+        "unit": "proofs/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": wall * 1e3 / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "python ints / u64 limbs",
+        "data": "synthetic",
+        "config": {"workload": f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048; each step = 1 proof on each of {workers} host processes"},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": workers, "kind": "port", "sample": f"{workers} x {args.steps} proofs, oracle port ({backend_name()})"},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "12")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-workers", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

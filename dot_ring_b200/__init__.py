@@ -3,7 +3,15 @@
 Host code is Python and calls the CUDA library ``libdotring_b200.so`` through ctypes
 (``dot_ring_b200._native``).  The library is loaded on first use and its absence is a hard
 ``ImportError``: there is no CPU fallback.
+
+Public names mirror ``dot_ring`` (dot_ring/__init__.py:32-77) for the path this engine covers.
 """
 
-__all__ = ["__version__"]
+from .curve import Bandersnatch
+from .kzg import KZG
+from .params import RingProofParams
+from .ring import Ring, RingRoot
+from .vrf import PedersenVRF, RingVRF
+
+__all__ = ["Bandersnatch", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "__version__"]
 __version__ = "0.1.0"

@@ -18,6 +18,7 @@ DR_OK, DR_EINVAL, DR_ECUDA, DR_ENOMEM, DR_ESTATE = 0, -1, -2, -3, -4
 _HERE = Path(__file__).resolve().parent
 DEFAULT_LIBRARY = _HERE / "libdotring_b200.so"
 FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+BANDERSNATCH_ORDER = 0x1CFB69D4CA675F520CCE760202687600FF8F87007419047174FD06B52876E7E1
 
 
 class NativeError(RuntimeError):
@@ -84,6 +85,9 @@ class Library:
         L.dr_ring_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 10
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
+
+        L.dr_te_decode_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]
+        L.dr_te_mul_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]
 
     def check(self, code: int) -> None:
         if code == DR_OK:
@@ -188,6 +192,29 @@ class Context:
         ops, ms = ctypes.c_double(), c_float()
         self.library.check(self.library.lib.dr_microbench(self.handle, k, iters, ctypes.byref(ops), ctypes.byref(ms)))
         return float(ops.value), float(ms.value)
+
+    def te_decode(self, encoded: list[bytes], checked: bool = True) -> list[tuple[int, int] | None]:
+        """Batch `dec_point`: affine (x, y) per item, None where the reference would raise ValueError."""
+        n = len(encoded)
+        if any(len(e) != 32 for e in encoded):
+            raise ValueError("point must be exactly 32 bytes")
+        out = ctypes.create_string_buffer(64 * max(n, 1))
+        ok = ctypes.create_string_buffer(max(n, 1))
+        self.library.check(self.library.lib.dr_te_decode_batch(self.handle, b"".join(encoded), n, 1 if checked else 0, out, ok))
+        raw, okr = out.raw, ok.raw
+        return [
+            (int.from_bytes(raw[64 * i : 64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32 : 64 * i + 64], "little")) if okr[i] else None
+            for i in range(n)
+        ]
+
+    def te_mul(self, points: list[bytes], scalars: list[int]) -> list[bytes | None]:
+        """Batch scalar multiplication on 32-byte encodings; one shared base when len(points) == 1."""
+        n = len(scalars)
+        out = ctypes.create_string_buffer(32 * max(n, 1))
+        ok = ctypes.create_string_buffer(max(n, 1))
+        ks = b"".join((int(k) % BANDERSNATCH_ORDER).to_bytes(32, "little") for k in scalars)
+        self.library.check(self.library.lib.dr_te_mul_batch(self.handle, b"".join(points), len(points), ks, n, out, ok))
+        return [out.raw[32 * i : 32 * i + 32] if ok.raw[i] else None for i in range(n)]
 
     def g1_compress(self, points_be96: bytes) -> bytes:
         count = len(points_be96) // 96

@@ -1,0 +1,60 @@
+"""Process-wide engine: one CUDA context + SRS (with its fixed-base table) per GPU.
+
+The reference keeps a module-level ``KZG.srs`` (dot_ring/ring_proof/pcs/kzg.py:114-119); the
+equivalent here is a lazily created :class:`Engine` per device, holding the ``dr_ctx`` and ``dr_srs``
+handles.  Device selection is a property of the engine (``DOT_RING_B200_DEVICE`` or
+``Engine(device=...)``), not of ``RingProofParams``.
+"""
+
+from __future__ import annotations
+
+import os
+import threading
+
+from . import _native
+from .srs import read_srs_file
+
+_lock = threading.Lock()
+_engines: dict[int, "Engine"] = {}
+
+
+class Engine:
+    def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None):
+        self.device = device
+        self.ctx = _native.Context(device, library)
+        self.window_bits = int(window_bits if window_bits is not None else os.environ.get("DOT_RING_B200_WINDOW_BITS", "12"))
+        self._srs: _native.NativeSrs | None = None
+        self._srs_points = srs_points
+        self.srs_bytes = read_srs_file(None, srs_points)
+
+    @property
+    def srs(self) -> _native.NativeSrs:
+        """SRS points + window table in HBM, built on first use (about 0.5 s for the default 26.6 GB table)."""
+        if self._srs is None:
+            self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits)
+        return self._srs
+
+    def close(self) -> None:
+        if self._srs is not None:
+            self._srs.close()
+            self._srs = None
+        self.ctx.close()
+
+
+def default_engine() -> Engine:
+    device = int(os.environ.get("DOT_RING_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = Engine(device)
+            _engines[device] = eng
+        return eng
+
+
+def set_default_engine(engine: Engine | None, device: int = 0) -> None:
+    """Install (or drop) the engine used by the module-level API; tests use it to inject the emulation build."""
+    with _lock:
+        if engine is None:
+            _engines.pop(device, None)
+        else:
+            _engines[device] = engine

@@ -1,0 +1,232 @@
+"""RingVRF / PedersenVRF: drop-in mirrors of dot_ring/vrf/ring/vrf.py:30-294 and
+dot_ring/vrf/pedersen/vrf.py:33-242 for the Bandersnatch suite, with batched entry points.
+
+``RingVRF[Bandersnatch].prove(alpha, ad, sk, pk, ring, ring_root)`` keeps the reference signature and
+is ``prove_batch`` with one item; ``prove_batch`` is the call the 4096-proof configuration uses.
+Blinding rows: ``RingProofParams(test_vectors=True)`` -> zeros (as in the reference);
+otherwise 12 fresh ``secrets.randbelow(prime)`` values per proof in the reference's draw order
+(b, acc_x, acc_y, acc_ip; columns.py:43-53,153-161) unless ``zk_rows`` injects them.
+"""
+
+from __future__ import annotations
+
+import secrets
+from collections.abc import Sequence
+from dataclasses import dataclass
+from typing import Any, ClassVar
+
+from .curve import Bandersnatch, CurveVariant
+from .params import RingProofParams
+from .ring import Column, Ring, RingRoot
+
+PEDERSEN_LEN = 192
+RING_PAYLOAD_LEN = 592
+RING_PROOF_LEN = PEDERSEN_LEN + RING_PAYLOAD_LEN
+
+
+class VRF:
+    """vrf/vrf.py:12-28: ``Scheme[curve]`` specialisation by subscription."""
+
+    cv: ClassVar[CurveVariant] = Bandersnatch
+
+    def __class_getitem__(cls, curve_variant: Any):
+        if not isinstance(curve_variant, CurveVariant):
+            return cls
+        return type(f"{cls.__name__}[{curve_variant.name}]", (cls,), {"cv": curve_variant})
+
+
+def _dec_scalar(cv: CurveVariant, value: bytes) -> int:
+    if len(value) != 32:
+        raise ValueError("scalar must be exactly 32 bytes")
+    scalar = int.from_bytes(value, "little")
+    if scalar >= cv.curve.params.subgroup_order:
+        raise ValueError("scalar is not canonical")
+    return scalar
+
+
+@dataclass(frozen=True)
+class PedersenVRF(VRF):
+    """gamma || Y_bar || R || O_k || s || s_b (points as 32-byte encodings)."""
+
+    output_point: bytes
+    blinded_pk: bytes
+    result_point: bytes
+    ok: bytes
+    s: int
+    sb: int
+
+    @classmethod
+    def proof_len(cls) -> int:
+        return PEDERSEN_LEN
+
+    @classmethod
+    def decode(cls, proof: bytes) -> "PedersenVRF":
+        """pedersen/vrf.py:48-73: four validated subgroup points and two canonical scalars."""
+        if len(proof) != PEDERSEN_LEN:
+            raise ValueError(f"invalid Pedersen VRF proof length: expected {PEDERSEN_LEN}, got {len(proof)}")
+        from .engine import default_engine
+
+        pts = [bytes(proof[32 * i : 32 * i + 32]) for i in range(4)]
+        if any(p is None for p in default_engine().ctx.te_decode(pts, checked=True)):
+            raise ValueError("Invalid point in proof")
+        return cls(pts[0], pts[1], pts[2], pts[3], _dec_scalar(cls.cv, proof[128:160]), _dec_scalar(cls.cv, proof[160:192]))
+
+    def encode(self) -> bytes:
+        return self.output_point + self.blinded_pk + self.result_point + self.ok + self.s.to_bytes(32, "little") + self.sb.to_bytes(32, "little")
+
+
+@dataclass
+class RingVRF(VRF):
+    pedersen_proof: PedersenVRF
+    c_b: Column
+    c_accip: Column
+    c_accx: Column
+    c_accy: Column
+    px_zeta: int
+    py_zeta: int
+    s_zeta: int
+    b_zeta: int
+    accip_zeta: int
+    accx_zeta: int
+    accy_zeta: int
+    c_q: Column
+    l_zeta_omega: int
+    open_agg_zeta: bytes
+    open_l_zeta_omega: bytes
+    _encoded: bytes | None = None
+
+    @classmethod
+    def proof_len(cls) -> int:
+        return RING_PROOF_LEN
+
+    def encode(self) -> bytes:
+        """vrf/ring/vrf.py:56-58 + proof_payload.py:68-91."""
+        if self._encoded is not None:
+            return self._encoded
+        from .kzg import KZG
+
+        le = lambda v: int(v).to_bytes(32, "little")  # noqa: E731
+        g = KZG.compress_g1(
+            self.c_b.commitment + self.c_accip.commitment + self.c_accx.commitment + self.c_accy.commitment + self.c_q.commitment
+            + self.open_agg_zeta + self.open_l_zeta_omega
+        )
+        return (
+            self.pedersen_proof.encode() + g[0:192]
+            + b"".join(le(v) for v in (self.px_zeta, self.py_zeta, self.s_zeta, self.b_zeta, self.accip_zeta, self.accx_zeta, self.accy_zeta))
+            + g[192:240] + le(self.l_zeta_omega) + g[240:288] + g[288:336]
+        )  # fmt: skip
+
+    @classmethod
+    def decode(cls, proof: bytes) -> "RingVRF":
+        """vrf/ring/vrf.py:60-93 + proof_payload.py:93-143: lengths, G1 / point validity, canonical scalars."""
+        if len(proof) != RING_PROOF_LEN:
+            raise ValueError(f"invalid Ring VRF proof length: Ring VRF proof must be exactly {RING_PROOF_LEN} bytes, got {len(proof)}")
+        from .kzg import KZG
+
+        proof = bytes(proof)
+        pedersen = PedersenVRF[cls.cv].decode(proof[:PEDERSEN_LEN])
+        body = proof[PEDERSEN_LEN:]
+        prime = cls.cv.curve.params.field_modulus
+        g1 = KZG.decompress_g1_batch(body[0:192] + body[416:464] + body[496:592])
+        scalars = [int.from_bytes(body[192 + 32 * i : 224 + 32 * i], "little") for i in range(7)] + [int.from_bytes(body[464:496], "little")]
+        if any(v >= prime for v in scalars):
+            raise ValueError("scalar is not canonical")
+        return cls(
+            pedersen,
+            Column("c_b", g1[0]), Column("c_accip", g1[1]), Column("c_accx", g1[2]), Column("c_accy", g1[3]),
+            *scalars[:7],
+            Column("c_q", g1[4]), scalars[7], g1[5], g1[6], _encoded=proof,
+        )  # fmt: skip
+
+    @classmethod
+    def _from_bytes_trusted(cls, proof: bytes) -> "RingVRF":
+        """Wrap device output without re-validating (points were produced by the prover itself)."""
+        return _LazyRingVRF.wrap(cls, proof)
+
+    @classmethod
+    def parse_keys(cls, keys: bytes) -> list[bytes]:
+        if len(keys) % 32 != 0:
+            raise ValueError(f"invalid concatenated key length: expected multiple of 32, got {len(keys)}")
+        return [keys[32 * i : 32 * (i + 1)] for i in range(len(keys) // 32)]
+
+    # ---- proving -----------------------------------------------------------------------------
+    @classmethod
+    def prove(
+        cls,
+        alpha: bytes,
+        additional_data: bytes,
+        secret_key: bytes,
+        producer_key: bytes,
+        ring: Ring,
+        ring_root: RingRoot | None = None,
+        salt: bytes = b"",
+        zk_rows: Sequence[int] | None = None,
+    ) -> "RingVRF":
+        """vrf/ring/vrf.py:185-209."""
+        return cls.prove_batch([alpha], [additional_data], secret_key, producer_key, ring, ring_root, salt=salt, zk_rows=zk_rows)[0]
+
+    @classmethod
+    def prove_batch(
+        cls,
+        alphas: Sequence[bytes],
+        additional_data: Sequence[bytes],
+        secret_key: bytes | Sequence[bytes],
+        producer_key: bytes | Sequence[bytes],
+        ring: Ring,
+        ring_root: RingRoot | None = None,
+        salt: bytes = b"",
+        zk_rows: Sequence[int] | None = None,
+        as_bytes: bool = False,
+    ):
+        """Prove ``len(alphas)`` items against one ring in one device pass; semantically a loop over ``prove``."""
+        n = len(alphas)
+        if len(additional_data) != n:
+            raise ValueError("alphas and additional_data must have the same length")
+        sks = [bytes(secret_key)] * n if isinstance(secret_key, (bytes, bytearray)) else [bytes(s) for s in secret_key]
+        pks = [bytes(producer_key)] * n if isinstance(producer_key, (bytes, bytearray)) else [bytes(p) for p in producer_key]
+        if len(sks) != n or len(pks) != n:
+            raise ValueError("secret_key / producer_key must be single values or one per item")
+        # vrf.py:196-197: producer_key must be pk(sk) -- one device scalar multiplication per distinct key pair
+        distinct = sorted(set(zip(sks, pks)))
+        derived = cls.cv.public_keys_from_secrets([sk for sk, _ in distinct])
+        for (_, pk), got in zip(distinct, derived):
+            if pk != got:
+                raise ValueError("producer_key does not match secret_key")
+        if ring_root is not None and ring_root.encode() != RingRoot.from_ring(ring).encode():
+            raise ValueError("ring_root does not match ring")
+        index = {pk: ring.index_of(pk) for _, pk in distinct}
+        if zk_rows is None and not ring.params.test_vectors:
+            prime = ring.params.prime
+            zk_rows = [secrets.randbelow(prime) for _ in range(12 * n)]
+        elif ring.params.test_vectors:
+            zk_rows = None
+        msgs = [bytes(salt) + bytes(a) for a in alphas]
+        proofs, status = ring.native.prove_batch(msgs, [bytes(a) for a in additional_data], sks, [index[pk] for pk in pks], zk_rows)
+        if any(status):
+            raise ValueError("producer_key does not match secret_key")
+        if as_bytes:
+            return proofs
+        return [cls._from_bytes_trusted(p) for p in proofs]
+
+
+class _LazyRingVRF:
+    """Field access on prover output decodes on demand; ``encode()`` is free."""
+
+    @staticmethod
+    def wrap(cls, proof: bytes) -> "RingVRF":
+        obj = object.__new__(cls)
+        object.__setattr__(obj, "_encoded", proof)
+        object.__setattr__(obj, "_lazy", True)
+        return obj
+
+
+def _lazy_getattr(self, name):
+    if name.startswith("__") or not object.__getattribute__(self, "__dict__").get("_lazy"):
+        raise AttributeError(name)
+    full = type(self).decode(object.__getattribute__(self, "_encoded"))
+    self.__dict__.update(full.__dict__)
+    self.__dict__["_lazy"] = False
+    return self.__dict__[name]
+
+
+RingVRF.__getattr__ = _lazy_getattr  # type: ignore[attr-defined]

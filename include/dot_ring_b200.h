@@ -136,6 +136,15 @@ int dr_ring_prove_phase_ms(dr_ctx* ctx, float out[6]);
 /* Proofs processed per internal pass (bounds device scratch: about 1 KiB * domain_size per proof). 0 = default 1024. */
 int dr_ctx_set_prove_chunk(dr_ctx* ctx, size_t chunk);
 
+/* ---- batched Bandersnatch point operations -------------------------------------------------------------
+ * dr_te_decode_batch replaces `dec_point` (dot_ring/vrf/codec.py:39-45) / `CurvePoint.string_to_point`
+ * (dot_ring/curve/point.py:178-214): ok[i] = 0 <=> the reference raises ValueError; checked != 0 adds the
+ * non-identity prime-subgroup test of `Curve.valid_point` (dot_ring/curve/curve.py:56-67).
+ * dr_te_mul_batch replaces `BandersnatchPoint.__mul__` (dot_ring/curve/specs/bandersnatch.py:177-191):
+ * out[i] = (scalars[i] mod order) * points[i] (or points[0] when n_points == 1). */
+int dr_te_decode_batch(dr_ctx* ctx, const uint8_t* in32, size_t n, int checked, uint8_t* out_xy64, uint8_t* ok);
+int dr_te_mul_batch(dr_ctx* ctx, const uint8_t* points32, size_t n_points, const uint8_t* scalars32, size_t n, uint8_t* out32, uint8_t* ok);
+
 /* ---- arithmetic-layer self test + integer-pipe ceilings ----------------------------------------
  * dr_field_op: element-wise Montgomery arithmetic on the device (reference equivalent:
  * dot_ring/curve/native_field/scalar.pyx:12-165 `Scalar`, tested by tests/test_curve_ops/test_native_field.py).

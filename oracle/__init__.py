@@ -23,3 +23,10 @@ _pedersen, _tiny; tests/vectors/others/ring_proof_*.json) copied as fixtures
 under ``tests/golden/reference_vectors/`` and against outputs of the unmodified
 reference run in the build container (``tests/golden/generate_golden.py``).
 """
+
+
+def backend_name() -> str:
+    """Which MSM the oracle is using: the plain-C restatement (oracle/c) or pure Python."""
+    from . import bls12_381
+
+    return "C Pippenger MSM + Python" if bls12_381._load_c_msm() else "pure Python"

@@ -144,7 +144,42 @@ def g1_eq(p1, p2) -> bool:
     return g1_to_affine(p1) == g1_to_affine(p2)
 
 
+_C_MSM = None
+
+
+def _load_c_msm():
+    """ctypes handle on oracle/c/liboracle_msm.so (plain-C Pippenger), or False when it is not built."""
+    global _C_MSM
+    if _C_MSM is None:
+        import ctypes
+        from pathlib import Path
+
+        so = Path(__file__).resolve().parent / "c" / "liboracle_msm.so"
+        try:
+            lib = ctypes.CDLL(str(so))
+            lib.oracle_g1_msm.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+            _C_MSM = lib
+        except OSError:
+            _C_MSM = False
+    return _C_MSM
+
+
 def g1_msm(points_affine, scalars, window: int | None = None):
+    """MSM entry point of the oracle: the C restatement when built (same algorithm, 64-bit limbs), else Python."""
+    lib = _load_c_msm()
+    n = min(len(points_affine), len(scalars))
+    if lib and window is None and n > 0 and all(p is not None for p in points_affine[:n]):
+        import ctypes
+
+        pts = b"".join(x.to_bytes(48, "big") + y.to_bytes(48, "big") for x, y in points_affine[:n])
+        ks = b"".join((int(k) % R).to_bytes(32, "little") for k in scalars[:n])
+        out = ctypes.create_string_buffer(96)
+        lib.oracle_g1_msm(pts, ks, n, out)
+        return g1_decompress(out.raw)
+    return g1_msm_python(points_affine, scalars, window)
+
+
+def g1_msm_python(points_affine, scalars, window: int | None = None):
     """Pippenger bucket MSM over affine (x, y) bases (None = infinity).
 
     Restates the semantics of blst ``P1_Affines.mult_pippenger`` as the

@@ -1,0 +1,112 @@
+"""CPU checks of the host-side mirror of the reference API (dot_ring_b200.Ring / RingRoot / RingVRF) and of the
+C-ABI surface.  The kernels run here through the *test-only* emulation build (tests/host/emul.py: same .cu
+sources compiled by g++, block after block on the CPU); the product package never selects it by itself.
+
+Mirrors the reference's tests/test_ark_vrf.py:118-132 (byte-exact ring root and proof) and the malformed-input
+cases of tests/test_ring_vrf/test_audit_regressions.py:30-114."""
+
+import ctypes
+
+import pytest
+
+import __graft_entry__ as entry
+from dot_ring_b200 import _native
+from dot_ring_b200 import engine as engine_mod
+from tests.helpers import hx, load, ring_proof_bytes, split_keys
+from tests.host.emul import emulation_library
+
+
+@pytest.fixture(scope="module")
+def api():
+    lib = emulation_library()
+    old = _native._default
+    _native.set_default_library(lib)
+    eng = engine_mod.Engine(0, window_bits=4, library=lib, srs_points=1537)
+    engine_mod.set_default_engine(eng, 0)
+    import dot_ring_b200 as pkg
+
+    yield pkg
+    engine_mod.set_default_engine(None, 0)
+    eng.close()
+    _native.set_default_library(old)
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    """No compute call: the CUDA build loads (libcudart only) and exports what include/dot_ring_b200.h declares."""
+    path = _native.DEFAULT_LIBRARY
+    if not path.exists():
+        pytest.skip("CUDA library not built (run ./build.sh)")
+    lib = ctypes.CDLL(str(path))
+    names = entry.declared_symbols()
+    assert len(names) >= 30
+    assert [n for n in names if not hasattr(lib, n)] == []
+    assert lib.dr_is_cuda_build() == 1
+
+
+def test_product_refuses_non_cuda_library():
+    lib = emulation_library()
+    with pytest.raises(ImportError):
+        _native.Library(lib.path, require_cuda=True)
+    with pytest.raises(ImportError):
+        _native.Library("/nonexistent/libdotring_b200.so")
+
+
+def test_ring_api_matches_reference_vectors(api):
+    vectors = load("bandersnatch_sha-512_ell2_ring.json")
+    params = api.RingProofParams(test_vectors=True)
+    for v in vectors[:2]:
+        keys = split_keys(hx(v, "ring_pks"))
+        ring = api.Ring(keys, params)
+        root = api.RingRoot.from_ring(ring, params)
+        assert root.encode().hex() == v["ring_pks_com"]
+        assert api.RingRoot.decode(root.encode(), params).encode() == root.encode()
+        proof = api.RingVRF[api.Bandersnatch].prove(hx(v, "alpha"), hx(v, "ad"), hx(v, "sk"), hx(v, "pk"), ring, root)
+        assert proof.encode() == ring_proof_bytes(v)
+        again = api.RingVRF[api.Bandersnatch].decode(proof.encode())
+        assert again.encode() == proof.encode() and again.l_zeta_omega == proof.l_zeta_omega
+
+
+def test_ring_api_error_behaviour(api):
+    v = load("bandersnatch_sha-512_ell2_ring.json")[0]
+    keys = split_keys(hx(v, "ring_pks"))
+    params = api.RingProofParams(test_vectors=True)
+    ring = api.Ring(keys, params)
+    cls = api.RingVRF[api.Bandersnatch]
+    other_pk = keys[(keys.index(hx(v, "pk")) + 1) % len(keys)]
+    with pytest.raises(ValueError):  # vrf/ring/vrf.py:196-197
+        cls.prove(hx(v, "alpha"), hx(v, "ad"), hx(v, "sk"), other_pk, ring)
+    outsider_pk, outsider_sk = api.Bandersnatch.secret_from_seed(b"\x07" * 32)
+    with pytest.raises(ValueError, match="not in ring"):  # members.py:71-81
+        cls.prove(b"a", b"b", outsider_sk, outsider_pk, ring)
+    with pytest.raises(ValueError):
+        cls.decode(b"\x00" * 783)
+    good = ring_proof_bytes(v)
+    bad_scalar = bytearray(good)
+    bad_scalar[192 + 192 : 192 + 224] = b"\xff" * 32  # px_zeta >= r
+    with pytest.raises(ValueError):
+        cls.decode(bytes(bad_scalar))
+    bad_g1 = bytearray(good)
+    bad_g1[192] ^= 0x80  # clears the compression flag of C_b
+    with pytest.raises(ValueError):
+        cls.decode(bytes(bad_g1))
+    with pytest.raises(ValueError):
+        api.RingRoot.decode(b"\x00" * 143, params)
+    with pytest.raises(ValueError):
+        api.Ring(keys * 40, params)  # 320 keys > max_ring_size 255
+    # undecodable keys become the padding point (members.py:36-41)
+    padded = api.Ring([b"\xff" * 32, keys[0]], params)
+    assert padded.nm_points[0] == params.cv.curve.params.auxiliary_points.padding_point
+
+
+def test_params_table(api):
+    """tests/test_coverage/test_params.py:66-88 size table."""
+    P = api.RingProofParams
+    for ring_size, domain, max_ring in [(8, 512, 255), (255, 512, 255), (256, 1024, 767), (1023, 2048, 1791), (1791, 2048, 1791), (1792, 4096, 3839)]:
+        p = P.from_ring_size(ring_size)
+        assert (p.domain_size, p.max_ring_size, p.radix_domain_size) == (domain, max_ring, 4 * domain)
+    with pytest.raises(ValueError):
+        P.from_ring_size(3840)  # domain 8192 > 4096
+    with pytest.raises(ValueError):
+        P.from_ring_size(0)
+    p = P.from_ring_size(1023)
+    assert pow(p.omega, 2048, p.prime) == 1 and pow(p.radix_omega, 4, p.prime) == p.omega
