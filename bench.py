@@ -68,11 +68,11 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.device = device
         self.samples: list[dict] = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self) -> None:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(
                     ["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5
@@ -82,10 +82,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append({"sm": float(f[0]), "max": float(f[1]), "power": float(f[2]), "reasons": f[3:7]})
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -93,6 +93,9 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i, r in enumerate(s["reasons"]) if r.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0]["max"], "power_w_max": max(s["power"] for s in self.samples), "reasons": reasons, "samples": len(sm)}
+
+
+DRY_RUN = os.environ.get("DOT_RING_B200_BENCH_DRYRUN") == "1"  # tests only: CPU emulation build + gloo
 
 
 def dist_setup(n_gpus: int):
@@ -105,37 +108,47 @@ def dist_setup(n_gpus: int):
     import torch
     import torch.distributed as dist
 
+    if DRY_RUN:
+        dist.init_process_group(backend="gloo")
+        return rank, local, world, dist
     torch.cuda.set_device(local)
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     return rank, local, world, dist
+
+
+def _device(local):
+    import torch
+
+    return torch.device("cpu") if DRY_RUN else torch.device("cuda", local)
 
 
 def barrier(dist, local):
     if dist is not None:
         import torch
 
+        if DRY_RUN:
+            dist.barrier()
+            return
         dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
 
-def reduce_max(dist, local, values: list[float]) -> list[float]:
+def _reduce(dist, local, values: list[float], op) -> list[float]:
     if dist is None:
         return values
     import torch
 
-    t = torch.tensor(values, dtype=torch.float64, device=torch.device("cuda", local))
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = torch.tensor(values, dtype=torch.float64, device=_device(local))
+    dist.all_reduce(t, op=op)
     return [float(x) for x in t.tolist()]
+
+
+def reduce_max(dist, local, values: list[float]) -> list[float]:
+    return _reduce(dist, local, values, None if dist is None else dist.ReduceOp.MAX)
 
 
 def reduce_sum(dist, local, values: list[float]) -> list[float]:
-    if dist is None:
-        return values
-    import torch
-
-    t = torch.tensor(values, dtype=torch.float64, device=torch.device("cuda", local))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return [float(x) for x in t.tolist()]
+    return _reduce(dist, local, values, None if dist is None else dist.ReduceOp.SUM)
 
 
 # -------------------------------------------------------------------------------------------------- ours
@@ -146,7 +159,15 @@ def run_ours(args) -> None:
     from dot_ring_b200 import engine as eng_mod
 
     t0 = time.perf_counter()
-    eng = eng_mod.Engine(local, window_bits=args.window_bits)
+    dry_run = DRY_RUN
+    library = None
+    if dry_run:
+        from tests.host.emul import emulation_library
+
+        library = emulation_library()
+    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library)
+    if not dry_run and not eng.ctx.library.is_cuda:
+        raise SystemExit("bench.py measures the CUDA build only")
     eng_mod.set_default_engine(eng, local)
     _ = eng.srs
     eng.ctx.sync()
@@ -180,7 +201,7 @@ def run_ours(args) -> None:
 
     launches0 = eng.ctx.library.launch_count()
     for w in range(args.warmup):
-        a, d, zk = inputs(-1 - w)
+        a, d, zk = inputs(500_000 + w)
         RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
     launches_warm = eng.ctx.library.launch_count()
 
@@ -204,8 +225,11 @@ def run_ours(args) -> None:
     launches = eng.ctx.library.launch_count() - launches_warm
 
     # integer-pipe ceiling measured live on this GPU (dependent-free mad.lo.u32, all SMs)
-    imad_peak, _ = eng.ctx.microbench("imad", 20000)
-    imad_wide_peak, _ = eng.ctx.microbench("imad_wide", 20000)
+    if dry_run:
+        imad_peak = imad_wide_peak = 148 * 64 * 1.965e9  # nominal; a dry run is not a measurement
+    else:
+        imad_peak, _ = eng.ctx.microbench("imad", 20000)
+        imad_wide_peak, _ = eng.ctx.microbench("imad_wide", 20000)
 
     mx = reduce_max(dist, local, [dev_ms, wall_s])
     proofs_total = batch * args.steps * world
@@ -216,6 +240,8 @@ def run_ours(args) -> None:
     executed = (sum(MSM_SIZES) * (-(-256 // args.window_bits)) * 10 * 600) * batch * args.steps / (commit_ms * 1e-3)
     table_traffic = sum(MSM_SIZES) * (-(-256 // args.window_bits)) * 96 * batch * args.steps  # algorithmic table bytes read
 
+    if dist is not None:
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -260,6 +286,8 @@ def run_ours(args) -> None:
         "phase_ms_per_step": {k: v / args.steps for k, v in zip(["pedersen+witness", "interpolate", "commit(msm)", "lde+constraints+quotient", "evals+openings", "transcripts+assembly"], phases)},
         "setup": {"srs_table_s": table_s, "ring_s": ring_s, "device": info["name"], "sm_count": info["sm_count"]},
     }
+    if dry_run:
+        line["dry_run"] = "CPU emulation of the kernels (tests only); not a measurement"
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single()
     print(json.dumps(line), flush=True)

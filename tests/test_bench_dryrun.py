@@ -1,0 +1,59 @@
+"""bench.py contract checks on the CPU: the JSON line, and the N>1 launch path under torchrun with gloo (world size 2).
+
+The kernels run through the test-only emulation build (DOT_RING_B200_BENCH_DRYRUN=1); the line is marked `dry_run`
+and is never a measurement.  The real bench refuses a non-CUDA library."""
+
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+KA1_ROOT_SHA256_PREFIX = "963f1e262eba87d5"  # ring 1023 root of the unmodified reference (tests/golden/ring1023_reference.json)
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "e2e", "gpu_launches", "clocks", "roofline"]  # fmt: skip
+
+
+def _run(cmd, timeout=900):
+    env = dict(os.environ, DOT_RING_B200_BENCH_DRYRUN="1")
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def _check_line(line, n_gpus, batch, steps):
+    for key in REQUIRED:
+        assert key in line, key
+    assert line["metric"] == "ring_vrf_proofs_per_s" and line["unit"] == "proofs/s"
+    assert line["n_gpus"] == n_gpus and line["steps"] == steps and line["scaling"] == "weak"
+    assert line["config"]["parity"].endswith(KA1_ROOT_SHA256_PREFIX)
+    assert abs(line["value"] * line["ms_per_step"] * 1e-3 - batch * n_gpus) < 1e-6 * batch * n_gpus
+    assert line["gpu_launches"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["value"] <= line["value"] * 1.001
+
+
+def test_bench_single_process_line():
+    line = _run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4", "--no-cpu-baseline"])
+    _check_line(line, 1, 1, 1)
+
+
+def test_bench_two_ranks_gloo():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29617",
+           "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4"]  # fmt: skip
+    line = _run(cmd)
+    _check_line(line, 2, 1, 1)
+    assert "cpu_baseline" not in line  # rank 0 at N=1 only
+
+
+def test_bench_refuses_cpu_library_without_dryrun():
+    env = {k: v for k, v in os.environ.items() if k != "DOT_RING_B200_BENCH_DRYRUN"}
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "0", "--batch", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0  # no GPU here: the product path must fail loudly, not fall back
