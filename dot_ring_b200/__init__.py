@@ -11,7 +11,7 @@ from .curve import Bandersnatch
 from .kzg import KZG
 from .params import RingProofParams
 from .ring import Ring, RingRoot
-from .vrf import PedersenVRF, RingVRF
+from .vrf import PedersenVRF, RingVRF, TinyVRF
 
-__all__ = ["Bandersnatch", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "__version__"]
+__all__ = ["Bandersnatch", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "TinyVRF", "__version__"]
 __version__ = "0.1.0"

@@ -86,6 +86,13 @@ class Library:
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
 
+        L.dr_pedersen_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
+        L.dr_pedersen_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_tiny_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_ring_proof_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int)]
+        L.dr_ring_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7 + [c_int, c_void_p, POINTER(c_int)]
+        L.dr_pairing_check_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_te_decode_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]
         L.dr_te_mul_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]
 
@@ -122,6 +129,66 @@ def set_default_library(lib: Library | None) -> None:
     """Test hook: inject an explicitly constructed Library (e.g. the tests/host emulation build)."""
     global _default
     _default = lib
+
+
+class VrfSuiteStruct(ctypes.Structure):
+    """dr_vrf_suite (include/dot_ring_b200.h)."""
+
+    _fields_ = [
+        ("suite_id_len", ctypes.c_uint32),
+        ("h2c_dst_len", ctypes.c_uint32),
+        ("suite_id", c_uint8 * 32),
+        ("h2c_dst", c_uint8 * 64),
+        ("generator", c_uint8 * 64),
+        ("blinding_base", c_uint8 * 64),
+    ]
+
+
+class VerifierKeyStruct(ctypes.Structure):
+    """dr_verifier_key (include/dot_ring_b200.h)."""
+
+    _fields_ = [
+        ("domain_size", ctypes.c_uint32),
+        ("label_len", ctypes.c_uint32),
+        ("label", c_uint8 * 32),
+        ("omega", c_uint8 * 32),
+        ("seed", c_uint8 * 64),
+        ("g1_0_be96", c_uint8 * 96),
+        ("g2_be192", c_uint8 * 384),
+        ("fixed_be96", c_uint8 * 288),
+    ]
+
+
+def _put(arr, data: bytes) -> None:
+    ctypes.memmove(arr, data, len(data))
+
+
+def _xy64(pt) -> bytes:
+    return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
+
+
+def make_suite(suite_id: bytes, h2c_dst: bytes, generator, blinding_base) -> VrfSuiteStruct:
+    s = VrfSuiteStruct()
+    s.suite_id_len, s.h2c_dst_len = len(suite_id), len(h2c_dst)
+    _put(s.suite_id, suite_id)
+    _put(s.h2c_dst, h2c_dst)
+    _put(s.generator, _xy64(generator))
+    _put(s.blinding_base, _xy64(blinding_base))
+    return s
+
+
+def pack_items(inputs: list[bytes], ads: list[bytes]):
+    """(blob, in_off, in_len, ad_off, ad_len) ctypes arrays for the batched entry points."""
+    n = len(inputs)
+    if len(ads) != n:
+        raise ValueError("inputs and additional data must have the same length")
+    blob = bytearray()
+    offs = [[], [], [], []]
+    for a, d in zip(inputs, ads):
+        offs[0].append(len(blob)); offs[1].append(len(a)); blob += a
+        offs[2].append(len(blob)); offs[3].append(len(d)); blob += d
+    U32 = ctypes.c_uint32 * max(n, 1)
+    return (bytes(blob) if blob else None, *[U32(*o) for o in offs])
 
 
 class Context:
@@ -215,6 +282,66 @@ class Context:
         ks = b"".join((int(k) % BANDERSNATCH_ORDER).to_bytes(32, "little") for k in scalars)
         self.library.check(self.library.lib.dr_te_mul_batch(self.handle, b"".join(points), len(points), ks, n, out, ok))
         return [out.raw[32 * i : 32 * i + 32] if ok.raw[i] else None for i in range(n)]
+
+    # ---- verification ---------------------------------------------------------------------------
+    def pedersen_verify(self, suite: VrfSuiteStruct, inputs: list[bytes], ads: list[bytes], proofs: list[bytes]) -> list[int]:
+        """Per item: 1 valid, 0 invalid, 2 malformed (PedersenVRF.decode would raise ValueError)."""
+        n = len(proofs)
+        if any(len(p) != 192 for p in proofs):
+            raise ValueError("invalid Pedersen VRF proof length: expected 192")
+        blob, a, b, c, d = pack_items(inputs, ads)
+        out = ctypes.create_string_buffer(max(n, 1))
+        self.library.check(self.library.lib.dr_pedersen_verify_batch(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(proofs), out))
+        return list(out.raw[:n])
+
+    def tiny_verify(self, suite: VrfSuiteStruct, public_keys: list[bytes], inputs: list[bytes], ads: list[bytes], proofs: list[bytes]) -> list[int]:
+        n = len(proofs)
+        if any(len(p) != 80 for p in proofs):
+            raise ValueError("invalid Tiny VRF proof length: expected 80")
+        if len(public_keys) != n or any(len(k) != 32 for k in public_keys):
+            raise ValueError("public keys must be 32 bytes, one per proof")
+        blob, a, b, c, d = pack_items(inputs, ads)
+        out = ctypes.create_string_buffer(max(n, 1))
+        self.library.check(
+            self.library.lib.dr_tiny_verify_batch(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(public_keys), b"".join(proofs), out)
+        )
+        return list(out.raw[:n])
+
+    def vrf_prove(self, scheme: str, suite: VrfSuiteStruct, inputs: list[bytes], ads: list[bytes], secret_keys: list[bytes]) -> list[bytes]:
+        """Batched `PedersenVRF.prove` ('pedersen', 192-byte proofs) / `TinyVRF.prove` ('tiny', 80 bytes)."""
+        n = len(inputs)
+        if len(secret_keys) != n or any(len(k) != 32 for k in secret_keys):
+            raise ValueError("secret keys must be 32 bytes, one per item")
+        size = {"pedersen": 192, "tiny": 80}[scheme]
+        fn = self.library.lib.dr_pedersen_prove_batch if scheme == "pedersen" else self.library.lib.dr_tiny_prove_batch
+        blob, a, b, c, d = pack_items(inputs, ads)
+        out = ctypes.create_string_buffer(size * max(n, 1))
+        self.library.check(fn(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(secret_keys), out))
+        return [out.raw[size * i : size * i + size] for i in range(n)]
+
+    def ring_proof_verify(self, key: VerifierKeyStruct, relations: list[tuple[int, int]], payloads: list[bytes], coeffs: list[int], aggregate: bool = False):
+        """`Verify(...).is_valid()` for a batch under an explicit verifier key -> (verdicts, all_ok)."""
+        n = len(payloads)
+        if any(len(p) != 592 for p in payloads) or len(relations) != n or len(coeffs) != 2 * n:
+            raise ValueError("bad ring-proof verification batch")
+        out = ctypes.create_string_buffer(max(n, 1))
+        all_ok = c_int(0)
+        self.library.check(
+            self.library.lib.dr_ring_proof_verify_batch(
+                self.handle, ctypes.byref(key), n, b"".join(_xy64(r) for r in relations), b"".join(payloads),
+                b"".join(int(v).to_bytes(32, "little") for v in coeffs), 1 if aggregate else 0, out, ctypes.byref(all_ok),
+            )
+        )
+        return list(out.raw[:n]), bool(all_ok.value)
+
+    def pairing_check(self, a1_be96: bytes, b1_be192: bytes, a2_be96: bytes, b2_be192: bytes) -> list[bool]:
+        """[e(a1_i, b1_i) == e(a2_i, b2_i)] for concatenated uncompressed encodings (pairing.py:24-31)."""
+        n = len(a1_be96) // 96
+        if not (len(a2_be96) == 96 * n and len(b1_be192) == 192 * n and len(b2_be192) == 192 * n):
+            raise ValueError("mismatched pairing operand lengths")
+        out = ctypes.create_string_buffer(max(n, 1))
+        self.library.check(self.library.lib.dr_pairing_check_batch(self.handle, a1_be96, b1_be192, a2_be96, b2_be192, n, out))
+        return [bool(b) for b in out.raw[:n]]
 
     def g1_compress(self, points_be96: bytes) -> bytes:
         count = len(points_be96) // 96
@@ -391,6 +518,25 @@ class NativeRing:
         )
         raw = proofs.raw
         return [raw[784 * i : 784 * i + 784] for i in range(n)], [int(status[i]) for i in range(n)]
+
+    def verify_batch(self, inputs: list[bytes], ads: list[bytes], proofs: list[bytes], coeffs: list[int], aggregate: bool = False):
+        """RingVRF decode + verify for 784-byte proofs -> (per-item verdicts 1 / 0 / 2, all_ok)."""
+        n = len(proofs)
+        if any(len(p) != 784 for p in proofs):
+            raise ValueError("invalid Ring VRF proof length: Ring VRF proof must be exactly 784 bytes")
+        if len(coeffs) != 2 * n:
+            raise ValueError("two batching coefficients per proof are required")
+        blob, a, b, c, d = pack_items(inputs, ads)
+        out = ctypes.create_string_buffer(max(n, 1))
+        all_ok = c_int(0)
+        lib = self.ctx.library
+        lib.check(
+            lib.lib.dr_ring_verify_batch(
+                self.ctx.handle, self.handle, n, blob, a, b, c, d, b"".join(proofs), b"".join(int(v).to_bytes(32, "little") for v in coeffs),
+                1 if aggregate else 0, out, ctypes.byref(all_ok),
+            )
+        )
+        return list(out.raw[:n]), bool(all_ok.value)
 
     def prove_phase_ms(self) -> list[float]:
         arr = (c_float * 6)()

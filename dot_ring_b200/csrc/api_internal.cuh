@@ -11,8 +11,11 @@
 #include "hash.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "pairing.cuh"
+#include "ring.cuh"
 #include "rt.cuh"
 #include "te.cuh"
+#include "verify.cuh"
 
 namespace dr {
 
@@ -59,6 +62,15 @@ struct Ctx {
     PhaseTimer phases;
     std::shared_ptr<void> prove_scratch;
     size_t prove_chunk = 0;
+    bool have_pairing_consts = false;
+    PairingConsts pairing_k;
+    const PairingConsts& pairing_consts() {
+        if (!have_pairing_consts) {
+            pairing_k = pairing_consts_host();
+            have_pairing_consts = true;
+        }
+        return pairing_k;
+    }
 
     void activate() {
 #if !defined(DR_HOST_EMULATION)
@@ -81,6 +93,25 @@ struct Srs {
     uint8_t g1_0_be96[96];
     uint8_t g2_be192[384];
 };
+
+struct Ring {
+    Ctx* ctx = nullptr;
+    Srs* srs = nullptr;
+    RingDev dev{};
+    DevBuf<TEAffine> nm;
+    DevBuf<Fr> fixed_coef, fixed_lde, w4, w4inv;
+    DevBuf<Shake128> prefix;
+    G1Affine commitments[3];
+    uint8_t commit_be96[288];
+    uint8_t root144[144];
+    TEAffine padding;
+    VerifierKeyDev vk{};
+    SuiteDev suite{};
+};
+
+
+VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TEAffine& seed, const uint8_t* label, uint32_t label_len, const uint8_t* g1_0_be96,
+                                 const uint8_t* g2_be192, const uint8_t* fixed_be96);
 
 // scalars: `batch` vectors of n Montgomery Fr, vector b at scalars + b*stride.  Result: affine points.
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine);

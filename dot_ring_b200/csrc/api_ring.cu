@@ -4,19 +4,6 @@
 
 namespace dr {
 
-struct Ring {
-    Ctx* ctx = nullptr;
-    Srs* srs = nullptr;
-    RingDev dev{};
-    DevBuf<TEAffine> nm;
-    DevBuf<Fr> fixed_coef, fixed_lde, w4, w4inv;
-    DevBuf<Shake128> prefix;
-    G1Affine commitments[3];
-    uint8_t commit_be96[288];
-    uint8_t root144[144];
-    TEAffine padding;
-};
-
 static Fr fr_from_param(const uint8_t* b) {
     Fr r;
     fr_from_le_bytes_raw(r, b);
@@ -227,6 +214,13 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
         h2d(ctx->stream, ring->prefix.p, &tr, sizeof(Shake128));
         stream_sync(ctx->stream);
     }
+    ring->vk = make_verifier_key(ctx, N, d.omega, d.seed, d.suite_id, d.suite_id_len, srs->g1_0_be96, srs->g2_be192, ring->commit_be96);
+    ring->suite.generator = d.generator;
+    ring->suite.blinding_base = d.blinding_base;
+    ring->suite.suite_id_len = d.suite_id_len;
+    memcpy(ring->suite.suite_id, d.suite_id, 32);
+    ring->suite.dst_len = d.dst_len;
+    memcpy(ring->suite.dst, d.dst, 64);
     *out = (dr_ring*)ring.release();
     DR_API_END
 }

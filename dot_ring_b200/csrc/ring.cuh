@@ -160,7 +160,8 @@ DR_HD void sha_absorb_point(Sha512& s, const TEAffine& p) {
 }
 
 // expand_message_xmd(SHA-512) for 96 output bytes (curve.py:145-185; Z_pad = 48 bytes for this suite)
-DR_HD_COLD void h2c_uniform_bytes(const RingDev& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
+template <class S>
+DR_HD_COLD void h2c_uniform_bytes(const S& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
     uint8_t dst_prime_len = (uint8_t)rg.dst_len;
     Sha512 h;
     h.init();
@@ -188,13 +189,66 @@ DR_HD_COLD void h2c_uniform_bytes(const RingDev& rg, const uint8_t* msg, uint32_
         for (int i = 0; i < 64 && 64 * (blk - 1) + i < 96; i++) out96[64 * (blk - 1) + i] = prev[i];
     }
 }
-DR_HD TEAffine vrf_encode_to_curve(const RingDev& rg, const uint8_t* msg, uint32_t msg_len) {
+template <class S>
+DR_HD TEAffine vrf_encode_to_curve(const S& rg, const uint8_t* msg, uint32_t msg_len) {
     uint8_t u[96];
     h2c_uniform_bytes(rg, msg, msg_len, u);
     return te_encode_to_curve_from_u(fr_from_be48_mod(u), fr_from_be48_mod(u + 48));
 }
 
-// ---- A. Pedersen VRF prove (pedersen/vrf.py:86-126), one thread per proof -------------------------------
+// ---- A. Pedersen VRF prove (pedersen/vrf.py:86-126) -------------------------------------------------------
+// Writes O | Ybar | R | Ok | s | sb; returns the public key, the blinded key and the blinding factor.
+template <class S>
+DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint8_t* msg, uint32_t msg_len, const uint8_t* ad, uint32_t ad_len, uint8_t* out192,
+                                    TEAffine& pk, TEAffine& blinded, uint32_t* blinding_raw) {
+    Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
+    pk = te_mul_fn(rg.generator, x);
+    TEAffine input = vrf_encode_to_curve(rg, msg, msg_len);
+    TEAffine output = te_mul_fn(input, x);
+    // vrf_transcript (primitives.py:102-144) with one I/O pair
+    Sha512 tr;
+    tr.init();
+    tr.update(rg.suite_id, rg.suite_id_len);
+    tr.update_byte(0x02);
+    uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    tr.update(le, 8);
+    sha_absorb_point(tr, input);
+    sha_absorb_point(tr, output);
+    for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(ad_len >> (8 * i)) : 0;
+    tr.update(le, 8);
+    tr.update(ad, ad_len);
+    // blinding factor
+    Sha512 tb = tr;
+    tb.update_byte(0x12);
+    Fn b = vrf_nonce(tb, x);
+    TEAffine bb = te_mul_fn(rg.blinding_base, b);
+    blinded = te_to_affine(te_add(TEExt::from_affine(pk), TEExt::from_affine(bb)));
+    sha_absorb_point(tr, blinded);
+    Fn k = vrf_nonce(tr, x);
+    Fn kb = vrf_nonce(tr, b);
+    TEAffine kg = te_mul_fn(rg.generator, k);
+    TEAffine kbb = te_mul_fn(rg.blinding_base, kb);
+    TEAffine R = te_to_affine(te_add(TEExt::from_affine(kg), TEExt::from_affine(kbb)));
+    TEAffine ok = te_mul_fn(input, k);
+    Sha512 tc = tr;
+    tc.update_byte(0x40);
+    sha_absorb_point(tc, R);
+    sha_absorb_point(tc, ok);
+    uint8_t cb[16];
+    vrf_squeeze(tc, cb, 16);
+    Fn c = fp_from_le_bytes_mod<Fn>(cb, 16);
+    Fn s = k + c * x;
+    Fn sb = kb + c * b;
+    te_encode(out192, output);
+    te_encode(out192 + 32, blinded);
+    te_encode(out192 + 64, R);
+    te_encode(out192 + 96, ok);
+    fn_to_le_bytes(out192 + 128, s);
+    fn_to_le_bytes(out192 + 160, sb);
+    fn_raw_limbs(blinding_raw, b);
+}
+
+// one thread per proof
 struct PedersenProveBody {
     DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProveInput* in, const uint8_t* blob, ProofState* st, uint32_t count) const {
         DR_THREAD_LOOP(t, ctx) {
@@ -202,51 +256,8 @@ struct PedersenProveBody {
             if (p < count) {
                 const ProveInput& pi = in[p];
                 ProofState& ps = st[p];
-                Fn x = fp_from_le_bytes_mod<Fn>(pi.sk, 32);
-                TEAffine pk = te_mul_fn(rg.generator, x);
-                TEAffine input = vrf_encode_to_curve(rg, blob + pi.alpha_off, pi.alpha_len);
-                TEAffine output = te_mul_fn(input, x);
-                // vrf_transcript (primitives.py:102-144) with one I/O pair
-                Sha512 tr;
-                tr.init();
-                tr.update(rg.suite_id, rg.suite_id_len);
-                tr.update_byte(0x02);
-                uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-                tr.update(le, 8);
-                sha_absorb_point(tr, input);
-                sha_absorb_point(tr, output);
-                for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(pi.ad_len >> (8 * i)) : 0;
-                tr.update(le, 8);
-                tr.update(blob + pi.ad_off, pi.ad_len);
-                // blinding factor
-                Sha512 tb = tr;
-                tb.update_byte(0x12);
-                Fn b = vrf_nonce(tb, x);
-                TEAffine bb = te_mul_fn(rg.blinding_base, b);
-                TEAffine blinded = te_to_affine(te_add(TEExt::from_affine(pk), TEExt::from_affine(bb)));
-                sha_absorb_point(tr, blinded);
-                Fn k = vrf_nonce(tr, x);
-                Fn kb = vrf_nonce(tr, b);
-                TEAffine kg = te_mul_fn(rg.generator, k);
-                TEAffine kbb = te_mul_fn(rg.blinding_base, kb);
-                TEAffine R = te_to_affine(te_add(TEExt::from_affine(kg), TEExt::from_affine(kbb)));
-                TEAffine ok = te_mul_fn(input, k);
-                Sha512 tc = tr;
-                tc.update_byte(0x40);
-                sha_absorb_point(tc, R);
-                sha_absorb_point(tc, ok);
-                uint8_t cb[16];
-                vrf_squeeze(tc, cb, 16);
-                Fn c = fp_from_le_bytes_mod<Fn>(cb, 16);
-                Fn s = k + c * x;
-                Fn sb = kb + c * b;
-                te_encode(ps.pedersen, output);
-                te_encode(ps.pedersen + 32, blinded);
-                te_encode(ps.pedersen + 64, R);
-                te_encode(ps.pedersen + 96, ok);
-                fn_to_le_bytes(ps.pedersen + 128, s);
-                fn_to_le_bytes(ps.pedersen + 160, sb);
-                fn_raw_limbs(ps.t, b);
+                TEAffine pk, blinded;
+                pedersen_prove_core(rg, pi.sk, blob + pi.alpha_off, pi.alpha_len, blob + pi.ad_off, pi.ad_len, ps.pedersen, pk, blinded, ps.t);
                 ps.k = pi.k;
                 ps.relation = blinded;
                 // producer_key must be pk(sk) and sit at row k of the ring (vrf/ring/vrf.py:196-197, members.py:71-81)

@@ -1,0 +1,510 @@
+// Verification kernels (batched): Tiny / Pedersen VRF verification and the ring-proof verifier.
+//
+// Device restatement of
+//   dot_ring/vrf/ietf/tiny.py:72-83                     TinyVRF.verify
+//   dot_ring/vrf/pedersen/vrf.py:48-73,128-143          PedersenVRF.decode / verify
+//   dot_ring/vrf/primitives.py:85-144                   challenge, vrf_transcript, delinearisation
+//   dot_ring/ring_proof/proof_payload.py:93-143         payload decode (lengths, canonical scalars, G1 validity)
+//   dot_ring/ring_proof/transcript/phases.py:46-69      derive_challenges_after_vk
+//   dot_ring/ring_proof/verify.py:51-210                quotient / linearisation terms, two LinearPcsVerifications
+//   dot_ring/ring_proof/pcs/kzg.py:56-108,304-338       random-linear-combined KZG check, 2 Miller loops + final exp
+// Work is split so that every launch has (items x sub-tasks) threads: point decodes (sqrt + subgroup check) and
+// G1 scalar multiplications are one thread per (item, point); transcripts / scalar algebra / pairing are one
+// thread per item.  Verdict codes: 1 valid, 0 invalid, 2 malformed (where the reference raises ValueError).
+#pragma once
+#include "pairing.cuh"
+#include "ring.cuh"
+
+namespace dr {
+
+struct SuiteDev {  // VRF suite constants (dot_ring/curve/specs/bandersnatch.py:48-107)
+    TEAffine generator, blinding_base;
+    uint32_t suite_id_len;
+    uint8_t suite_id[32];
+    uint32_t dst_len;
+    uint8_t dst[64];
+};
+
+struct VerifyInput {  // host-packed per item: salt|alpha and ad inside the blob
+    uint32_t in_off, in_len, ad_off, ad_len;
+};
+
+constexpr uint32_t ST_MALFORMED = 1, ST_PEDERSEN_BAD = 2;
+
+DR_HD void load_le_limbs8(uint32_t* out, const uint8_t* in, int nbytes) {
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (int b = 0; b < nbytes; b++) out[b >> 2] |= (uint32_t)in[b] << (8 * (b & 3));
+}
+DR_HD void neg_affine_inplace(TEAffine& p) { p.x = p.x.neg(); }
+
+// ---- decode + subgroup check, one thread per point (vrf/codec.py:39-45) ------------------------------------
+// in: count encodings of 32 bytes at in + stride*(i / per_item) + 32*(i % per_item)
+struct TeDecodeManyBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* in, uint32_t stride, uint32_t per_item, uint32_t count, TEAffine* out, uint8_t* ok) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                TEAffine p;
+                bool good = te_decode_checked(p, in + (size_t)stride * (i / per_item) + 32 * (i % per_item));
+                out[i] = good ? p : TEAffine::identity();
+                ok[i] = good ? 1 : 0;
+            }
+        }
+    }
+};
+
+// Pedersen verification equations for one decoded proof; pts = O, Ybar, R, Ok.  Returns status bits.
+template <class S>
+DR_HD_COLD uint32_t pedersen_verify_core(const S& su, const TEAffine* pts, const uint8_t* ok4, const uint8_t* proof192, const uint8_t* msg, uint32_t msg_len,
+                                         const uint8_t* ad, uint32_t ad_len) {
+    if (!(ok4[0] && ok4[1] && ok4[2] && ok4[3])) return ST_MALFORMED;
+    uint32_t ks[3][8];
+    load_le_limbs8(ks[0], proof192 + 128, 32);  // s
+    load_le_limbs8(ks[1], proof192 + 160, 32);  // sb
+    if (Fn::geq_mod(ks[0]) || Fn::geq_mod(ks[1])) return ST_MALFORMED;
+    TEAffine input = vrf_encode_to_curve(su, msg, msg_len);
+    Sha512 tr;
+    tr.init();
+    tr.update(su.suite_id, su.suite_id_len);
+    tr.update_byte(0x02);
+    uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    tr.update(le, 8);
+    sha_absorb_point(tr, input);
+    sha_absorb_point(tr, pts[0]);
+    for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(ad_len >> (8 * i)) : 0;
+    tr.update(le, 8);
+    tr.update(ad, ad_len);
+    sha_absorb_point(tr, pts[1]);
+    tr.update_byte(0x40);
+    sha_absorb_point(tr, pts[2]);
+    sha_absorb_point(tr, pts[3]);
+    uint8_t cb[16];
+    vrf_squeeze(tr, cb, 16);
+    uint32_t c[8];
+    load_le_limbs8(c, cb, 16);
+    // s*I - c*O == Ok
+    TEAffine p2[3];
+    uint32_t k2[3][8];
+    p2[0] = input;
+    p2[1] = te_neg(pts[0]);
+    for (int i = 0; i < 8; i++) {
+        k2[0][i] = ks[0][i];
+        k2[1][i] = c[i];
+    }
+    bool ok = te_ext_eq_affine(te_msm_small(p2, k2, 2), pts[3]);
+    // s*G + sb*B - c*Ybar == R
+    p2[0] = su.generator;
+    p2[1] = su.blinding_base;
+    p2[2] = te_neg(pts[1]);
+    for (int i = 0; i < 8; i++) {
+        k2[1][i] = ks[1][i];
+        k2[2][i] = c[i];
+    }
+    ok = ok && te_ext_eq_affine(te_msm_small(p2, k2, 3), pts[2]);
+    return ok ? 0u : ST_PEDERSEN_BAD;
+}
+
+// one thread per proof; pts / ok hold the 4 decoded points of every proof
+struct PedersenVerifyBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t proof_stride, const TEAffine* pts,
+                          const uint8_t* ok, uint32_t count, uint32_t* status) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                status[i] = pedersen_verify_core(su, pts + 4 * (size_t)i, ok + 4 * (size_t)i, proofs + (size_t)proof_stride * i, blob + vi.in_off, vi.in_len, blob + vi.ad_off,
+                                                 vi.ad_len);
+            }
+        }
+    }
+};
+
+// Tiny (IETF) verification, one thread per item; pts = [O_i, PK_i] decoded by TeDecodeManyBody.
+// proofs80: O (32) | c (16) | s (32).  status bit0 malformed, bit1 invalid.
+struct TinyVerifyBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs80, const TEAffine* pts, const uint8_t* ok,
+                          uint32_t count, uint32_t* status) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                const uint8_t* pr = proofs80 + 80 * (size_t)i;
+                uint32_t st = 0;
+                uint32_t ks[2][8];
+                load_le_limbs8(ks[0], pr + 48, 32);  // s
+                load_le_limbs8(ks[1], pr + 32, 16);  // c
+                if (!ok[2 * (size_t)i] || !ok[2 * (size_t)i + 1] || Fn::geq_mod(ks[0])) st = ST_MALFORMED;
+                if (!st) {
+                    const TEAffine out = pts[2 * (size_t)i], pk = pts[2 * (size_t)i + 1];
+                    TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
+                    Sha512 tr;
+                    tr.init();
+                    tr.update(su.suite_id, su.suite_id_len);
+                    tr.update_byte(0x00);
+                    uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+                    tr.update(le, 8);
+                    sha_absorb_point(tr, su.generator);
+                    sha_absorb_point(tr, pk);
+                    sha_absorb_point(tr, input);
+                    sha_absorb_point(tr, out);
+                    for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
+                    tr.update(le, 8);
+                    tr.update(blob + vi.ad_off, vi.ad_len);
+                    // delinearisation scalar z (primitives.py:128-144), merged pair (G + z I, PK + z O)
+                    Sha512 td = tr;
+                    td.update_byte(0x30);
+                    uint8_t zb[16];
+                    vrf_squeeze(td, zb, 16);
+                    uint32_t z[8];
+                    load_le_limbs8(z, zb, 16);
+                    TEExt min = te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4));
+                    TEExt mout = te_add(TEExt::from_affine(pk), te_mul_raw(out, z, 4));
+                    TEAffine p2[2] = {te_to_affine(min), te_neg(te_to_affine(mout))};
+                    TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
+                    tr.update_byte(0x40);
+                    sha_absorb_point(tr, r);
+                    uint8_t cb[16];
+                    vrf_squeeze(tr, cb, 16);
+                    bool same = true;
+                    for (int b = 0; b < 16; b++) same = same && (cb[b] == pr[32 + b]);
+                    if (!same) st = ST_PEDERSEN_BAD;
+                }
+                status[i] = st;
+            }
+        }
+    }
+};
+
+// ---- standalone provers (pedersen/vrf.py:86-126, ietf/tiny.py:35-70), one thread per item -------------------------
+struct PedersenProveStandaloneBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count, uint8_t* out192) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                TEAffine pk, blinded;
+                uint32_t braw[8];
+                pedersen_prove_core(su, sks32 + 32 * (size_t)i, blob + vi.in_off, vi.in_len, blob + vi.ad_off, vi.ad_len, out192 + 192 * (size_t)i, pk, blinded, braw);
+            }
+        }
+    }
+};
+
+struct TinyProveBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count, uint8_t* out80) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                Fn x = fp_from_le_bytes_mod<Fn>(sks32 + 32 * (size_t)i, 32);
+                TEAffine pk = te_mul_fn(su.generator, x);
+                TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
+                TEAffine output = te_mul_fn(input, x);
+                Sha512 tr;
+                tr.init();
+                tr.update(su.suite_id, su.suite_id_len);
+                tr.update_byte(0x00);
+                uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+                tr.update(le, 8);
+                sha_absorb_point(tr, su.generator);
+                sha_absorb_point(tr, pk);
+                sha_absorb_point(tr, input);
+                sha_absorb_point(tr, output);
+                for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
+                tr.update(le, 8);
+                tr.update(blob + vi.ad_off, vi.ad_len);
+                Sha512 td = tr;
+                td.update_byte(0x30);
+                uint8_t zb[16];
+                vrf_squeeze(td, zb, 16);
+                uint32_t z[8];
+                load_le_limbs8(z, zb, 16);
+                TEAffine min = te_to_affine(te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4)));
+                Fn k = vrf_nonce(tr, x);
+                TEAffine r = te_mul_fn(min, k);
+                tr.update_byte(0x40);
+                sha_absorb_point(tr, r);
+                uint8_t* o = out80 + 80 * (size_t)i;
+                vrf_squeeze(tr, o + 32, 16);
+                Fn c = fp_from_le_bytes_mod<Fn>(o + 32, 16);
+                te_encode(o, output);
+                fn_to_le_bytes(o + 48, k + c * x);
+            }
+        }
+    }
+};
+
+// ---- ring-proof verifier ------------------------------------------------------------------------------------
+struct VerifierKeyDev {
+    uint32_t N, logN;
+    Fr omega, w_last, n_inv;
+    Fr tail[4];         // coefficients of (X - w^(N-1))(X - w^(N-2))(X - w^(N-3))
+    TEAffine seed;      // accumulator base
+    G1Affine fixed[4];  // C_px, C_py, C_s, [1]_1
+    G2Affine g2[2];     // [1]_2, [tau]_2
+    PairingConsts pc;
+    Shake128 prefix;    // transcript after absorbing the verifier key (root.py:54-71)
+};
+
+constexpr int VERIFY_TERMS = 13;  // scalar multiplications per proof (see RingVerifyAlgebraBody)
+
+struct VerifyState {
+    uint32_t status;
+    G1Affine g1[7];  // C_b, C_accip, C_accx, C_accy, C_q, Phi_zeta, Phi_zeta_omega
+    Fr sc[VERIFY_TERMS];
+    G1 term[VERIFY_TERMS];
+};
+
+// 7 G1 decompressions per payload, one thread per point (proof_payload.py:93-118, kzg.py:137-144)
+struct PayloadG1DecodeBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* payloads, uint32_t stride, uint32_t count, VerifyState* vs) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < 7 * count) {
+                uint32_t p = i / 7, j = i % 7;
+                const uint32_t off[7] = {0, 48, 96, 144, 416, 496, 544};
+                G1Affine a;
+                bool good = g1_decode(a, payloads + (size_t)stride * p + off[j], 48);
+                vs[p].g1[j] = good ? a : G1Affine::inf();
+                if (!good) vs[p].status = ST_MALFORMED;  // racing writers store the same value
+            }
+        }
+    }
+};
+
+// Challenges + scalar algebra for one payload (phases.py:46-69, verify.py:51-210), then the 13 scalars of the
+// random-linear-combined check with coefficients (ra, rb) for the proof's two openings:
+//   lhs = sum_j sc[j]*g1[j] (j<7) + sc[9]*C_px + sc[10]*C_py + sc[11]*C_s + sc[12]*[1]_1,  rhs = sc[7]*Phi_zeta + sc[8]*Phi_zeta_omega
+//   accept  <=>  e(lhs, [1]_2) == e(rhs, [tau]_2)
+struct RingVerifyAlgebraBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, const uint8_t* payloads, uint32_t stride, const TEAffine* relations, uint32_t rel_stride,
+                          const uint8_t* coeffs_le32, uint32_t count, VerifyState* vs) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                VerifyState& s = vs[p];
+                const uint8_t* pl = payloads + (size_t)stride * p;
+                // evaluations px, py, s, b, accip, accx, accy at zeta and L(zeta w): canonical scalars only
+                Fr ev[8];
+                bool canon = true;
+                for (int i = 0; i < 8; i++) {
+                    Fr raw;
+                    fr_from_le_bytes_raw(raw, pl + (i < 7 ? 192 + 32 * i : 464));
+                    canon = canon && raw.is_canonical_raw();
+                    ev[i] = raw.to_mont();
+                }
+                if (!canon) s.status |= ST_MALFORMED;
+                Fr ra, rb;
+                fr_from_le_bytes_raw(ra, coeffs_le32 + 64 * (size_t)p);
+                fr_from_le_bytes_raw(rb, coeffs_le32 + 64 * (size_t)p + 32);
+                ra = ra.to_mont();
+                rb = rb.to_mont();
+                const TEAffine rel = relations[(size_t)rel_stride * p];
+                // ---- transcript
+                Shake128 tr = vk.prefix;
+                shake_absorb_label(tr, "instance", 8);
+                shake_absorb_fr(tr, rel.x);
+                shake_absorb_fr(tr, rel.y);
+                tr.absorb_be32(64);
+                shake_absorb_label(tr, "committed_cols", 14);
+                for (int i = 0; i < 4; i++) shake_absorb_g1(tr, s.g1[i]);
+                tr.absorb_be32(4 * 96);
+                Fr alpha[7], zeta, nu[8];
+                shake_challenges(tr, "constraints_aggregation", 23, alpha, 7);
+                shake_absorb_label(tr, "quotient", 8);
+                shake_absorb_g1(tr, s.g1[4]);
+                tr.absorb_be32(96);
+                shake_challenges(tr, "evaluation_point", 16, &zeta, 1);
+                shake_absorb_label(tr, "register_evaluations", 20);
+                tr.absorb(pl + 192, 7 * 32);
+                tr.absorb_be32(7 * 32);
+                shake_absorb_label(tr, "shifted_linearization_evaluation", 32);
+                tr.absorb(pl + 464, 32);
+                tr.absorb_be32(32);
+                shake_challenges(tr, "kzg_aggregation", 15, nu, 8);
+                // ---- verify.py:51-144
+                const Fr one = Fr::one();
+                Fr zn = zeta;
+                for (uint32_t i = 0; i < vk.logN; i++) zn = zn.sqr();
+                Fr zn1 = zn - one, zm1 = zeta - one, zml = zeta - vk.w_last;
+                // three inversions by Montgomery's trick; a zero denominator makes the reference raise -> invalid
+                bool degenerate = zn1.is_zero();
+                Fr d1 = zm1.is_zero() ? one : zm1, d2 = zml.is_zero() ? one : zml, d0 = degenerate ? one : zn1;
+                Fr p01 = d0 * d1;
+                Fr inv_all = (p01 * d2).inv();
+                Fr inv_zml = inv_all * p01;
+                Fr inv01 = inv_all * d2;
+                Fr inv_zn1 = inv01 * d1, inv_zm1 = inv01 * d0;
+                Fr l0 = zm1.is_zero() ? one : vk.n_inv * zn1 * inv_zm1;
+                Fr ln = zml.is_zero() ? one : vk.w_last * vk.n_inv * zn1 * inv_zml;
+                const Fr &x2 = ev[0], &y2 = ev[1], &sz = ev[2], &b = ev[3], &aip = ev[4], &x1 = ev[5], &y1 = ev[6], &lzw = ev[7];
+                Fr omb = one - b;
+                Fr x1y1 = x1 * y1, x2y2 = x2 * y2;
+                TEAffine rps = te_to_affine(te_add(TEExt::from_affine(vk.seed), TEExt::from_affine(rel)));
+                Fr cv[7];
+                cv[0] = (aip + b * sz).neg() * zml;
+                cv[1] = (b * (x1y1 + x2y2).neg() + omb * x1.neg()) * zml;
+                cv[2] = (b * (x1y1 - x2y2).neg() + omb * y1.neg()) * zml;
+                cv[3] = b * omb;
+                cv[4] = (x1 - vk.seed.x) * l0 + (x1 - rps.x) * ln;
+                cv[5] = (y1 - vk.seed.y) * l0 + (y1 - rps.y) * ln;
+                cv[6] = aip * l0 + (aip - one) * ln;
+                Fr lin = Fr::zero();
+                for (int i = 0; i < 7; i++) lin = lin + alpha[i] * cv[i];
+                Fr prod = ((zeta + vk.tail[2]) * zeta + vk.tail[1]) * zeta + vk.tail[0];
+                Fr q_zeta = (lin + lzw) * prod * inv_zn1;
+                Fr agg = nu[0] * x2 + nu[1] * y2 + nu[2] * sz + nu[3] * b + nu[4] * aip + nu[5] * x1 + nu[6] * y1 + nu[7] * q_zeta;
+                Fr cx = b * (y1 * y2 - fr_mul5(x1 * x2)) + omb;
+                Fr cy = b * (x1 * y2 - x2 * y1) + omb;
+                Fr s_ip = alpha[0] * zml, s_x = alpha[1] * (cx * zml), s_y = alpha[2] * (cy * zml);
+                Fr zeta_omega = zeta * vk.omega;
+                if (degenerate) s.status |= ST_PEDERSEN_BAD;
+                // ---- kzg.py:56-81 with this proof's two coefficients
+                s.sc[0] = ra * nu[3];
+                s.sc[1] = ra * nu[4] + rb * s_ip;
+                s.sc[2] = ra * nu[5] + rb * s_x;
+                s.sc[3] = ra * nu[6] + rb * s_y;
+                s.sc[4] = ra * nu[7];
+                s.sc[5] = ra * zeta;
+                s.sc[6] = rb * zeta_omega;
+                s.sc[7] = ra;
+                s.sc[8] = rb;
+                s.sc[9] = ra * nu[0];
+                s.sc[10] = ra * nu[1];
+                s.sc[11] = ra * nu[2];
+                s.sc[12] = (ra * agg + rb * lzw).neg();
+            }
+        }
+    }
+};
+
+// k * P for a Montgomery Fr scalar, fixed 4-bit windows
+DR_HD_COLD G1 g1_mul_fr(const G1Affine& p, const Fr& k_mont) {
+    if (p.is_inf()) return G1::inf();
+    Fr k = k_mont.from_mont();
+    G1 tab[16];
+    tab[0] = G1::inf();
+    tab[1] = G1::from_affine(p);
+#pragma unroll 1
+    for (int i = 2; i < 16; i++) {
+        if (i & 1) {
+            tab[i] = tab[i - 1];
+            g1_madd(tab[i], p);
+        } else {
+            tab[i] = g1_dbl(tab[i >> 1]);
+        }
+    }
+    G1 acc = G1::inf();
+#pragma unroll 1
+    for (int i = 7; i >= 0; i--) {
+#pragma unroll 1
+        for (int sft = 28; sft >= 0; sft -= 4) {
+            if (!acc.is_inf()) acc = g1_dbl(g1_dbl(g1_dbl(g1_dbl(acc))));
+            uint32_t d = (k.v[i] >> sft) & 15;
+            if (d) g1_add(acc, tab[d]);
+        }
+    }
+    return acc;
+}
+
+// one thread per (proof, term)
+struct RingVerifyTermsBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, VerifyState* vs) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < VERIFY_TERMS * count) {
+                uint32_t p = i / VERIFY_TERMS, j = i % VERIFY_TERMS;
+                VerifyState& s = vs[p];
+                const G1Affine& base = j < 7 ? s.g1[j] : j < 9 ? s.g1[j - 2] : vk.fixed[j - 9];
+                s.term[j] = (s.status & ST_MALFORMED) ? G1::inf() : g1_mul_fr(base, s.sc[j]);
+            }
+        }
+    }
+};
+
+DR_HD void ring_verify_sides(const VerifyState& s, G1& lhs, G1& rhs) {
+    lhs = s.term[0];
+    for (int j = 1; j < 7; j++) g1_add(lhs, s.term[j]);
+    for (int j = 9; j < VERIFY_TERMS; j++) g1_add(lhs, s.term[j]);
+    rhs = s.term[7];
+    g1_add(rhs, s.term[8]);
+}
+
+// per-item verdicts: one pairing check per proof.  extra_status: Pedersen status per proof (or null).
+struct RingVerifyFinishBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            if (p < count) {
+                const VerifyState& s = vs[p];
+                uint32_t st = s.status | (extra_status ? extra_status[p] : 0u);
+                uint8_t v;
+                if (st & ST_MALFORMED) {
+                    v = 2;
+                } else if (st) {
+                    v = 0;
+                } else {
+                    G1 lhs, rhs;
+                    ring_verify_sides(s, lhs, rhs);
+                    v = pairing_equal(g1_to_affine(lhs), vk.g2[0], g1_to_affine(rhs), vk.g2[1], vk.pc) ? 1 : 0;
+                }
+                verdict[p] = v;
+            }
+        }
+    }
+};
+
+// aggregated check (RingVRF.batch_verify, vrf/ring/vrf.py:239-283): one block sums every proof's sides, one pairing.
+// verdict[p] carries the per-item decode / Pedersen status (1 ok, 0 invalid, 2 malformed); *all_ok the batch verdict.
+struct RingVerifyAggregateBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict,
+                          uint32_t* all_ok) const {
+        G1* sm = (G1*)ctx.smem;  // 2 * nthreads
+        uint32_t* bad = (uint32_t*)(sm + 2 * ctx.nthreads);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) *bad = 0;
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            G1 lhs = G1::inf(), rhs = G1::inf();
+            bool any_bad = false;
+#pragma unroll 1
+            for (uint32_t p = t; p < count; p += ctx.nthreads) {
+                const VerifyState& s = vs[p];
+                uint32_t st = s.status | (extra_status ? extra_status[p] : 0u);
+                verdict[p] = (st & ST_MALFORMED) ? 2 : st ? 0 : 1;
+                if (st) {
+                    any_bad = true;
+                } else {
+                    G1 l, r;
+                    ring_verify_sides(s, l, r);
+                    g1_add(lhs, l);
+                    g1_add(rhs, r);
+                }
+            }
+            sm[t] = lhs;
+            sm[ctx.nthreads + t] = rhs;
+            if (any_bad) *bad = 1;  // racing writers store the same value
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
+                G1 b = sm[ctx.nthreads + t];
+                g1_add(b, sm[ctx.nthreads + t + stride]);
+                sm[ctx.nthreads + t] = b;
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) {
+                bool ok = !*bad && pairing_equal(g1_to_affine(sm[0]), vk.g2[0], g1_to_affine(sm[ctx.nthreads]), vk.g2[1], vk.pc);
+                *all_ok = ok ? 1u : 0u;
+            }
+        }
+    }
+};
+
+}  // namespace dr

@@ -10,6 +10,7 @@ otherwise 12 fresh ``secrets.randbelow(prime)`` values per proof in the referenc
 
 from __future__ import annotations
 
+import hashlib
 import secrets
 from collections.abc import Sequence
 from dataclasses import dataclass
@@ -44,6 +45,109 @@ def _dec_scalar(cv: CurveVariant, value: bytes) -> int:
     return scalar
 
 
+def _random_nonzero_coefficients(count: int, order: int) -> list[int]:
+    """pcs/kzg.py:84-108: first coefficient 1, the rest rejection-sampled from SHAKE256(32 random bytes | ctr)."""
+    if count <= 0:
+        return []
+    coeffs = [1]
+    byte_len = (order.bit_length() + 7) // 8
+    limit = (1 << (8 * byte_len)) - ((1 << (8 * byte_len)) % order)
+    seed = secrets.token_bytes(32)
+    counter = 0
+    while len(coeffs) < count:
+        raw = hashlib.shake_256(seed + counter.to_bytes(8, "little")).digest(byte_len * (count - len(coeffs)) * 2)
+        counter += 1
+        for offset in range(0, len(raw), byte_len):
+            candidate = int.from_bytes(raw[offset : offset + byte_len], "big")
+            if candidate >= limit:
+                continue
+            coeff = candidate % order
+            if coeff:
+                coeffs.append(coeff)
+                if len(coeffs) == count:
+                    break
+    return coeffs
+
+
+def _suite_struct(cv: CurveVariant):
+    from . import _native
+
+    p = cv.curve.params
+    return _native.make_suite(p.suite_id, p.hash_to_curve.dst, p.generator, p.auxiliary_points.blinding_base)
+
+
+def _point_to_hash(cv: CurveVariant, point: bytes, size: int = 32) -> bytes:
+    """primitives.py:91-96 over the 32-byte encoding of the output point."""
+    from .transcript import _squeeze
+
+    return _squeeze(cv.curve.params.suite_id + bytes([0x20]) + bytes(point), size)
+
+
+@dataclass(frozen=True)
+class TinyVRF(VRF):
+    """ietf/tiny.py:27-89: gamma (32) | c (16) | s (32)."""
+
+    output_point: bytes
+    c: int
+    s: int
+
+    @classmethod
+    def proof_len(cls) -> int:
+        return 80
+
+    @classmethod
+    def decode(cls, proof: bytes) -> "TinyVRF":
+        if len(proof) != 80:
+            raise ValueError(f"invalid Tiny VRF proof length: expected 80, got {len(proof)}")
+        from .engine import default_engine
+
+        proof = bytes(proof)
+        if default_engine().ctx.te_decode([proof[:32]], checked=True)[0] is None:
+            raise ValueError("Invalid output point")
+        return cls(proof[:32], int.from_bytes(proof[32:48], "little"), _dec_scalar(cls.cv, proof[48:80]))
+
+    def encode(self) -> bytes:
+        return self.output_point + self.c.to_bytes(16, "little") + self.s.to_bytes(32, "little")
+
+    @classmethod
+    def prove(cls, alpha: bytes, secret_key: bytes, additional_data: bytes, salt: bytes = b"") -> "TinyVRF":
+        return cls.prove_batch([alpha], [secret_key], [additional_data], [salt])[0]
+
+    @classmethod
+    def prove_batch(cls, alphas, secret_keys, additional_data, salts=None, as_bytes: bool = False):
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(alphas)
+        raw = default_engine().ctx.vrf_prove(
+            "tiny", _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, alphas, strict=True)], [bytes(d) for d in additional_data], [bytes(k) for k in secret_keys]
+        )
+        if as_bytes:
+            return raw
+        return [cls(p[:32], int.from_bytes(p[32:48], "little"), int.from_bytes(p[48:], "little")) for p in raw]
+
+    def verify(self, public_key: bytes, input: bytes, additional_data: bytes, salt: bytes = b"") -> bool:
+        """ietf/tiny.py:72-83; an undecodable public key raises ValueError as in the reference."""
+        verdict = self.verify_batch([self.encode()], [public_key], [input], [additional_data], [salt])[0]
+        if verdict == 2:
+            raise ValueError("Invalid public key")
+        return verdict == 1
+
+    @classmethod
+    def verify_batch(cls, proofs, public_keys, inputs, additional_data, salts=None) -> list[int]:
+        """Independent verifications (the reference has no batch equation for Tiny): 1 valid, 0 invalid, 2 malformed."""
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(proofs)
+        raw = [p if isinstance(p, (bytes, bytearray)) else p.encode() for p in proofs]
+        return default_engine().ctx.tiny_verify(
+            _suite_struct(cls.cv), [bytes(k) for k in public_keys], [bytes(s) + bytes(a) for s, a in zip(salts, inputs, strict=True)], [bytes(d) for d in additional_data], [bytes(p) for p in raw]
+        )
+
+    @classmethod
+    def proof_to_hash(cls, gamma: bytes, mul_cofactor: bool = False) -> bytes:
+        return PedersenVRF[cls.cv].proof_to_hash(gamma, mul_cofactor)
+
+
 @dataclass(frozen=True)
 class PedersenVRF(VRF):
     """gamma || Y_bar || R || O_k || s || s_b (points as 32-byte encodings)."""
@@ -73,6 +177,59 @@ class PedersenVRF(VRF):
 
     def encode(self) -> bytes:
         return self.output_point + self.blinded_pk + self.result_point + self.ok + self.s.to_bytes(32, "little") + self.sb.to_bytes(32, "little")
+
+    @classmethod
+    def prove(cls, alpha: bytes, secret_key: bytes, additional_data: bytes, salt: bytes = b"") -> "PedersenVRF":
+        """pedersen/vrf.py:86-126."""
+        return cls.prove_batch([alpha], [secret_key], [additional_data], [salt])[0]
+
+    @classmethod
+    def prove_batch(cls, alphas, secret_keys, additional_data, salts=None, as_bytes: bool = False):
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(alphas)
+        raw = default_engine().ctx.vrf_prove(
+            "pedersen", _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, alphas, strict=True)], [bytes(d) for d in additional_data], [bytes(k) for k in secret_keys]
+        )
+        if as_bytes:
+            return raw
+        return [cls(p[0:32], p[32:64], p[64:96], p[96:128], int.from_bytes(p[128:160], "little"), int.from_bytes(p[160:192], "little")) for p in raw]
+
+    def verify(self, input: bytes, additional_data: bytes, salt: bytes = b"") -> bool:
+        """pedersen/vrf.py:128-143."""
+        return self.verify_batch([self], [input], [additional_data], [salt])[0] == 1
+
+    @classmethod
+    def verify_batch(cls, proofs, inputs, additional_data, salts=None) -> list[int]:
+        """Per-item verdicts for a batch: 1 valid, 0 invalid, 2 malformed."""
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(proofs)
+        raw = [bytes(p) if isinstance(p, (bytes, bytearray)) else p.encode() for p in proofs]
+        return default_engine().ctx.pedersen_verify(
+            _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, inputs, strict=True)], [bytes(d) for d in additional_data], raw
+        )
+
+    @classmethod
+    def batch_verify(cls, proofs, inputs, additional_data, salts=None) -> bool:
+        """pedersen/vrf.py:171-242: True iff every proof verifies (mismatched lengths / malformed input -> False)."""
+        try:
+            if not (len(proofs) == len(inputs) == len(additional_data)) or (salts is not None and len(salts) != len(proofs)):
+                return False
+            return all(v == 1 for v in cls.verify_batch(proofs, inputs, additional_data, salts))
+        except (AssertionError, AttributeError, TypeError, ValueError):
+            return False
+
+    @classmethod
+    def proof_to_hash(cls, gamma: bytes, mul_cofactor: bool = False) -> bytes:
+        """pedersen/vrf.py:165-168 on the 32-byte encoding of gamma."""
+        if mul_cofactor:
+            from .engine import default_engine
+
+            gamma = default_engine().ctx.te_mul([bytes(gamma)], [cls.cv.curve.params.cofactor])[0]
+            if gamma is None:
+                raise ValueError("Invalid point")
+        return _point_to_hash(cls.cv, gamma)
 
 
 @dataclass
@@ -207,6 +364,46 @@ class RingVRF(VRF):
         if as_bytes:
             return proofs
         return [cls._from_bytes_trusted(p) for p in proofs]
+
+    # ---- verification ------------------------------------------------------------------------
+    @classmethod
+    def _verify_common(cls, proofs, inputs, additional_data, ring: Ring, ring_root: RingRoot, aggregate: bool):
+        """-> (per-item verdicts, all_ok).  vrf/ring/vrf.py:173-182 (`matches_ring`), 226-283."""
+        raw = [bytes(p) if isinstance(p, (bytes, bytearray)) else p.encode() for p in proofs]
+        n = len(raw)
+        if not (len(inputs) == len(additional_data) == n):
+            raise ValueError("proofs, inputs and additional_data must have the same length")
+        if not ring_root.matches_ring(ring):
+            return [0] * n, False
+        if n == 0:
+            return [], True
+        order = ring.params.prime
+        if aggregate:
+            coeffs = _random_nonzero_coefficients(2 * n, order)
+        else:  # independent checks: (1, r) per proof, as KZG.batch_verify draws for a single proof's two openings
+            coeffs = [v for r in _random_nonzero_coefficients(n + 1, order)[1:] for v in (1, r)]
+        return ring.native.verify_batch([bytes(a) for a in inputs], [bytes(d) for d in additional_data], raw, coeffs, aggregate)
+
+    def verify(self, input: bytes, ad_data: bytes, ring: Ring, ring_root: RingRoot) -> bool:
+        """vrf/ring/vrf.py:226-232."""
+        return self._verify_common([self], [input], [ad_data], ring, ring_root, False)[0][0] == 1
+
+    @classmethod
+    def verify_batch(cls, proofs, inputs, additional_data, ring: Ring, ring_root: RingRoot) -> list[int]:
+        """Independent verifications, one verdict per item: 1 valid, 0 invalid, 2 malformed encoding."""
+        return cls._verify_common(proofs, inputs, additional_data, ring, ring_root, False)[0]
+
+    @classmethod
+    def batch_verify(cls, proofs, inputs, additional_data, ring: Ring, ring_root: RingRoot) -> bool:
+        """vrf/ring/vrf.py:239-283: one aggregated pairing check for the whole batch; any error -> False."""
+        try:
+            return cls._verify_common(proofs, inputs, additional_data, ring, ring_root, True)[1]
+        except (AssertionError, AttributeError, TypeError, ValueError):
+            return False
+
+    @classmethod
+    def proof_to_hash(cls, gamma: bytes, mul_cofactor: bool = False) -> bytes:
+        return PedersenVRF[cls.cv].proof_to_hash(gamma, mul_cofactor)
 
 
 class _LazyRingVRF:

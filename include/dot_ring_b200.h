@@ -145,6 +145,64 @@ int dr_ctx_set_prove_chunk(dr_ctx* ctx, size_t chunk);
 int dr_te_decode_batch(dr_ctx* ctx, const uint8_t* in32, size_t n, int checked, uint8_t* out_xy64, uint8_t* ok);
 int dr_te_mul_batch(dr_ctx* ctx, const uint8_t* points32, size_t n_points, const uint8_t* scalars32, size_t n, uint8_t* out32, uint8_t* ok);
 
+/* ---- VRF verification, batched -------------------------------------------------------------------------------
+ * Item i: input = blob[in_off[i] .. +in_len[i]) (salt | alpha), ad = blob[ad_off[i] .. +ad_len[i]).
+ * verdict[i]: 1 valid, 0 invalid, 2 malformed (the reference raises ValueError while decoding: bad length is the
+ * caller's business, bad point / non-canonical scalar is reported here).
+ * dr_pedersen_verify_batch replaces `PedersenVRF.decode` + `.verify` (dot_ring/vrf/pedersen/vrf.py:48-73,128-143) per item and, as
+ * the conjunction of the verdicts, `PedersenVRF.batch_verify` (:171-242).  proofs192: O | Ybar | R | Ok | s | sb.
+ * dr_tiny_verify_batch replaces `TinyVRF.decode` + `.verify` (dot_ring/vrf/ietf/tiny.py:46-83).  proofs80: O | c (16) | s. */
+typedef struct dr_vrf_suite {
+    uint32_t suite_id_len;
+    uint32_t h2c_dst_len;
+    uint8_t suite_id[32];
+    uint8_t h2c_dst[64];
+    uint8_t generator[64];     /* affine x | y, 32-byte little-endian each */
+    uint8_t blinding_base[64];
+} dr_vrf_suite;
+int dr_pedersen_verify_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                             const uint32_t* ad_len, const uint8_t* proofs192, uint8_t* verdict);
+int dr_tiny_verify_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                         const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs80, uint8_t* verdict);
+
+/* Batched provers for the two plain schemes: `PedersenVRF.prove` (dot_ring/vrf/pedersen/vrf.py:86-126) and `TinyVRF.prove`
+ * (dot_ring/vrf/ietf/tiny.py:35-70); nonces are the reference's deterministic transcript nonces (primitives.py:66-82). */
+int dr_pedersen_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                            const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs192);
+int dr_tiny_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                        const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs80);
+
+/* ---- ring-proof verification ------------------------------------------------------------------------------------
+ * dr_ring_proof_verify_batch replaces `Verify(...).is_valid()` (dot_ring/ring_proof/verify.py:213-324: payload decode,
+ * `derive_challenges_after_vk`, `_compute_quotient_and_linearization_terms`, `linear_pcs_verifications`) followed by
+ * `KZG.batch_verify_linear_preconverted` (pcs/kzg.py:56-108,304-338) for n (relation point, 592-byte payload) pairs under
+ * one verifier key.  coeffs_le32: 2n canonical non-zero Fr values, the random batching coefficients the reference draws in
+ * `_random_nonzero_coefficients` (the caller owns the randomness; (1, r) per proof for independent checks).
+ * aggregate == 0: one pairing check per proof, verdict[i] as above.  aggregate != 0: all proofs folded into one check
+ * (`RingVRF.batch_verify`, vrf/ring/vrf.py:239-283); verdict[i] then only reports decode / Pedersen status, *all_ok the result.
+ * dr_ring_verify_batch = `RingVRF.decode` + `RingVRF.verify` / `batch_verify` (vrf/ring/vrf.py:60-93,226-283): Pedersen part +
+ * ring proof with the relation Ybar against the verifier key of `ring` (the caller compares ring roots, root.py:111-112). */
+typedef struct dr_verifier_key {
+    uint32_t domain_size;
+    uint32_t label_len;
+    uint8_t label[32];         /* transcript label, e.g. the suite id or "w3f-ring-proof-test" */
+    uint8_t omega[32];
+    uint8_t seed[64];          /* accumulator base, affine x | y */
+    uint8_t g1_0_be96[96];     /* [1]_1 */
+    uint8_t g2_be192[384];     /* [1]_2, [tau]_2 uncompressed */
+    uint8_t fixed_be96[288];   /* C_px, C_py, C_s uncompressed */
+} dr_verifier_key;
+int dr_ring_proof_verify_batch(dr_ctx* ctx, const dr_verifier_key* key, size_t n, const uint8_t* relations_xy64, const uint8_t* payloads592, const uint8_t* coeffs_le32,
+                               int aggregate, uint8_t* verdict, int* all_ok);
+int dr_ring_verify_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                         const uint32_t* ad_len, const uint8_t* proofs784, const uint8_t* coeffs_le32, int aggregate, uint8_t* verdict, int* all_ok);
+
+/* ---- pairing check ------------------------------------------------------------------------------------------
+ * Replaces `blst_miller_loop` + `blst_final_verify` (dot_ring/ring_proof/pcs/pairing.py:24-31) for a batch:
+ * equal[i] = ( e(a1_i, b1_i) == e(a2_i, b2_i) ), G1 as 96-byte and G2 as 192-byte zcash uncompressed encodings
+ * (x.c1 | x.c0 | y.c1 | y.c0, srs.py:80-88).  DR_EINVAL on a malformed point. */
+int dr_pairing_check_batch(dr_ctx* ctx, const uint8_t* a1_be96, const uint8_t* b1_be192, const uint8_t* a2_be96, const uint8_t* b2_be192, size_t n, uint8_t* equal);
+
 /* ---- arithmetic-layer self test + integer-pipe ceilings ----------------------------------------
  * dr_field_op: element-wise Montgomery arithmetic on the device (reference equivalent:
  * dot_ring/curve/native_field/scalar.pyx:12-165 `Scalar`, tested by tests/test_curve_ops/test_native_field.py).

@@ -1,0 +1,46 @@
+"""CPU run of the verification parity cases: kernels through the test-only emulation build (tests/host/emul.py)."""
+
+import pytest
+
+from dot_ring_b200 import _native
+from tests import verify_cases as cases
+from tests.host.emul import emulation_library
+from tests.ring_fixtures import native_srs
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _native.Context(0, emulation_library())
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def srs(ctx):
+    s = native_srs(ctx, 1537, 4)
+    yield s
+    s.close()
+
+
+def test_pairing(ctx):
+    cases.pairing_kats(ctx)
+
+
+def test_pedersen_vectors(ctx):
+    cases.pedersen_vectors(ctx)
+
+
+def test_tiny_vectors(ctx):
+    cases.tiny_vectors(ctx)
+
+
+def test_vrf_batch_fixtures(ctx):
+    cases.vrf_batch_fixtures(ctx)
+
+
+def test_ring8_verify(srs):
+    cases.ring8_vectors(srs, count=2)
+
+
+def test_w3f_verifier_vectors(ctx):
+    cases.w3f_vectors(ctx)
