@@ -251,7 +251,8 @@ class Context:
         abuf = b"".join(int(x).to_bytes(size, order) for x in a)
         bbuf = b"".join(int(x).to_bytes(size, order) for x in b)
         self.library.check(self.library.lib.dr_field_op(self.handle, fidx, oidx, abuf, bbuf, out, len(a)))
-        return [int.from_bytes(out.raw[size * i : size * i + size], order) for i in range(len(a))]
+        raw = out.raw
+        return [int.from_bytes(raw[size * i : size * i + size], order) for i in range(len(a))]
 
     def microbench(self, kind: str, iters: int) -> tuple[float, float]:
         """(ops per second over the chip, elapsed ms) for 'imad' | 'imad_wide' | 'fq_mul' | 'fr_mul' | 'g1_madd'."""
@@ -281,7 +282,8 @@ class Context:
         ok = ctypes.create_string_buffer(max(n, 1))
         ks = b"".join((int(k) % BANDERSNATCH_ORDER).to_bytes(32, "little") for k in scalars)
         self.library.check(self.library.lib.dr_te_mul_batch(self.handle, b"".join(points), len(points), ks, n, out, ok))
-        return [out.raw[32 * i : 32 * i + 32] if ok.raw[i] else None for i in range(n)]
+        raw, okr = out.raw, ok.raw
+        return [raw[32 * i : 32 * i + 32] if okr[i] else None for i in range(n)]
 
     # ---- verification ---------------------------------------------------------------------------
     def pedersen_verify(self, suite: VrfSuiteStruct, inputs: list[bytes], ads: list[bytes], proofs: list[bytes]) -> list[int]:
@@ -317,7 +319,8 @@ class Context:
         blob, a, b, c, d = pack_items(inputs, ads)
         out = ctypes.create_string_buffer(size * max(n, 1))
         self.library.check(fn(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(secret_keys), out))
-        return [out.raw[size * i : size * i + size] for i in range(n)]
+        raw = out.raw
+        return [raw[size * i : size * i + size] for i in range(n)]
 
     def ring_proof_verify(self, key: VerifierKeyStruct, relations: list[tuple[int, int]], payloads: list[bytes], coeffs: list[int], aggregate: bool = False):
         """`Verify(...).is_valid()` for a batch under an explicit verifier key -> (verdicts, all_ok)."""
@@ -397,7 +400,8 @@ class NativeSrs:
         data = b"".join((int(c) % FR_MODULUS).to_bytes(32, "little") for v in coeff_vectors for c in v)
         lib = self.ctx.library
         lib.check(lib.lib.dr_kzg_commit(self.ctx.handle, self.handle, data, n, batch, out))
-        return [out.raw[96 * i : 96 * i + 96] for i in range(batch)]
+        raw = out.raw
+        return [raw[96 * i : 96 * i + 96] for i in range(batch)]
 
     def commit_bench(self, n: int, batch: int, iters: int, seed: int = 1) -> tuple[float, bytes]:
         ms = c_float()
