@@ -4,7 +4,8 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 SRC=dot_ring_b200/csrc
-OUT=dot_ring_b200/libdotring_b200.so
+OUT=${OUT:-dot_ring_b200/libdotring_b200.so}
+BUILD_DIR=${BUILD_DIR:-build}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 SOURCES=$(ls $SRC/api_*.cu)
 if [ "${1:-}" = "--emul" ]; then
@@ -20,10 +21,10 @@ if [ "${1:-}" = "--emul" ]; then
   echo "built tests/host/libdotring_emul.so"
   exit 0
 fi
-mkdir -p build
+mkdir -p $BUILD_DIR
 objs=""
 for f in $SOURCES; do
-  o=build/$(basename "$f" .cu).o
+  o=$BUILD_DIR/$(basename "$f" .cu).o
   if [ ! -f "$o" ] || [ -n "$(find $SRC include -newer "$o" \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' -o -name '*.inc' \) | head -1)" ]; then
     $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA:-} -c "$f" -o "$o" &
   fi

@@ -85,6 +85,7 @@ class Library:
         L.dr_ring_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 10
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
+        L.dr_ctx_set_dense_witness_commit.argtypes = [c_void_p, c_int]
 
         L.dr_pedersen_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
@@ -213,6 +214,10 @@ class Context:
 
     def sync(self) -> None:
         self.library.check(self.library.lib.dr_ctx_sync(self.handle))
+
+    def set_dense_witness_commit(self, enabled: bool) -> None:
+        """Commit witness columns from interpolated coefficients (the reference's route) instead of the sparse Lagrange form."""
+        self.library.check(self.library.lib.dr_ctx_set_dense_witness_commit(self.handle, 1 if enabled else 0))
 
     def timer_start(self) -> None:
         self.library.check(self.library.lib.dr_ctx_timer_start(self.handle))

@@ -72,6 +72,41 @@ void PhaseTimer::collect(Ctx* ctx) {
     phase_of.clear();
 }
 
+void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table) {
+    if (geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
+    table.alloc(geom.total_entries());
+    uint32_t chunks = geom.H >= 512 ? geom.H / 256 : 1;  // <= 256 serial additions per thread
+    size_t nthreads = (size_t)geom.n_points * chunks;
+    const uint32_t tb = 64;
+    Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
+    if (geom.W <= 32)
+        launch(ctx->stream, grid, tb, 0, TableBuildBody<32>(), points, table.p, geom, chunks);
+    else
+        launch(ctx->stream, grid, tb, 0, TableBuildBody<64>(), points, table.p, geom, chunks);
+}
+
+const LagrangeTable& Srs::lagrange_table(uint32_t N, uint32_t logN, const Fr& omega, const Fr* tw_inv_half, const Fr& n_inv) {
+    for (auto& l : lagrange)
+        if (l->N == N && l->omega == omega) return *l;
+    if (N > n) throw Error(DR_EINVAL, "SRS smaller than the domain");
+    auto l = std::make_unique<LagrangeTable>();
+    l->N = N;
+    l->omega = omega;
+    DevBuf<G1> work(N);
+    DevBuf<G1Affine> sj(N);
+    Stream st = ctx->stream;
+    launch(st, Dim3((N + 63) / 64), 64, 0, G1BitReverseBody(), (const G1Affine*)points.p, N, logN, work.p);
+    for (uint32_t half = 1; half < N; half <<= 1) launch(st, Dim3((N / 2 + 31) / 32), 32, 0, G1NttStageBody(), work.p, N, half, tw_inv_half);
+    launch(st, Dim3((N + 31) / 32), 32, 0, G1ScaleBody(), work.p, N, n_inv);
+    const uint32_t pt = 128;
+    launch(st, Dim3(1), pt, pt * sizeof(G1), G1PrefixSumBody(), work.p, N, sj.p);
+    l->geom = make_geom(geom.c < 10 ? geom.c : 10, N);  // 2.6 GB at N = 2048; follows a smaller SRS window (tests)
+    build_window_table(ctx, sj.p, l->geom, l->table);
+    stream_sync(st);
+    lagrange.push_back(std::move(l));
+    return *lagrange.back();
+}
+
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
     if (n == 0 || batch == 0) return;
     if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
@@ -86,7 +121,10 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
     }
     ctx->partials.ensure((size_t)batch * slices);
     const uint32_t threads = COMMIT_THREADS;
-    launch(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
+#ifndef DR_COMMIT_MINB
+#define DR_COMMIT_MINB 4
+#endif
+    launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
     launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
 }
 
@@ -231,7 +269,6 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     memcpy(srs->g1_0_be96, g1_be96, 96);
     memcpy(srs->g2_be192, g2_be192, 384);
     srs->geom = make_geom(cbits, srs->n);
-    if (srs->geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
     DevBuf<uint8_t> raw(n_g1 * 96);
     DevBuf<uint32_t> bad(1);
     dev_zero(ctx->stream, bad.p, 4);
@@ -243,15 +280,7 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     stream_sync(ctx->stream);
     if (bad_h) throw Error(DR_EINVAL, "invalid BLS12-381 G1 encoding in SRS");
     // fixed-base table
-    srs->table.alloc(srs->geom.total_entries());
-    uint32_t chunks = srs->geom.H >= 512 ? srs->geom.H / 256 : 1;  // <= 256 serial additions per thread
-    size_t nthreads = (size_t)srs->n * chunks;
-    const uint32_t tb = 64;
-    Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
-    if (srs->geom.W <= 32)
-        launch(ctx->stream, grid, tb, 0, TableBuildBody<32>(), (const G1Affine*)srs->points.p, srs->table.p, srs->geom, chunks);
-    else
-        launch(ctx->stream, grid, tb, 0, TableBuildBody<64>(), (const G1Affine*)srs->points.p, srs->table.p, srs->geom, chunks);
+    build_window_table(ctx, srs->points.p, srs->geom, srs->table);
     stream_sync(ctx->stream);
     *out = (dr_srs*)srs.release();
     DR_API_END

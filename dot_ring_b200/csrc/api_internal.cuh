@@ -62,6 +62,7 @@ struct Ctx {
     PhaseTimer phases;
     std::shared_ptr<void> prove_scratch;
     size_t prove_chunk = 0;
+    bool dense_witness_commit = false;  // A/B + cross-check: commit witness columns from coefficients like the reference
     bool have_pairing_consts = false;
     PairingConsts pairing_k;
     const PairingConsts& pairing_consts() {
@@ -84,6 +85,14 @@ struct Ctx {
     }
 };
 
+// Window table of S_j = sum_{i<j} [L_i(tau)]_1, j = 1..N, for one evaluation domain (sparse witness commitments).
+struct LagrangeTable {
+    uint32_t N = 0;
+    Fr omega;
+    TableGeom geom{};
+    DevBuf<G1Affine> table;
+};
+
 struct Srs {
     Ctx* ctx = nullptr;
     uint32_t n = 0;
@@ -92,6 +101,9 @@ struct Srs {
     TableGeom geom{};
     uint8_t g1_0_be96[96];
     uint8_t g2_be192[384];
+    std::vector<std::unique_ptr<LagrangeTable>> lagrange;
+    // built on first use for (N, omega); tw_inv_half = [omega^-k], k < N/2, on the device
+    const LagrangeTable& lagrange_table(uint32_t N, uint32_t logN, const Fr& omega, const Fr* tw_inv_half, const Fr& n_inv);
 };
 
 struct Ring {
@@ -105,6 +117,7 @@ struct Ring {
     uint8_t commit_be96[288];
     uint8_t root144[144];
     TEAffine padding;
+    const struct LagrangeTable* lag = nullptr;  // owned by the Srs (shared by every ring on the same domain)
     VerifierKeyDev vk{};
     SuiteDev suite{};
 };
@@ -112,6 +125,9 @@ struct Ring {
 
 VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TEAffine& seed, const uint8_t* label, uint32_t label_len, const uint8_t* g1_0_be96,
                                  const uint8_t* g2_be192, const uint8_t* fixed_be96);
+
+// Fixed-base window table (msm.cuh) for n affine points already on the device.
+void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table);
 
 // scalars: `batch` vectors of n Montgomery Fr, vector b at scalars + b*stride.  Result: affine points.
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine);

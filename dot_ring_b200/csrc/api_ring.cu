@@ -316,7 +316,15 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         pt.mark(ctx, 1);
         launch(ctx->stream, Dim3(4, m), ntt_threads, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
         pt.mark(ctx, 2);
-        commit_device(ctx, ring->srs, sc.wit_coef.p, N, N, 4 * m, sc.res.p);
+        if (ctx->dense_witness_commit) {
+            commit_device(ctx, ring->srs, sc.wit_coef.p, N, N, 4 * m, sc.res.p);
+        } else {
+            if (!ring->lag) ring->lag = &ring->srs->lagrange_table(N, rg.logN, rg.omega, rg.tw_inv, rg.n_inv);
+            ctx->partials.ensure((size_t)4 * m);
+            launch(ctx->stream, Dim3(4, m), 32, 32 * sizeof(G1), WitnessCommitBody(), (const G1Affine*)ring->lag->table.p, ring->lag->geom, rg, (const ProofState*)sc.st.p,
+                   ctx->partials.p);
+            launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, 1u, 4 * m, sc.res.p);
+        }
         // column order (b, accx, accy, accip) -> payload slots (0, 2, 3, 1)
         launch(ctx->stream, Dim3((4 * m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 4u, 0x01030200u, sc.st.p, m);
         pt.mark(ctx, 5);
@@ -362,6 +370,14 @@ int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !out) throw Error(DR_EINVAL, "bad argument");
     for (int i = 0; i < 6; i++) out[i] = ctx->phases.total[i];
+    DR_API_END
+}
+
+int dr_ctx_set_dense_witness_commit(dr_ctx* c, int enabled) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx) throw Error(DR_EINVAL, "bad argument");
+    ctx->dense_witness_commit = enabled != 0;
     DR_API_END
 }
 

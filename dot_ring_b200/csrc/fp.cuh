@@ -29,6 +29,40 @@
 
 namespace dr {
 
+// Out-of-line multiplication.  A 12-limb Montgomery multiplication is ~6 KB of straight-line SASS; a mixed G1
+// addition inlines ten of them, which overflows the instruction cache (ncu: `no_instruction` was the second
+// largest stall of the commit kernel).  Operands and result travel by value, which the device ABI keeps
+// entirely in registers (no local-memory traffic), so a call costs a CALL/RET pair and a few moves.
+// -DDR_FQ_MUL_INLINE / -DDR_FR_MUL_INLINE restore full inlining for A/B measurements.
+#if defined(__CUDA_ARCH__)
+struct Limbs12 {
+    uint32_t v[12];
+};
+struct Limbs8 {
+    uint32_t v[8];
+};
+static __device__ __noinline__ Limbs12 fq_mul_outofline(Limbs12 a, Limbs12 b) {
+    Limbs12 r;
+    fq_mul_ptx(r.v, a.v, b.v);
+    return r;
+}
+static __device__ __noinline__ Limbs12 fq_sqr_outofline(Limbs12 a) {
+    Limbs12 r;
+    fq_sqr_ptx(r.v, a.v);
+    return r;
+}
+static __device__ __noinline__ Limbs8 fr_mul_outofline(Limbs8 a, Limbs8 b) {
+    Limbs8 r;
+    fr_mul_ptx(r.v, a.v, b.v);
+    return r;
+}
+static __device__ __noinline__ Limbs8 fr_sqr_outofline(Limbs8 a) {
+    Limbs8 r;
+    fr_sqr_ptx(r.v, a.v);
+    return r;
+}
+#endif
+
 struct FqTag {
     static constexpr int N = DR_FQ_LIMBS;
     static constexpr uint32_t M0 = DR_FQ_M0;
@@ -45,8 +79,30 @@ struct FqTag {
         return m[i];
     }
 #if defined(__CUDA_ARCH__)
+#if defined(DR_FQ_MUL_INLINE)
     DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_mul_ptx(r, a, b); }
     DR_D static void sqr(uint32_t* r, const uint32_t* a) { fq_sqr_ptx(r, a); }
+#else
+    DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        Limbs12 x, y;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            x.v[i] = a[i];
+            y.v[i] = b[i];
+        }
+        Limbs12 z = fq_mul_outofline(x, y);
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] = z.v[i];
+    }
+    DR_D static void sqr(uint32_t* r, const uint32_t* a) {
+        Limbs12 x;
+#pragma unroll
+        for (int i = 0; i < 12; i++) x.v[i] = a[i];
+        Limbs12 z = fq_sqr_outofline(x);
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] = z.v[i];
+    }
+#endif
     DR_D static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_add_ptx(r, a, b); }
     DR_D static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_sub_ptx(r, a, b); }
 #endif
@@ -68,8 +124,30 @@ struct FrTag {
         return m[i];
     }
 #if defined(__CUDA_ARCH__)
+#if !defined(DR_FR_MUL_CALL)
     DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_mul_ptx(r, a, b); }
     DR_D static void sqr(uint32_t* r, const uint32_t* a) { fr_sqr_ptx(r, a); }
+#else
+    DR_D static void mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        Limbs8 x, y;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            x.v[i] = a[i];
+            y.v[i] = b[i];
+        }
+        Limbs8 z = fr_mul_outofline(x, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = z.v[i];
+    }
+    DR_D static void sqr(uint32_t* r, const uint32_t* a) {
+        Limbs8 x;
+#pragma unroll
+        for (int i = 0; i < 8; i++) x.v[i] = a[i];
+        Limbs8 z = fr_sqr_outofline(x);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = z.v[i];
+    }
+#endif
     DR_D static void add(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_add_ptx(r, a, b); }
     DR_D static void sub(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_sub_ptx(r, a, b); }
 #endif

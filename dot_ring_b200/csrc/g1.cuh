@@ -120,6 +120,34 @@ DR_HD_COLD void g1_add(G1& acc, const G1& b) {
     acc.ZZZ = acc.ZZZ * b.ZZZ * PPP;
 }
 
+// k * P for canonical little-endian limbs k (8 limbs), fixed 4-bit windows
+DR_HD_COLD G1 g1_mul_limbs(const G1& p, const uint32_t* k) {
+    if (p.is_inf()) return G1::inf();
+    G1 tab[16];
+    tab[0] = G1::inf();
+    tab[1] = p;
+#pragma unroll 1
+    for (int i = 2; i < 16; i++) {
+        if (i & 1) {
+            tab[i] = tab[i - 1];
+            g1_add(tab[i], p);
+        } else {
+            tab[i] = g1_dbl(tab[i >> 1]);
+        }
+    }
+    G1 acc = G1::inf();
+#pragma unroll 1
+    for (int i = 7; i >= 0; i--) {
+#pragma unroll 1
+        for (int sft = 28; sft >= 0; sft -= 4) {
+            if (!acc.is_inf()) acc = g1_dbl(g1_dbl(g1_dbl(g1_dbl(acc))));
+            uint32_t d = (k[i] >> sft) & 15;
+            if (d) g1_add(acc, tab[d]);
+        }
+    }
+    return acc;
+}
+
 DR_HD G1 g1_neg(const G1& p) {
     G1 r = p;
     r.Y = p.Y.neg();

@@ -165,6 +165,85 @@ struct TableBuildBody {
     }
 };
 
+// ---- Lagrange prefix-sum bases ------------------------------------------------------------------------------
+// [L_i(tau)]_1 = (1/N) sum_k w^(-ik) [tau^k]_1 is an inverse DFT over group elements: log2 N radix-2 stages of N/2
+// butterflies (one scalar multiplication each), then S_j = sum_{i<j} [L_i(tau)]_1.  One-off per (SRS, domain).
+struct G1BitReverseBody {  // out[rev(i)] = in[i]
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* in, uint32_t N, uint32_t logN, G1* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < N) {
+                uint32_t r = 0;
+                for (uint32_t b = 0; b < logN; b++) r |= ((i >> b) & 1u) << (logN - 1 - b);
+                out[r] = G1::from_affine(in[i]);
+            }
+        }
+    }
+};
+// stage with butterfly span `half`: (a, b) -> (a + w b, a - w b), w = winv_half[(N / (2 half)) * j]
+struct G1NttStageBody {
+    DR_HD void operator()(const BlockCtx& ctx, G1* data, uint32_t N, uint32_t half, const Fr* winv_half) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < N / 2) {
+                uint32_t j = i % half, base = (i / half) * 2 * half + j;
+                G1 a = data[base], b = data[base + half];
+                if (j) {
+                    Fr w = winv_half[(N / (2 * half)) * j].from_mont();
+                    b = g1_mul_limbs(b, w.v);
+                }
+                G1 s = a;
+                g1_add(s, b);
+                g1_add(a, g1_neg(b));
+                data[base] = s;
+                data[base + half] = a;
+            }
+        }
+    }
+};
+// data[i] <- (1/N) data[i]
+struct G1ScaleBody {
+    DR_HD void operator()(const BlockCtx& ctx, G1* data, uint32_t N, Fr n_inv) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < N) {
+                Fr k = n_inv.from_mont();
+                data[i] = g1_mul_limbs(data[i], k.v);
+            }
+        }
+    }
+};
+// inclusive prefix sums in place, then affine: out[j-1] = S_j = sum_{i<j} data[i], j = 1..N.  One block, two phases.
+struct G1PrefixSumBody {
+    DR_HD void operator()(const BlockCtx& ctx, G1* data, uint32_t N, G1Affine* out) const {
+        G1* sm = (G1*)ctx.smem;  // per-thread chunk totals
+        const uint32_t per = (N + ctx.nthreads - 1) / ctx.nthreads;
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+            uint32_t lo = t * per, hi = lo + per < N ? lo + per : N;
+#pragma unroll 1
+            for (uint32_t i = lo; i < hi; i++) {
+                g1_add(acc, data[i]);
+                data[i] = acc;
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            G1 off = G1::inf();
+#pragma unroll 1
+            for (uint32_t u = 0; u < t; u++) g1_add(off, sm[u]);
+            uint32_t lo = t * per, hi = lo + per < N ? lo + per : N;
+#pragma unroll 1
+            for (uint32_t i = lo; i < hi; i++) {
+                G1 v = data[i];
+                g1_add(v, off);
+                out[i] = g1_to_affine(v);
+            }
+        }
+    }
+};
+
 // ---- signed-digit recoding -------------------------------------------------------------------------
 // k: canonical little-endian limbs (< 2^255).  Returns digit w in [-(H-1), H]; carry is threaded.
 DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) {

@@ -15,6 +15,7 @@
 #pragma once
 #include "g1.cuh"
 #include "hash.cuh"
+#include "msm.cuh"
 #include "ntt.cuh"
 #include "rt.cuh"
 #include "te.cuh"
@@ -351,6 +352,52 @@ struct WitnessInttBody {
         Fr ninv = rg.n_inv;
         ntt_block(
             ctx, rg.N, rg.logN, rg.tw_inv, [&](uint32_t r) { return witness_eval(rg, ps, col, r); }, [&](uint32_t k, const Fr& v) { dst[k] = v * ninv; });
+    }
+};
+
+// ---- D'. witness commitments from the evaluation form: grid (4 columns, proofs) ---------------------------------
+// A witness column is piecewise constant (b: one-hot + bits, acc_ip: a step, acc_x / acc_y: change only where a bit
+// of the blinding factor is set) except for its three blinding rows, so in the Lagrange basis
+//   C = sum_i v_i [L_i(tau)]_1 = sum_{j=1..N} (v_{j-1} - v_j) S_j,   S_j = sum_{i<j} [L_i(tau)]_1,  v_N := 0
+// has ~130 non-zero terms instead of N.  It is the same group element as KZG.commit(interpolate(v))
+// (columns.py:29-60), hence the same bytes; the S_j have their own fixed-base window table per ring.
+struct WitnessCommitBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, RingDev rg, const ProofState* st, G1* out) const {
+        G1* sm = (G1*)ctx.smem;
+        const ProofState& ps = st[ctx.by];
+        const uint32_t col = ctx.bx, N = rg.N;
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+#pragma unroll 1
+            for (uint32_t j = 1 + t; j <= N; j += ctx.nthreads) {
+                Fr d = witness_eval(rg, ps, col, j - 1);
+                if (j < N) d = d - witness_eval(rg, ps, col, j);
+                if (d.is_zero()) continue;
+                // steps of +-1 (b, acc_ip) cost one table entry: use whichever of d, -d is the shorter integer
+                Fr kc = d.from_mont(), nk = d.neg().from_mont();
+                bool flip = (nk.v[1] | nk.v[2] | nk.v[3] | nk.v[4] | nk.v[5] | nk.v[6] | nk.v[7]) == 0;
+                if (flip) kc = nk;
+                uint32_t carry = 0;
+#pragma unroll 1
+                for (uint32_t w = 0; w < g.W; w++) {
+                    int dg = msm_digit(kc.v, w, g.c, carry);
+                    if (dg) g1_madd(acc, table[g.entry(j - 1, w, (uint32_t)(dg < 0 ? -dg : dg))], (dg < 0) != flip);
+                }
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) out[(size_t)ctx.by * 4 + col] = sm[0];
+        }
     }
 };
 

@@ -67,6 +67,13 @@ __global__ void kernel_entry(Body body, Args... args) {
     BlockCtx ctx{blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, gridDim.z, blockDim.x, dr_smem};
     body(ctx, args...);
 }
+// Same, with an occupancy contract: the body is always launched with <= THREADS threads and wants BLOCKS CTAs per SM.
+template <int THREADS, int BLOCKS, class Body, class... Args>
+__global__ void __launch_bounds__(THREADS, BLOCKS) kernel_entry_lb(Body body, Args... args) {
+    extern __shared__ __align__(16) uint8_t dr_smem[];
+    BlockCtx ctx{blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, gridDim.z, blockDim.x, dr_smem};
+    body(ctx, args...);
+}
 
 // launch counter (bench.py reports it as gpu_launches)
 inline uint64_t& launch_counter() {
@@ -78,6 +85,17 @@ template <class Body, class... Args>
 inline void launch(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
     auto kern = kernel_entry<Body, Args...>;
+    if (smem > 48 * 1024) DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(grid.x, grid.y, grid.z), threads, smem, s>>>(body, args...);
+    DR_CUDA(cudaGetLastError());
+    launch_counter()++;
+}
+
+template <int THREADS, int BLOCKS, class Body, class... Args>
+inline void launch_lb(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+    if (threads > (uint32_t)THREADS) throw Error(DR_ESTATE, "launch exceeds the kernel's launch bounds");
+    auto kern = kernel_entry_lb<THREADS, BLOCKS, Body, Args...>;
     if (smem > 48 * 1024) DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(grid.x, grid.y, grid.z), threads, smem, s>>>(body, args...);
     DR_CUDA(cudaGetLastError());
@@ -132,6 +150,10 @@ inline void launch(Stream, Dim3 grid, uint32_t threads, size_t smem, Body body, 
                 body(ctx, args...);
             }
     launch_counter()++;
+}
+template <int THREADS, int BLOCKS, class Body, class... Args>
+inline void launch_lb(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
+    launch(s, grid, threads, smem, body, args...);
 }
 inline void* dev_alloc(size_t bytes) {
     void* p = calloc(bytes ? bytes : 16, 1);

@@ -378,33 +378,10 @@ struct RingVerifyAlgebraBody {
     }
 };
 
-// k * P for a Montgomery Fr scalar, fixed 4-bit windows
-DR_HD_COLD G1 g1_mul_fr(const G1Affine& p, const Fr& k_mont) {
-    if (p.is_inf()) return G1::inf();
+// k * P for a Montgomery Fr scalar
+DR_HD G1 g1_mul_fr(const G1Affine& p, const Fr& k_mont) {
     Fr k = k_mont.from_mont();
-    G1 tab[16];
-    tab[0] = G1::inf();
-    tab[1] = G1::from_affine(p);
-#pragma unroll 1
-    for (int i = 2; i < 16; i++) {
-        if (i & 1) {
-            tab[i] = tab[i - 1];
-            g1_madd(tab[i], p);
-        } else {
-            tab[i] = g1_dbl(tab[i >> 1]);
-        }
-    }
-    G1 acc = G1::inf();
-#pragma unroll 1
-    for (int i = 7; i >= 0; i--) {
-#pragma unroll 1
-        for (int sft = 28; sft >= 0; sft -= 4) {
-            if (!acc.is_inf()) acc = g1_dbl(g1_dbl(g1_dbl(g1_dbl(acc))));
-            uint32_t d = (k.v[i] >> sft) & 15;
-            if (d) g1_add(acc, tab[d]);
-        }
-    }
-    return acc;
+    return g1_mul_limbs(G1::from_affine(p), k.v);
 }
 
 // one thread per (proof, term)

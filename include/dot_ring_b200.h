@@ -135,6 +135,10 @@ int dr_ring_prove_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* blo
 int dr_ring_prove_phase_ms(dr_ctx* ctx, float out[6]);
 /* Proofs processed per internal pass (bounds device scratch: about 1 KiB * domain_size per proof). 0 = default 1024. */
 int dr_ctx_set_prove_chunk(dr_ctx* ctx, size_t chunk);
+/* Witness-column commitments (columns.py:29-60,153-161) are computed from the evaluation form over Lagrange prefix-sum bases
+ * (~130 non-zero terms per column instead of N); enabled != 0 switches to the reference's route, KZG.commit of the interpolated
+ * coefficients.  Both give the same group element, hence identical proofs (tests cross-check the two). */
+int dr_ctx_set_dense_witness_commit(dr_ctx* ctx, int enabled);
 
 /* ---- batched Bandersnatch point operations -------------------------------------------------------------
  * dr_te_decode_batch replaces `dec_point` (dot_ring/vrf/codec.py:39-45) / `CurvePoint.string_to_point`

@@ -110,3 +110,30 @@ def test_params_table(api):
         P.from_ring_size(0)
     p = P.from_ring_size(1023)
     assert pow(p.omega, 2048, p.prime) == 1 and pow(p.radix_omega, 4, p.prime) == p.omega
+
+
+def test_sparse_and_dense_witness_commitments_give_identical_proofs(api):
+    """The witness columns are committed from their evaluation form over Lagrange prefix-sum bases; the reference's route
+    (interpolate, then KZG.commit of the coefficients; columns.py:29-60) must give byte-identical proofs, blinded rows included."""
+    import random
+
+    from dot_ring_b200 import engine as engine_mod
+
+    v = load("bandersnatch_sha-512_ell2_ring.json")[3]
+    keys = split_keys(hx(v, "ring_pks"))
+    params = api.RingProofParams()  # blinded rows
+    ring = api.Ring(keys, params)
+    rng = random.Random(99)
+    zk = [rng.randrange(params.prime) for _ in range(24)]
+    cls = api.RingVRF[api.Bandersnatch]
+    args = ([hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], hx(v, "sk"), hx(v, "pk"), ring)
+    sparse = cls.prove_batch(*args, zk_rows=zk, as_bytes=True)
+    ctx = engine_mod.default_engine().ctx
+    ctx.set_dense_witness_commit(True)
+    try:
+        dense = cls.prove_batch(*args, zk_rows=zk, as_bytes=True)
+    finally:
+        ctx.set_dense_witness_commit(False)
+    assert sparse == dense and sparse[0] != sparse[1]
+    root = api.RingRoot.from_ring(ring, params)
+    assert cls.verify_batch(sparse, [hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], ring, root) == [1, 1]

@@ -115,3 +115,23 @@ def test_ring1023_batch_proofs_verify_with_oracle(srs):
         assert rp.verify_ring(params, fixed, prefix, pr.pedersen.blinded_pk, pr.ring, srs_o)
     assert oring.nm_points[3] == tuple(ring.points())[3]
     ring.close()
+
+
+def test_sparse_and_dense_witness_commitments_agree_at_full_size(ctx, srs):
+    """Same proofs from the Lagrange-prefix (sparse) witness commitments and from KZG.commit of the interpolated columns."""
+    pk, sk, keys = bench_ring_keys(1023)
+    params = rp.Params.from_ring_size(1023)
+    ring = native_ring(srs, keys, params)
+    n = 96
+    rng = random.Random(3)
+    zk = [rng.randrange(fr.R) for _ in range(12 * n)]
+    alphas = [b"x" * (j % 7) + le64(j) for j in range(n)]
+    ads = [b"ad" + le64(j) for j in range(n)]
+    sparse, st1 = ring.prove_batch(alphas, ads, [sk] * n, [3] * n, zk_rows=zk)
+    ctx.set_dense_witness_commit(True)
+    try:
+        dense, st2 = ring.prove_batch(alphas, ads, [sk] * n, [3] * n, zk_rows=zk)
+    finally:
+        ctx.set_dense_witness_commit(False)
+    assert st1 == st2 == [0] * n and sparse == dense
+    ring.close()

@@ -11,6 +11,8 @@ from dot_ring_b200 import _native  # noqa: E402
 from dot_ring_b200.srs import read_srs_file  # noqa: E402
 
 out = {}
+if os.environ.get("DR_LIB"):  # A/B builds of the same sources (tools only)
+    _native.set_default_library(_native.Library(os.environ["DR_LIB"]))
 ctx = _native.Context(0)
 out["device"] = ctx.device_info()
 for kind, iters in (("imad", 20000), ("imad_wide", 20000), ("fq_mul", 2000), ("fr_mul", 4000), ("g1_madd", 300)):
@@ -32,4 +34,4 @@ for n, batch in ((2048, 16), (2048, 256), (2048, 4096), (6145, 1024), (2048, 1),
 out["commit"] = res
 out["launches"] = ctx.library.launch_count()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("PROBE_OUT", "gpurun_out/probe.json"), "w"), indent=1)

@@ -13,6 +13,8 @@ from tests.helpers import bench_ring_keys, le64  # noqa: E402
 from tests.ring_fixtures import native_ring, native_srs  # noqa: E402
 
 cbits = int(os.environ.get("DR_WINDOW_BITS", "12"))
+if os.environ.get("DR_LIB"):  # A/B builds of the same sources (tools only)
+    _native.set_default_library(_native.Library(os.environ["DR_LIB"]))
 ctx = _native.Context(0)
 t0 = time.time()
 srs = native_srs(ctx, None, cbits)
@@ -24,7 +26,7 @@ ring = native_ring(srs, keys, params)
 print("ring create s", time.time() - t0, flush=True)
 out = {"window_bits": cbits, "runs": []}
 rng = random.Random(0)
-for n in (16, 256, 1024, 4096):
+for n in [int(x) for x in os.environ.get("PROVE_NS", "16,256,1024,4096").split(",")]:
     zk = [rng.randrange(fr.R) for _ in range(12 * n)]
     alphas = [b"bench-batch-input" + le64(j) for j in range(n)]
     ads = [b"bench-batch-ad" + le64(j) for j in range(n)]
@@ -37,4 +39,4 @@ for n in (16, 256, 1024, 4096):
     out["runs"].append({"n": n, "wall_s": dt, "proofs_per_s": n / dt, "phase_ms": ph, "device_ms": sum(ph)})
     print(out["runs"][-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/probe_prove.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("PROBE_OUT", "gpurun_out/probe_prove.json"), "w"), indent=1)
