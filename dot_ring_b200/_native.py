@@ -70,6 +70,8 @@ class Library:
         L.dr_srs_table_bytes.restype = c_size_t
         L.dr_kzg_commit.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
         L.dr_kzg_commit_bench.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_uint64, POINTER(c_float), c_void_p]
+        L.dr_g1_msm.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        L.dr_g1_msm_bench.argtypes = [c_void_p, c_size_t, c_int, c_uint64, c_int, c_void_p, POINTER(c_float), POINTER(ctypes.c_uint32), c_void_p]
         L.dr_g1_compress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_g1_decompress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
         L.dr_fr_ntt.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_void_p]
@@ -350,6 +352,25 @@ class Context:
         out = ctypes.create_string_buffer(max(n, 1))
         self.library.check(self.library.lib.dr_pairing_check_batch(self.handle, a1_be96, b1_be192, a2_be96, b2_be192, n, out))
         return [bool(b) for b in out.raw[:n]]
+
+    def g1_msm(self, points_be96: bytes, scalars: list[int]) -> bytes:
+        """`KZG.msm_g1` (kzg.py:147-149) over arbitrary points: 96-byte uncompressed result."""
+        count = len(points_be96) // 96
+        if len(scalars) != count:
+            raise ValueError("points and scalars must have the same length")
+        out = ctypes.create_string_buffer(96)
+        ks = b"".join((int(k) % FR_MODULUS).to_bytes(32, "little") for k in scalars)
+        self.library.check(self.library.lib.dr_g1_msm(self.handle, points_be96, ks, count, out))
+        return out.raw
+
+    def g1_msm_bench(self, n: int, iters: int, seed: int, distribution: int, tau: int) -> tuple[float, int, bytes]:
+        """(ms per MSM, window bits, result) of an n-point MSM over the synthetic SRS tau^i * G, operands on the device."""
+        ms, c = c_float(), ctypes.c_uint32()
+        out = ctypes.create_string_buffer(96)
+        self.library.check(
+            self.library.lib.dr_g1_msm_bench(self.handle, n, iters, seed, distribution, int(tau).to_bytes(32, "little"), ctypes.byref(ms), ctypes.byref(c), out)
+        )
+        return float(ms.value), int(c.value), out.raw
 
     def g1_compress(self, points_be96: bytes) -> bytes:
         count = len(points_be96) // 96

@@ -279,7 +279,20 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     DevBuf<uint8_t> dblob(blob_len ? blob_len : 1);
     h2d(ctx->stream, dblob.p, blob, blob_len);
 
-    const size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 1024;
+    // proofs per pass: the one-thread-per-proof kernels (Pedersen part, witness chain, transcripts) are latency-bound, so
+    // a pass should be as wide as the scratch (35 N field elements + state per proof) allows
+    size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 4096;
+#if !defined(DR_HOST_EMULATION)
+    if (!ctx->prove_chunk) {
+        size_t free_b = 0, total_b = 0;
+        DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        ProveScratch& cur = scratch_for(ctx);
+        size_t per_proof = 35 * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
+        size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
+        size_t fit = have / 2 / per_proof;
+        if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
+    }
+#endif
     ProveScratch& sc = scratch_for(ctx);
     sc.ensure(n < chunk_cap ? n : chunk_cap, N);
     PhaseTimer& pt = ctx->phases;

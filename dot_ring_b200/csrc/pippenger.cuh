@@ -1,0 +1,242 @@
+// Variable-base G1 multi-scalar multiplication (bucket method) for arbitrary point sets.
+//
+// Stands in for blst's `P1_Affines.mult_pippenger(points, scalars)` as the reference calls it through
+// `KZG.msm_g1` (dot_ring/ring_proof/pcs/kzg.py:147-149) and in the verifier's lhs / rhs folds (kzg.py:295-296,332-333).
+// Commitments over the fixed SRS do not come here (they use the window tables of msm.cuh); this path serves point sets
+// that are not known in advance and the 2^11 .. 2^20 sweep over a synthetic SRS.
+//
+// Pipeline (all on device, no host round trips):
+//   digits   signed c-bit digits of every scalar + per-bucket histogram (atomics)
+//   scan     exclusive prefix sums of the histogram and of the work units (a unit = at most UNIT points of one bucket, so a
+//            skewed scalar distribution -- every scalar equal, 0/1-heavy columns -- cannot serialise on one thread)
+//   scatter  counting-sort the (point, sign) references by bucket
+//   units    one thread per unit: XYZZ mixed additions of its points
+//   buckets  one thread per bucket: fold its units
+//   reduce   per window, T_w = sum_k k * S_k by segmented running sums; window fold by Horner with c doublings
+#pragma once
+#include "g1.cuh"
+#include "msm.cuh"
+#include "rt.cuh"
+
+namespace dr {
+
+constexpr uint32_t MSM_UNIT = 64;     // points per work unit
+constexpr uint32_t MSM_SEGMENT = 64;  // buckets per running-sum segment
+
+#if defined(__CUDA_ARCH__)
+DR_D uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t old = *p;
+    *p = old + v;
+    return old;
+}
+#endif
+
+struct MsmGeom {
+    uint32_t n, c, W, H;  // H = 2^(c-1) buckets per window
+    DR_HD uint32_t buckets() const { return W * H; }
+};
+
+// scalars: n x 32-byte little-endian (any value < 2^256, reduced mod r here) -> digits[w * n + i]
+struct MsmDigitsBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* scalars_le32, MsmGeom g, int32_t* digits, uint32_t* count) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < g.n) {
+                Fr k = fp_from_le_bytes_mod<Fr>(scalars_le32 + 32 * (size_t)i, 32).from_mont();
+                uint32_t carry = 0;
+#pragma unroll 1
+                for (uint32_t w = 0; w < g.W; w++) {
+                    int d = msm_digit(k.v, w, g.c, carry);
+                    digits[(size_t)w * g.n + i] = d;
+                    if (d) atomic_add_u32(&count[w * g.H + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+                }
+            }
+        }
+    }
+};
+
+// One block.  offset[b] = exclusive scan of count[b]; unit_offset[b] = exclusive scan of ceil(count[b] / UNIT);
+// totals[0] = number of units.  cursor[b] is reset to 0 for the scatter pass.
+struct MsmScanBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint32_t* count, uint32_t nb, uint32_t* offset, uint32_t* unit_offset, uint32_t* cursor, uint32_t* totals) const {
+        uint32_t* sm = (uint32_t*)ctx.smem;  // 2 * nthreads
+        const uint32_t per = (nb + ctx.nthreads - 1) / ctx.nthreads;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t a = 0, u = 0;
+            uint32_t lo = t * per, hi = lo + per < nb ? lo + per : nb;
+            for (uint32_t b = lo; b < hi; b++) {
+                a += count[b];
+                u += (count[b] + MSM_UNIT - 1) / MSM_UNIT;
+            }
+            sm[t] = a;
+            sm[ctx.nthreads + t] = u;
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t a = 0, u = 0;
+            for (uint32_t s = 0; s < t; s++) {
+                a += sm[s];
+                u += sm[ctx.nthreads + s];
+            }
+            uint32_t lo = t * per, hi = lo + per < nb ? lo + per : nb;
+            for (uint32_t b = lo; b < hi; b++) {
+                offset[b] = a;
+                unit_offset[b] = u;
+                cursor[b] = 0;
+                a += count[b];
+                u += (count[b] + MSM_UNIT - 1) / MSM_UNIT;
+            }
+            if (t == ctx.nthreads - 1) totals[0] = u;
+        }
+    }
+};
+
+// refs[offset[b] + slot] = point index | sign << 31
+struct MsmScatterBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const int32_t* digits, const uint32_t* offset, uint32_t* cursor, uint32_t* refs) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < g.n) {
+#pragma unroll 1
+                for (uint32_t w = 0; w < g.W; w++) {
+                    int d = digits[(size_t)w * g.n + i];
+                    if (d) {
+                        uint32_t b = w * g.H + (uint32_t)(d < 0 ? -d : d) - 1;
+                        uint32_t slot = atomic_add_u32(&cursor[b], 1u);
+                        refs[offset[b] + slot] = i | (d < 0 ? 0x80000000u : 0u);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// unit u belongs to the bucket b with unit_offset[b] <= u < unit_offset[b + 1] (binary search)
+struct MsmUnitSumBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const G1Affine* points, const uint32_t* count, const uint32_t* offset, const uint32_t* unit_offset,
+                          const uint32_t* totals, const uint32_t* refs, G1* unit_sum) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t u = ctx.bx * ctx.nthreads + t;
+            if (u < totals[0]) {
+                uint32_t lo = 0, hi = g.buckets() - 1;
+                while (lo < hi) {  // last bucket with unit_offset <= u
+                    uint32_t mid = (lo + hi + 1) >> 1;
+                    if (unit_offset[mid] <= u) lo = mid;
+                    else hi = mid - 1;
+                }
+                // empty buckets share their unit_offset with the next one: step to the owner
+                uint32_t b = lo;
+                uint32_t first = offset[b] + (u - unit_offset[b]) * MSM_UNIT;
+                uint32_t end = offset[b] + count[b];
+                uint32_t stop = first + MSM_UNIT < end ? first + MSM_UNIT : end;
+                G1 acc = G1::inf();
+#pragma unroll 1
+                for (uint32_t r = first; r < stop; r++) {
+                    uint32_t ref = refs[r];
+                    g1_madd(acc, points[ref & 0x7FFFFFFFu], (ref >> 31) != 0);
+                }
+                unit_sum[u] = acc;
+            }
+        }
+    }
+};
+
+struct MsmBucketFoldBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const uint32_t* count, const uint32_t* unit_offset, const G1* unit_sum, G1* bucket) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t b = ctx.bx * ctx.nthreads + t;
+            if (b < g.buckets()) {
+                uint32_t units = (count[b] + MSM_UNIT - 1) / MSM_UNIT;
+                G1 acc = G1::inf();
+#pragma unroll 1
+                for (uint32_t u = 0; u < units; u++) g1_add(acc, unit_sum[unit_offset[b] + u]);
+                bucket[b] = acc;
+            }
+        }
+    }
+};
+
+// segment s of window w covers buckets k = lo..hi (1-based digit values): out = sum_k k * S_k
+struct MsmSegmentReduceBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const G1* bucket, uint32_t segs_per_window, G1* seg_sum) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t id = ctx.bx * ctx.nthreads + t;
+            if (id < g.W * segs_per_window) {
+                uint32_t w = id / segs_per_window, s = id % segs_per_window;
+                uint32_t lo = s * MSM_SEGMENT + 1;
+                uint32_t hi = lo + MSM_SEGMENT - 1 < g.H ? lo + MSM_SEGMENT - 1 : g.H;
+                G1 running = G1::inf(), acc = G1::inf();
+#pragma unroll 1
+                for (uint32_t k = hi; k >= lo; k--) {
+                    g1_add(running, bucket[(size_t)w * g.H + k - 1]);
+                    g1_add(acc, running);  // after the loop: sum (k - lo + 1) * S_k
+                }
+                // + (lo - 1) * sum S_k
+                uint32_t m = lo - 1;
+                if (m) {
+                    G1 add = G1::inf();
+#pragma unroll 1
+                    for (int bit = 31; bit >= 0; bit--) {
+                        if (!add.is_inf()) add = g1_dbl(add);
+                        if ((m >> bit) & 1) g1_add(add, running);
+                    }
+                    g1_add(acc, add);
+                }
+                seg_sum[id] = acc;
+            }
+        }
+    }
+};
+
+// one block: thread w folds its window's segments; thread 0 then folds the windows (Horner, c doublings per step)
+struct MsmFinalBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const G1* seg_sum, uint32_t segs_per_window, G1Affine* out) const {
+        G1* sm = (G1*)ctx.smem;  // W entries
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < g.W) {
+                G1 acc = G1::inf();
+#pragma unroll 1
+                for (uint32_t s = 0; s < segs_per_window; s++) g1_add(acc, seg_sum[(size_t)t * segs_per_window + s]);
+                sm[t] = acc;
+            }
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) {
+                G1 acc = sm[g.W - 1];
+#pragma unroll 1
+                for (int w = (int)g.W - 2; w >= 0; w--) {
+#pragma unroll 1
+                    for (uint32_t k = 0; k < g.c; k++) acc = g1_dbl(acc);
+                    g1_add(acc, sm[w]);
+                }
+                *out = g1_to_affine(acc);
+            }
+        }
+    }
+};
+
+// ---- synthetic SRS for the sweep: P_i = tau^i * G ----------------------------------------------------------------
+struct SyntheticSrsBody {
+    DR_HD void operator()(const BlockCtx& ctx, G1Affine gen, Fr tau, uint32_t n, G1Affine* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < n) {
+                Fr e = Fr::one(), base = tau;
+                uint32_t k = i;
+#pragma unroll 1
+                while (k) {
+                    if (k & 1) e = e * base;
+                    base = base.sqr();
+                    k >>= 1;
+                }
+                Fr raw = e.from_mont();
+                out[i] = g1_to_affine(g1_mul_limbs(G1::from_affine(gen), raw.v));
+            }
+        }
+    }
+};
+
+}  // namespace dr

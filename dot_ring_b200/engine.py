@@ -22,7 +22,8 @@ class Engine:
     def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None):
         self.device = device
         self.ctx = _native.Context(device, library)
-        self.window_bits = int(window_bits if window_bits is not None else os.environ.get("DOT_RING_B200_WINDOW_BITS", "12"))
+        env = os.environ.get("DOT_RING_B200_WINDOW_BITS")
+        self.window_bits = int(window_bits) if window_bits is not None else (int(env) if env else None)
         self._srs: _native.NativeSrs | None = None
         self._srs_points = srs_points
         self.srs_bytes = read_srs_file(None, srs_points)
@@ -31,8 +32,20 @@ class Engine:
     def srs(self) -> _native.NativeSrs:
         """SRS points + window table in HBM, built on first use (about 0.5 s for the default 26.6 GB table)."""
         if self._srs is None:
+            if self.window_bits is None:
+                self.window_bits = self._auto_window_bits()
             self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits)
         return self._srs
+
+    def _auto_window_bits(self) -> int:
+        """Largest window whose table (n * ceil(256/c) * 2^(c-1) * 96 B) fits in half of the free HBM: 14 bits = 92 GB for
+        the bundled 6145-point SRS on a 180 GB B200 (19 additions per coefficient; 12 bits = 27 GB, 22 additions)."""
+        free = self.ctx.device_info()["free_bytes"]
+        n = self.srs_bytes.n_g1
+        for c in (14, 13, 12, 11, 10, 9, 8):
+            if n * -(-256 // c) * (1 << (c - 1)) * 96 <= free // 2:
+                return c
+        return 8
 
     def close(self) -> None:
         if self._srs is not None:

@@ -30,6 +30,14 @@ class KZG:
         return eng.srs.commit(vecs)
 
     @classmethod
+    def msm_g1(cls, points, scalars) -> bytes:
+        """kzg.py:147-149 over arbitrary points (96-byte uncompressed each): device bucket-method MSM."""
+        pts = list(points)
+        if len(pts) != len(scalars):
+            raise ValueError("points and scalars must have the same length")
+        return default_engine().ctx.g1_msm(b"".join(bytes(p) for p in pts), [int(k) for k in scalars])
+
+    @classmethod
     def compress_g1(cls, point: bytes) -> bytes:
         """kzg.py:129-131."""
         return default_engine().ctx.g1_compress(bytes(point))

@@ -72,6 +72,17 @@ int dr_kzg_commit(dr_ctx* ctx, dr_srs* srs, const uint8_t* coeffs_le32, size_t n
 /* Same with operands already resident on the device (Montgomery limbs); used for roofline timing. */
 int dr_kzg_commit_bench(dr_ctx* ctx, dr_srs* srs, size_t n, size_t batch, int iters, uint64_t seed, float* ms_per_iter, uint8_t* out_first_be96);
 
+/* ---- variable-base G1 MSM ---------------------------------------------------------------------------------
+ * Replaces `KZG.msm_g1` = `blst.P1_Affines.mult_pippenger(points, scalars)` (dot_ring/ring_proof/pcs/kzg.py:147-149) for point sets
+ * that are not the fixed SRS: sum_i (k_i mod r) * P_i by the bucket method (signed windows, counting sort by bucket, work units
+ * bounded per thread, segmented bucket reduction).  points: n x 96-byte uncompressed; scalars: n x 32-byte little-endian.
+ * dr_g1_msm_bench times the same pipeline with operands resident on the device over the synthetic SRS P_i = tau^i * G
+ * (distribution 0: uniform scalars from splitmix64(seed), 1: all ones, 2: random bits), so the result is checkable as
+ * (sum_i k_i tau^i) * G at any size. */
+int dr_g1_msm(dr_ctx* ctx, const uint8_t* points_be96, const uint8_t* scalars_le32, size_t n, uint8_t out_be96[96]);
+int dr_g1_msm_bench(dr_ctx* ctx, size_t n, int iters, uint64_t seed, int distribution, const uint8_t tau_le32[32], float* ms_per_iter, uint32_t* window_bits,
+                    uint8_t out_be96[96]);
+
 /* ---- G1 codecs -------------------------------------------------------------------------------
  * Replaces kzg.py:121-144 (`compress_g1`, `serialize_g1_uncompressed`, `decompress_g1`).
  * ok[i] = 0 marks a malformed encoding (reference: ValueError("invalid BLS12-381 G1 encoding")). */

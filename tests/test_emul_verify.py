@@ -3,6 +3,7 @@
 import pytest
 
 from dot_ring_b200 import _native
+from tests import msm_cases
 from tests import verify_cases as cases
 from tests.host.emul import emulation_library
 from tests.ring_fixtures import native_srs
@@ -44,3 +45,8 @@ def test_ring8_verify(srs):
 
 def test_w3f_verifier_vectors(ctx):
     cases.w3f_vectors(ctx)
+
+
+def test_g1_msm_vs_oracle(ctx):
+    msm_cases.msm_vs_oracle(ctx, [1, 5, 130, 700])
+    msm_cases.synthetic_property(ctx, [300])

@@ -105,3 +105,13 @@ def test_g1_codecs(ctx):
     assert back == ser and ok == b"\x01" * len(pts)
     _, ok = ctx.g1_decompress(b"\xff" * 48 + bytes(48))
     assert ok == b"\x00\x00"
+
+
+def test_g1_msm_vs_oracle_and_sweep_property(ctx):
+    """Variable-base MSM: against the oracle on SRS points up to 6145, and at 2^11 .. 2^20 points over the synthetic SRS
+    tau^i * G where the result must equal (sum k_i tau^i) * G (uniform, all-ones and random-bit scalars)."""
+    from tests import msm_cases
+
+    msm_cases.msm_vs_oracle(ctx, [1, 33, 2048, 6145])
+    msm_cases.synthetic_property(ctx, [1 << 11, 1 << 14], (0, 1, 2))
+    msm_cases.synthetic_property(ctx, [1 << 17, 1 << 20], (0, 2))
