@@ -296,7 +296,7 @@ def run_ours(args) -> None:
         line["dry_run"] = "CPU emulation of the kernels (tests only); not a measurement"
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if last:
         sys.stderr.write(f"[bench] last proof sha256 {hashlib.sha256(last[-1]).hexdigest()[:16]}\n")
 
@@ -379,10 +379,28 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was
+    re-routed to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for native libraries (NCCL prints its version banner on stdout)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
