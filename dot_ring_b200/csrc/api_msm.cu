@@ -23,8 +23,8 @@ struct MsmWork {
     MsmGeom g{};
     uint32_t segs = 0;
     DevBuf<int32_t> digits;
-    DevBuf<uint32_t> count, offset, unit_offset, cursor, totals, refs;
-    DevBuf<G1> unit_sum, bucket, seg_sum;
+    DevBuf<uint32_t> count, offset, unit_offset, cursor, totals, refs, block_tot;
+    DevBuf<G1> unit_sum, bucket, seg_sum, window_sum;
     DevBuf<G1Affine> result;
     void prepare(size_t n) {
         g.n = (uint32_t)n;
@@ -43,6 +43,8 @@ struct MsmWork {
         unit_sum.ensure((size_t)g.W * n / MSM_UNIT + nb + 1);  // units <= refs / UNIT + one partial unit per bucket
         bucket.ensure(nb);
         seg_sum.ensure((size_t)g.W * segs);
+        window_sum.ensure(g.W);
+        block_tot.ensure(2 * ((nb + SCAN_TILE - 1) / SCAN_TILE));
         result.ensure(1);
     }
 };
@@ -54,8 +56,10 @@ static void msm_device(Ctx* ctx, MsmWork& w, const G1Affine* points, const uint8
     Stream st = ctx->stream;
     dev_zero(st, w.count.p, (size_t)nb * 4);
     launch(st, Dim3((g.n + 127) / 128), 128, 0, MsmDigitsBody(), scalars_le32, g, w.digits.p, w.count.p);
-    const uint32_t scan_threads = 512;
-    launch(st, Dim3(1), scan_threads, 2 * scan_threads * sizeof(uint32_t), MsmScanBody(), (const uint32_t*)w.count.p, nb, w.offset.p, w.unit_offset.p, w.cursor.p, w.totals.p);
+    const uint32_t tiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+    launch(st, Dim3(tiles), SCAN_TILE, 4 * SCAN_TILE * sizeof(uint32_t), MsmScanTileBody(), (const uint32_t*)w.count.p, nb, w.offset.p, w.unit_offset.p, w.block_tot.p);
+    launch(st, Dim3(1), 32, 0, MsmScanBlocksBody(), w.block_tot.p, tiles, w.totals.p);
+    launch(st, Dim3(tiles), SCAN_TILE, 0, MsmScanApplyBody(), nb, (const uint32_t*)w.block_tot.p, w.offset.p, w.unit_offset.p, w.cursor.p);
     launch(st, Dim3((g.n + 127) / 128), 128, 0, MsmScatterBody(), g, (const int32_t*)w.digits.p, (const uint32_t*)w.offset.p, w.cursor.p, w.refs.p);
     // upper bound on the unit count is known on the host; threads beyond totals[0] exit
     const size_t max_units = (size_t)g.W * g.n / MSM_UNIT + nb + 1;
@@ -63,7 +67,8 @@ static void msm_device(Ctx* ctx, MsmWork& w, const G1Affine* points, const uint8
            (const uint32_t*)w.unit_offset.p, (const uint32_t*)w.totals.p, (const uint32_t*)w.refs.p, w.unit_sum.p);
     launch(st, Dim3((nb + 63) / 64), 64, 0, MsmBucketFoldBody(), g, (const uint32_t*)w.count.p, (const uint32_t*)w.unit_offset.p, (const G1*)w.unit_sum.p, w.bucket.p);
     launch(st, Dim3((g.W * w.segs + 63) / 64), 64, 0, MsmSegmentReduceBody(), g, (const G1*)w.bucket.p, w.segs, w.seg_sum.p);
-    launch(st, Dim3(1), 64, 64 * sizeof(G1), MsmFinalBody(), g, (const G1*)w.seg_sum.p, w.segs, w.result.p);
+    launch(st, Dim3(g.W), 64, 64 * sizeof(G1), MsmWindowFoldBody(), (const G1*)w.seg_sum.p, w.segs, w.window_sum.p);
+    launch(st, Dim3(1), 64, 64 * sizeof(G1), MsmFinalBody(), g, (const G1*)w.window_sum.p, w.result.p);
 }
 
 }  // namespace dr

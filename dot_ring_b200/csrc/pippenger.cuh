@@ -12,7 +12,7 @@
 //   scatter  counting-sort the (point, sign) references by bucket
 //   units    one thread per unit: XYZZ mixed additions of its points
 //   buckets  one thread per bucket: fold its units
-//   reduce   per window, T_w = sum_k k * S_k by segmented running sums; window fold by Horner with c doublings
+//   reduce   per window, T_w = sum_k k * S_k by segmented running sums, tree-folded; windows shifted by c*w doublings in parallel
 #pragma once
 #include "g1.cuh"
 #include "msm.cuh"
@@ -20,18 +20,8 @@
 
 namespace dr {
 
-constexpr uint32_t MSM_UNIT = 64;     // points per work unit
+constexpr uint32_t MSM_UNIT = 16;     // points per work unit (small units keep the lanes of a warp in step)
 constexpr uint32_t MSM_SEGMENT = 64;  // buckets per running-sum segment
-
-#if defined(__CUDA_ARCH__)
-DR_D uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-#else
-inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
-    uint32_t old = *p;
-    *p = old + v;
-    return old;
-}
-#endif
 
 struct MsmGeom {
     uint32_t n, c, W, H;  // H = 2^(c-1) buckets per window
@@ -57,38 +47,71 @@ struct MsmDigitsBody {
     }
 };
 
-// One block.  offset[b] = exclusive scan of count[b]; unit_offset[b] = exclusive scan of ceil(count[b] / UNIT);
-// totals[0] = number of units.  cursor[b] is reset to 0 for the scatter pass.
-struct MsmScanBody {
-    DR_HD void operator()(const BlockCtx& ctx, const uint32_t* count, uint32_t nb, uint32_t* offset, uint32_t* unit_offset, uint32_t* cursor, uint32_t* totals) const {
-        uint32_t* sm = (uint32_t*)ctx.smem;  // 2 * nthreads
-        const uint32_t per = (nb + ctx.nthreads - 1) / ctx.nthreads;
+// Exclusive scans of count[b] (-> offset) and of ceil(count[b] / UNIT) (-> unit_offset) in three coalesced passes:
+//   A  each block scans SCAN_TILE consecutive buckets in shared memory (ping-pong Hillis-Steele) and records its two totals
+//   B  one block turns the per-block totals into exclusive block bases (and writes the grand total of units)
+//   C  every element adds its block base; cursor[b] is reset for the scatter pass
+constexpr uint32_t SCAN_TILE = 256;
+struct MsmScanTileBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint32_t* count, uint32_t nb, uint32_t* offset, uint32_t* unit_offset, uint32_t* block_tot) const {
+        uint32_t* sm = (uint32_t*)ctx.smem;  // 4 * SCAN_TILE: two ping-pong pairs (points, units)
+        const uint32_t T = ctx.nthreads;     // == SCAN_TILE
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t a = 0, u = 0;
-            uint32_t lo = t * per, hi = lo + per < nb ? lo + per : nb;
-            for (uint32_t b = lo; b < hi; b++) {
-                a += count[b];
-                u += (count[b] + MSM_UNIT - 1) / MSM_UNIT;
-            }
-            sm[t] = a;
-            sm[ctx.nthreads + t] = u;
+            uint32_t b = ctx.bx * T + t;
+            uint32_t cnt = b < nb ? count[b] : 0;
+            sm[t] = cnt;
+            sm[2 * T + t] = (cnt + MSM_UNIT - 1) / MSM_UNIT;
         }
         DR_BLOCK_SYNC();
+        uint32_t src = 0;
+        for (uint32_t d = 1; d < T; d <<= 1) {
+            DR_THREAD_LOOP(t, ctx) {
+                uint32_t dst = src ^ 1;
+                sm[dst * T + t] = sm[src * T + t] + (t >= d ? sm[src * T + t - d] : 0);
+                sm[(2 + dst) * T + t] = sm[(2 + src) * T + t] + (t >= d ? sm[(2 + src) * T + t - d] : 0);
+            }
+            DR_BLOCK_SYNC();
+            src ^= 1;
+        }
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t a = 0, u = 0;
-            for (uint32_t s = 0; s < t; s++) {
-                a += sm[s];
-                u += sm[ctx.nthreads + s];
+            uint32_t b = ctx.bx * T + t;
+            if (b < nb) {  // inclusive -> exclusive
+                offset[b] = t ? sm[src * T + t - 1] : 0;
+                unit_offset[b] = t ? sm[(2 + src) * T + t - 1] : 0;
             }
-            uint32_t lo = t * per, hi = lo + per < nb ? lo + per : nb;
-            for (uint32_t b = lo; b < hi; b++) {
-                offset[b] = a;
-                unit_offset[b] = u;
+            if (t == T - 1) {
+                block_tot[2 * ctx.bx] = sm[src * T + t];
+                block_tot[2 * ctx.bx + 1] = sm[(2 + src) * T + t];
+            }
+        }
+    }
+};
+struct MsmScanBlocksBody {  // one block, one thread per chunk of tiles; nblocks is small (<= 2048)
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t* block_tot, uint32_t nblocks, uint32_t* totals) const {
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) {
+                uint32_t a = 0, u = 0;
+                for (uint32_t i = 0; i < nblocks; i++) {
+                    uint32_t ca = block_tot[2 * i], cu = block_tot[2 * i + 1];
+                    block_tot[2 * i] = a;
+                    block_tot[2 * i + 1] = u;
+                    a += ca;
+                    u += cu;
+                }
+                totals[0] = u;
+            }
+        }
+    }
+};
+struct MsmScanApplyBody {
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t nb, const uint32_t* block_tot, uint32_t* offset, uint32_t* unit_offset, uint32_t* cursor) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t b = ctx.bx * ctx.nthreads + t;
+            if (b < nb) {
+                offset[b] += block_tot[2 * ctx.bx];
+                unit_offset[b] += block_tot[2 * ctx.bx + 1];
                 cursor[b] = 0;
-                a += count[b];
-                u += (count[b] + MSM_UNIT - 1) / MSM_UNIT;
             }
-            if (t == ctx.nthreads - 1) totals[0] = u;
         }
     }
 };
@@ -190,30 +213,54 @@ struct MsmSegmentReduceBody {
     }
 };
 
-// one block: thread w folds its window's segments; thread 0 then folds the windows (Horner, c doublings per step)
-struct MsmFinalBody {
-    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const G1* seg_sum, uint32_t segs_per_window, G1Affine* out) const {
-        G1* sm = (G1*)ctx.smem;  // W entries
+// block w: tree-fold the window's segments -> T_w
+struct MsmWindowFoldBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1* seg_sum, uint32_t segs_per_window, G1* window_sum) const {
+        G1* sm = (G1*)ctx.smem;
         DR_THREAD_LOOP(t, ctx) {
-            if (t < g.W) {
-                G1 acc = G1::inf();
+            G1 acc = G1::inf();
 #pragma unroll 1
-                for (uint32_t s = 0; s < segs_per_window; s++) g1_add(acc, seg_sum[(size_t)t * segs_per_window + s]);
-                sm[t] = acc;
-            }
+            for (uint32_t s = t; s < segs_per_window; s += ctx.nthreads) g1_add(acc, seg_sum[(size_t)ctx.bx * segs_per_window + s]);
+            sm[t] = acc;
         }
         DR_BLOCK_SYNC();
-        DR_THREAD_LOOP(t, ctx) {
-            if (t == 0) {
-                G1 acc = sm[g.W - 1];
-#pragma unroll 1
-                for (int w = (int)g.W - 2; w >= 0; w--) {
-#pragma unroll 1
-                    for (uint32_t k = 0; k < g.c; k++) acc = g1_dbl(acc);
-                    g1_add(acc, sm[w]);
-                }
-                *out = g1_to_affine(acc);
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
             }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) window_sum[ctx.bx] = sm[0];
+        }
+    }
+};
+// sum_w 2^(c w) T_w: thread w shifts its window by c*w doublings, then a tree adds the W shifted sums
+struct MsmFinalBody {
+    DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const G1* window_sum, G1Affine* out) const {
+        G1* sm = (G1*)ctx.smem;  // nthreads entries (power of two >= W)
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+            if (t < g.W) {
+                acc = window_sum[t];
+#pragma unroll 1
+                for (uint32_t k = 0; k < g.c * t; k++) acc = g1_dbl(acc);
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) *out = g1_to_affine(sm[0]);
         }
     }
 };

@@ -361,13 +361,26 @@ struct WitnessInttBody {
 //   C = sum_i v_i [L_i(tau)]_1 = sum_{j=1..N} (v_{j-1} - v_j) S_j,   S_j = sum_{i<j} [L_i(tau)]_1,  v_N := 0
 // has ~130 non-zero terms instead of N.  It is the same group element as KZG.commit(interpolate(v))
 // (columns.py:29-60), hence the same bytes; the S_j have their own fixed-base window table per ring.
+// Two phases per (column, proof) block: (1) the threads scan the rows and compact the non-zero steps, with their signed
+// window digits, into shared memory; (2) the (step, window) pairs are dealt round-robin to the threads, so every lane
+// issues the same number of table additions however the steps are distributed over the rows.
+constexpr uint32_t WC_MAX_STEPS = 272;  // <= 1 (row k) + 253 (bit rows) + 3 blinding rows + slack, per column
+// shared memory: [steps: WC_MAX_STEPS x (row, flip, W digits) as int16] [counter] [per-thread partial sums]
+DR_HD size_t witness_commit_steps_bytes(uint32_t W) { return (((size_t)WC_MAX_STEPS * (2 + W) * sizeof(int16_t) + 16 + 15) / 16) * 16; }
+DR_HD size_t witness_commit_smem(uint32_t W, uint32_t threads) { return witness_commit_steps_bytes(W) + threads * sizeof(G1); }
 struct WitnessCommitBody {
     DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, RingDev rg, const ProofState* st, G1* out) const {
-        G1* sm = (G1*)ctx.smem;
+        int16_t* steps = (int16_t*)ctx.smem;
+        const uint32_t stride = 2 + g.W;
+        uint32_t* nsteps = (uint32_t*)(ctx.smem + (size_t)WC_MAX_STEPS * stride * sizeof(int16_t));
+        G1* sm = (G1*)(ctx.smem + witness_commit_steps_bytes(g.W));
         const ProofState& ps = st[ctx.by];
         const uint32_t col = ctx.bx, N = rg.N;
         DR_THREAD_LOOP(t, ctx) {
-            G1 acc = G1::inf();
+            if (t == 0) *nsteps = 0;
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
 #pragma unroll 1
             for (uint32_t j = 1 + t; j <= N; j += ctx.nthreads) {
                 Fr d = witness_eval(rg, ps, col, j - 1);
@@ -377,12 +390,27 @@ struct WitnessCommitBody {
                 Fr kc = d.from_mont(), nk = d.neg().from_mont();
                 bool flip = (nk.v[1] | nk.v[2] | nk.v[3] | nk.v[4] | nk.v[5] | nk.v[6] | nk.v[7]) == 0;
                 if (flip) kc = nk;
-                uint32_t carry = 0;
+                uint32_t slot = atomic_add_u32(nsteps, 1u);
+                if (slot < WC_MAX_STEPS) {
+                    int16_t* s = steps + (size_t)slot * stride;
+                    s[0] = (int16_t)j;  // base S_j is table point j - 1 (N <= 4096)
+                    s[1] = flip ? 1 : 0;
+                    uint32_t carry = 0;
 #pragma unroll 1
-                for (uint32_t w = 0; w < g.W; w++) {
-                    int dg = msm_digit(kc.v, w, g.c, carry);
-                    if (dg) g1_madd(acc, table[g.entry(j - 1, w, (uint32_t)(dg < 0 ? -dg : dg))], (dg < 0) != flip);
+                    for (uint32_t w = 0; w < g.W; w++) s[2 + w] = (int16_t)msm_digit(kc.v, w, g.c, carry);
                 }
+            }
+        }
+        DR_BLOCK_SYNC();
+        const uint32_t total = (*nsteps < WC_MAX_STEPS ? *nsteps : WC_MAX_STEPS) * g.W;
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+#pragma unroll 1
+            for (uint32_t it = t; it < total; it += ctx.nthreads) {
+                const int16_t* s = steps + (size_t)(it / g.W) * stride;
+                uint32_t w = it % g.W;
+                int dg = s[2 + w];
+                if (dg) g1_madd(acc, table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg < 0 ? -dg : dg))], (dg < 0) != (s[1] != 0));
             }
             sm[t] = acc;
         }

@@ -42,6 +42,17 @@ struct BlockCtx {
 #define DR_BLOCK_SYNC() ((void)0)
 #endif
 
+// atomics: the emulation build runs the threads of a block one after another, so a plain update is exact there
+#if defined(__CUDA_ARCH__)
+DR_D uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t old = *p;
+    *p = old + v;
+    return old;
+}
+#endif
+
 struct Dim3 {
     uint32_t x, y, z;
     Dim3(uint32_t x_ = 1, uint32_t y_ = 1, uint32_t z_ = 1) : x(x_), y(y_), z(z_) {}
