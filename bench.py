@@ -200,7 +200,7 @@ def run_ours(args) -> None:
         return (
             [b"bench-batch-input" + le64(base + j) for j in range(batch)],
             [b"bench-batch-ad" + le64(base + j) for j in range(batch)],
-            [rng.randrange(FR) for _ in range(12 * batch)],
+            b"".join(rng.randrange(FR).to_bytes(32, "little") for _ in range(12 * batch)),  # blinding rows as wire bytes
         )
 
     launches0 = eng.ctx.library.launch_count()

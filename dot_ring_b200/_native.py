@@ -535,7 +535,11 @@ class NativeRing:
         proofs = ctypes.create_string_buffer(784 * max(n, 1))
         status = U32()
         zk = None
-        if zk_rows is not None:
+        if isinstance(zk_rows, (bytes, bytearray)):  # already 12 x 32-byte little-endian values per proof
+            if len(zk_rows) != 12 * 32 * n:
+                raise ValueError("zk_rows must hold 12 field elements per proof")
+            zk = bytes(zk_rows)
+        elif zk_rows is not None:
             if len(zk_rows) != 12 * n:
                 raise ValueError("zk_rows must hold 12 field elements per proof")
             zk = b"".join(int(v).to_bytes(32, "little") for v in zk_rows)

@@ -21,7 +21,7 @@
 namespace dr {
 
 constexpr uint32_t MSM_UNIT = 16;     // points per work unit (small units keep the lanes of a warp in step)
-constexpr uint32_t MSM_SEGMENT = 64;  // buckets per running-sum segment
+constexpr uint32_t MSM_SEGMENT = 16;  // buckets per running-sum segment (short serial chains; the segments are tree-folded)
 
 struct MsmGeom {
     uint32_t n, c, W, H;  // H = 2^(c-1) buckets per window

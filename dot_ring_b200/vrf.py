@@ -332,7 +332,7 @@ class RingVRF(VRF):
         ring: Ring,
         ring_root: RingRoot | None = None,
         salt: bytes = b"",
-        zk_rows: Sequence[int] | None = None,
+        zk_rows: Sequence[int] | bytes | None = None,
         as_bytes: bool = False,
     ):
         """Prove ``len(alphas)`` items against one ring in one device pass; semantically a loop over ``prove``."""
