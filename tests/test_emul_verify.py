@@ -3,6 +3,7 @@
 import pytest
 
 from dot_ring_b200 import _native
+from tests import edge_cases
 from tests import msm_cases
 from tests import verify_cases as cases
 from tests.host.emul import emulation_library
@@ -50,3 +51,9 @@ def test_w3f_verifier_vectors(ctx):
 def test_g1_msm_vs_oracle(ctx):
     msm_cases.msm_vs_oracle(ctx, [1, 5, 130, 700])
     msm_cases.synthetic_property(ctx, [300])
+
+
+def test_edge_cases(ctx, srs):
+    edge_cases.empty_batches(ctx, srs)
+    edge_cases.ring_capacity_and_bad_keys(srs)
+    edge_cases.ragged_inputs_match_oracle(srs, ((512, 5),), n_items=2)

@@ -135,3 +135,12 @@ def test_python_api_end_to_end_on_gpu():
     finally:
         engine_mod.set_default_engine(None, 0)
         eng.close()
+
+
+def test_edge_cases_and_domain_1024(ctx, srs):
+    """Empty / ragged inputs, capacity limits, malformed keys; byte parity with the oracle prover at N = 512 and N = 1024."""
+    from tests import edge_cases
+
+    edge_cases.empty_batches(ctx, srs)
+    edge_cases.ring_capacity_and_bad_keys(srs)
+    edge_cases.ragged_inputs_match_oracle(srs, ((512, 5), (1024, 300)), n_items=4)
