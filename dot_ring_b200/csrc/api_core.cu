@@ -167,6 +167,13 @@ int dr_ctx_create(int device, dr_ctx** out) {
     if (device < 0 || device >= count) throw Error(DR_EINVAL, "no such CUDA device");
     DR_CUDA(cudaSetDevice(device));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // Fix the per-thread stack once: kernels here need between 0 and ~16 KB of local memory, and letting the runtime grow the
+    // backing store lazily costs a device-wide reallocation (hundreds of ms) whenever a larger kernel follows a smaller one.
+    if (const char* e = getenv("DOT_RING_B200_STACK_BYTES")) {
+        DR_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atol(e)));
+    } else {
+        DR_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+    }
     DR_CUDA(cudaEventCreate(&ctx->ev_start));
     DR_CUDA(cudaEventCreate(&ctx->ev_stop));
 #else

@@ -119,12 +119,13 @@ struct Ring {
     TEAffine padding;
     const struct LagrangeTable* lag = nullptr;  // owned by the Srs (shared by every ring on the same domain)
     VerifierKeyDev vk{};
+    DevBuf<LineCoeffs> vk_lines;
     SuiteDev suite{};
 };
 
 
 VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TEAffine& seed, const uint8_t* label, uint32_t label_len, const uint8_t* g1_0_be96,
-                                 const uint8_t* g2_be192, const uint8_t* fixed_be96);
+                                 const uint8_t* g2_be192, const uint8_t* fixed_be96, DevBuf<LineCoeffs>& lines);
 
 // Fixed-base window table (msm.cuh) for n affine points already on the device.
 void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table);

@@ -25,7 +25,7 @@ struct PairingCheckBody {
 
 
 VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TEAffine& seed, const uint8_t* label, uint32_t label_len, const uint8_t* g1_0_be96,
-                                 const uint8_t* g2_be192, const uint8_t* fixed_be96) {
+                                 const uint8_t* g2_be192, const uint8_t* fixed_be96, DevBuf<LineCoeffs>& lines) {
     if (N < 8 || (N & (N - 1))) throw Error(DR_EINVAL, "domain_size must be a power of two");
     VerifierKeyDev vk{};
     vk.N = N;
@@ -52,6 +52,15 @@ VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TE
     for (int i = 0; i < 2; i++)
         if (!g2_decode_uncompressed(vk.g2[i], g2_be192 + 192 * i)) throw Error(DR_EINVAL, "invalid BLS12-381 G2 encoding in verifier key");
     vk.pc = ctx->pairing_consts();
+    {  // Miller-loop lines of the two fixed G2 points (pairing_warp.cuh), once per verifier key
+        std::vector<LineCoeffs> host(2 * MILLER_LINES);
+        miller_precompute_lines(vk.g2[0], host.data());
+        miller_precompute_lines(vk.g2[1], host.data() + MILLER_LINES);
+        lines.alloc(host.size());
+        h2d(ctx->stream, lines.p, host.data(), host.size() * sizeof(LineCoeffs));
+        stream_sync(ctx->stream);
+        vk.lines = lines.p;
+    }
     // transcript prefix (root.py:54-71, phases.py:72-74): label | "vk" | G1[0] | G2[0..1] | 3 fixed commitments
     Shake128 tr;
     tr.init();
@@ -136,11 +145,22 @@ static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t 
     launch(ctx->stream, Dim3((VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
     uint32_t all = 0;
     if (aggregate) {
-        const uint32_t threads = 128;
-        launch(ctx->stream, Dim3(1), threads, 2 * threads * sizeof(G1) + 16, RingVerifyAggregateBody(), vk, m, (const VerifyState*)vs.p, extra_status, dverdict.p, dall.p);
+        const uint32_t threads = 64;
+        uint32_t nparts = (m + 4 * threads - 1) / (4 * threads);
+        if (nparts > 64) nparts = 64;
+        DevBuf<G1> partial(2 * (size_t)nparts);
+        DevBuf<uint32_t> bad(1);
+        dev_zero(ctx->stream, bad.p, 4);
+        launch(ctx->stream, Dim3(nparts), threads, 2 * threads * sizeof(G1), RingVerifyPartialSumBody(), m, (const VerifyState*)vs.p, extra_status, dverdict.p, partial.p, bad.p);
+        launch(ctx->stream, Dim3(1), 32, ring_verify_warp_smem(), RingVerifyAggregateBody(), vk, (const G1*)partial.p, nparts, (const uint32_t*)bad.p, dall.p);
         d2h(ctx->stream, &all, dall.p, 4);
+        d2h(ctx->stream, verdict, dverdict.p, n);
+        stream_sync(ctx->stream);  // partial / bad go out of scope
     } else {
-        launch(ctx->stream, Dim3((m + 31) / 32), 32, 0, RingVerifyFinishBody(), vk, m, (const VerifyState*)vs.p, extra_status, dverdict.p);
+#ifndef DR_PAIRING_MINB
+#define DR_PAIRING_MINB 8
+#endif
+        launch_lb<32, DR_PAIRING_MINB>(ctx->stream, Dim3(m), 32, ring_verify_warp_smem(), RingVerifyFinishBody(), vk, m, (const VerifyState*)vs.p, extra_status, dverdict.p);
     }
     d2h(ctx->stream, verdict, dverdict.p, n);
     stream_sync(ctx->stream);
@@ -292,8 +312,9 @@ int dr_ring_proof_verify_batch(dr_ctx* c, const dr_verifier_key* key, size_t n, 
     ctx->activate();
     if (all_ok) *all_ok = 1;
     if (!n) return DR_OK;
+    DevBuf<LineCoeffs> lines;
     VerifierKeyDev vk = make_verifier_key(ctx, key->domain_size, fr_param(key->omega), te_param(key->seed), key->label, key->label_len, key->g1_0_be96, key->g2_be192,
-                                          key->fixed_be96);
+                                          key->fixed_be96, lines);
     std::vector<TEAffine> rel(n);
     for (size_t i = 0; i < n; i++) rel[i] = {fr_param(relations_xy64 + 64 * i), fr_param(relations_xy64 + 64 * i + 32)};
     DevBuf<TEAffine> drel(n);

@@ -13,6 +13,7 @@
 // thread per item.  Verdict codes: 1 valid, 0 invalid, 2 malformed (where the reference raises ValueError).
 #pragma once
 #include "pairing.cuh"
+#include "pairing_warp.cuh"
 #include "ring.cuh"
 
 namespace dr {
@@ -243,6 +244,7 @@ struct VerifierKeyDev {
     G1Affine fixed[4];  // C_px, C_py, C_s, [1]_1
     G2Affine g2[2];     // [1]_2, [tau]_2
     PairingConsts pc;
+    const LineCoeffs* lines;  // [2][MILLER_LINES] precomputed Miller-loop lines of g2[0], g2[1] (device memory)
     Shake128 prefix;    // transcript after absorbing the verifier key (root.py:54-71)
 };
 
@@ -448,51 +450,60 @@ DR_HD void ring_verify_sides(const VerifyState& s, G1& lhs, G1& rhs) {
     g1_add(rhs, s.term[8]);
 }
 
-// per-item verdicts: one pairing check per proof.  extra_status: Pedersen status per proof (or null).
+// per-item verdicts: one 32-thread block per proof runs the warp-cooperative pairing check.
+// extra_status: Pedersen status per proof (or null).
+DR_HD size_t ring_verify_warp_smem() { return sizeof(PairingWarpState) + 2 * sizeof(G1) + 16; }
 struct RingVerifyFinishBody {
     DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict) const {
-        DR_THREAD_LOOP(t, ctx) {
-            uint32_t p = ctx.bx * ctx.nthreads + t;
-            if (p < count) {
-                const VerifyState& s = vs[p];
-                uint32_t st = s.status | (extra_status ? extra_status[p] : 0u);
-                uint8_t v;
-                if (st & ST_MALFORMED) {
-                    v = 2;
-                } else if (st) {
-                    v = 0;
-                } else {
-                    G1 lhs, rhs;
-                    ring_verify_sides(s, lhs, rhs);
-                    v = pairing_equal(g1_to_affine(lhs), vk.g2[0], g1_to_affine(rhs), vk.g2[1], vk.pc) ? 1 : 0;
-                }
-                verdict[p] = v;
+        PairingWarpState* st = (PairingWarpState*)ctx.smem;
+        G1* P = (G1*)(ctx.smem + ((sizeof(PairingWarpState) + 15) / 16) * 16);
+        const uint32_t p = ctx.bx;
+        if (p >= count) return;
+        const VerifyState& s = vs[p];
+        const uint32_t stt = s.status | (extra_status ? extra_status[p] : 0u);
+        if (stt) {  // uniform over the block
+            DR_THREAD_LOOP(t, ctx) {
+                if (t == 0) verdict[p] = (stt & ST_MALFORMED) ? 2 : 0;
             }
+            return;
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) {
+                G1 lhs = s.term[0];
+                for (int j = 1; j < 7; j++) g1_add(lhs, s.term[j]);
+                for (int j = 9; j < VERIFY_TERMS; j++) g1_add(lhs, s.term[j]);
+                P[0] = lhs;
+            }
+            if (t == 1) {
+                G1 rhs = s.term[7];
+                g1_add(rhs, s.term[8]);
+                P[1] = g1_neg(rhs);  // e(lhs, [1]_2) * e(-rhs, [tau]_2) == 1
+            }
+        }
+        DR_BLOCK_SYNC();
+        pairing_product_is_one_warp(ctx, st, P, vk.lines, vk.pc);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) verdict[p] = st->verdict ? 1 : 0;
         }
     }
 };
 
-// aggregated check (RingVRF.batch_verify, vrf/ring/vrf.py:239-283): one block sums every proof's sides, one pairing.
-// verdict[p] carries the per-item decode / Pedersen status (1 ok, 0 invalid, 2 malformed); *all_ok the batch verdict.
-struct RingVerifyAggregateBody {
-    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict,
-                          uint32_t* all_ok) const {
+// aggregated check (RingVRF.batch_verify, vrf/ring/vrf.py:239-283), stage 1: every block folds a strided share of the proofs'
+// two sides into one (lhs, rhs) pair; verdict[p] carries the per-item decode / Pedersen status (1 ok, 0 invalid, 2 malformed).
+struct RingVerifyPartialSumBody {
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict, G1* partial,
+                          uint32_t* any_bad) const {
         G1* sm = (G1*)ctx.smem;  // 2 * nthreads
-        uint32_t* bad = (uint32_t*)(sm + 2 * ctx.nthreads);
-        DR_THREAD_LOOP(t, ctx) {
-            if (t == 0) *bad = 0;
-        }
-        DR_BLOCK_SYNC();
+        const uint32_t stride_all = ctx.gx * ctx.nthreads;
         DR_THREAD_LOOP(t, ctx) {
             G1 lhs = G1::inf(), rhs = G1::inf();
-            bool any_bad = false;
 #pragma unroll 1
-            for (uint32_t p = t; p < count; p += ctx.nthreads) {
+            for (uint32_t p = ctx.bx * ctx.nthreads + t; p < count; p += stride_all) {
                 const VerifyState& s = vs[p];
                 uint32_t st = s.status | (extra_status ? extra_status[p] : 0u);
                 verdict[p] = (st & ST_MALFORMED) ? 2 : st ? 0 : 1;
                 if (st) {
-                    any_bad = true;
+                    *any_bad = 1;  // racing writers store the same value
                 } else {
                     G1 l, r;
                     ring_verify_sides(s, l, r);
@@ -502,7 +513,6 @@ struct RingVerifyAggregateBody {
             }
             sm[t] = lhs;
             sm[ctx.nthreads + t] = rhs;
-            if (any_bad) *bad = 1;  // racing writers store the same value
         }
         DR_BLOCK_SYNC();
         for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
@@ -518,9 +528,29 @@ struct RingVerifyAggregateBody {
         }
         DR_THREAD_LOOP(t, ctx) {
             if (t == 0) {
-                bool ok = !*bad && pairing_equal(g1_to_affine(sm[0]), vk.g2[0], g1_to_affine(sm[ctx.nthreads]), vk.g2[1], vk.pc);
-                *all_ok = ok ? 1u : 0u;
+                partial[2 * ctx.bx] = sm[0];
+                partial[2 * ctx.bx + 1] = sm[ctx.nthreads];
             }
+        }
+    }
+};
+// stage 2: one block folds the partial pairs and runs the single pairing check
+struct RingVerifyAggregateBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, const G1* partial, uint32_t nparts, const uint32_t* any_bad, uint32_t* all_ok) const {
+        PairingWarpState* st = (PairingWarpState*)ctx.smem;
+        G1* P = (G1*)(ctx.smem + ((sizeof(PairingWarpState) + 15) / 16) * 16);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < 2) {
+                G1 acc = G1::inf();
+#pragma unroll 1
+                for (uint32_t i = 0; i < nparts; i++) g1_add(acc, partial[2 * i + t]);
+                P[t] = t == 0 ? acc : g1_neg(acc);
+            }
+        }
+        DR_BLOCK_SYNC();
+        pairing_product_is_one_warp(ctx, st, P, vk.lines, vk.pc);
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) *all_ok = (!*any_bad && st->verdict) ? 1u : 0u;
         }
     }
 };

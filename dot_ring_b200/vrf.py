@@ -343,15 +343,19 @@ class RingVRF(VRF):
         pks = [bytes(producer_key)] * n if isinstance(producer_key, (bytes, bytearray)) else [bytes(p) for p in producer_key]
         if len(sks) != n or len(pks) != n:
             raise ValueError("secret_key / producer_key must be single values or one per item")
-        # vrf.py:196-197: producer_key must be pk(sk) -- one device scalar multiplication per distinct key pair
-        distinct = sorted(set(zip(sks, pks)))
-        derived = cls.cv.public_keys_from_secrets([sk for sk, _ in distinct])
-        for (_, pk), got in zip(distinct, derived):
-            if pk != got:
-                raise ValueError("producer_key does not match secret_key")
+        # vrf.py:196-197: producer_key must be pk(sk) -- one device scalar multiplication per distinct key pair, remembered per ring
+        cache = ring.__dict__.setdefault("_signer_rows", {})
+        pairs = set(zip(sks, pks))
+        distinct = sorted(pairs - cache.keys())
+        if distinct:
+            derived = cls.cv.public_keys_from_secrets([sk for sk, _ in distinct])
+            for (sk, pk), got in zip(distinct, derived):
+                if pk != got:
+                    raise ValueError("producer_key does not match secret_key")
+                cache[(sk, pk)] = ring.index_of(pk)
         if ring_root is not None and ring_root.encode() != RingRoot.from_ring(ring).encode():
             raise ValueError("ring_root does not match ring")
-        index = {pk: ring.index_of(pk) for _, pk in distinct}
+        index = {pk: cache[(sk, pk)] for sk, pk in pairs}
         if zk_rows is None and not ring.params.test_vectors:
             prime = ring.params.prime
             zk_rows = [secrets.randbelow(prime) for _ in range(12 * n)]

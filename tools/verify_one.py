@@ -18,9 +18,11 @@ ad = [b"bench-batch-ad" + le64(j) for j in range(n)]
 proofs, status = ring.prove_batch(al, ad, [sk] * n, [3] * n, zk_rows=[rng.randrange(fr.R) for _ in range(12 * n)])
 for agg in (False, True):
     co = cases.coeffs_for(n, 1, independent=not agg)
-    for rep in range(2):
+    times = []
+    for rep in range(5):
         t0 = time.perf_counter()
         v, ok = ring.verify_batch(al, ad, proofs, co, aggregate=agg)
-        dt = time.perf_counter() - t0
+        times.append(round((time.perf_counter() - t0) * 1e3, 1))
     assert ok
-    print("aggregate" if agg else "per-item", n, "%.1f ms" % (dt * 1e3), "%.0f verifies/s" % (n / dt), flush=True)
+    dt = min(times) * 1e-3
+    print("aggregate" if agg else "per-item", n, times, "best %.0f verifies/s" % (n / dt), flush=True)
