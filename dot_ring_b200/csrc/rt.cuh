@@ -172,9 +172,15 @@ inline void* dev_alloc(size_t bytes) {
     return p;
 }
 inline void dev_free(void* p) { free(p); }
-inline void h2d(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
-inline void d2h(Stream, void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
-inline void d2d(Stream, void* dst, const void* src, size_t bytes) { memmove(dst, src, bytes); }
+inline void h2d(Stream, void* dst, const void* src, size_t bytes) {
+    if (bytes) memcpy(dst, src, bytes);
+}
+inline void d2h(Stream, void* dst, const void* src, size_t bytes) {
+    if (bytes) memcpy(dst, src, bytes);
+}
+inline void d2d(Stream, void* dst, const void* src, size_t bytes) {
+    if (bytes) memmove(dst, src, bytes);
+}
 inline void dev_zero(Stream, void* dst, size_t bytes) { memset(dst, 0, bytes); }
 inline void stream_sync(Stream) {}
 inline void* host_alloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 16); }
