@@ -7,11 +7,11 @@ Host code is Python and calls the CUDA library ``libdotring_b200.so`` through ct
 Public names mirror ``dot_ring`` (dot_ring/__init__.py:32-77) for the path this engine covers.
 """
 
-from .curve import Bandersnatch
+from .curve import Bandersnatch, Bandersnatch_SHAKE128
 from .kzg import KZG
 from .params import RingProofParams
 from .ring import Ring, RingRoot
 from .vrf import PedersenVRF, RingVRF, TinyVRF
 
-__all__ = ["Bandersnatch", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "TinyVRF", "__version__"]
+__all__ = ["Bandersnatch", "Bandersnatch_SHAKE128", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "TinyVRF", "__version__"]
 __version__ = "0.1.0"

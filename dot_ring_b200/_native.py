@@ -140,6 +140,8 @@ class VrfSuiteStruct(ctypes.Structure):
     _fields_ = [
         ("suite_id_len", ctypes.c_uint32),
         ("h2c_dst_len", ctypes.c_uint32),
+        ("hash_id", ctypes.c_uint32),
+        ("pad", ctypes.c_uint32),
         ("suite_id", c_uint8 * 32),
         ("h2c_dst", c_uint8 * 64),
         ("generator", c_uint8 * 64),
@@ -170,9 +172,13 @@ def _xy64(pt) -> bytes:
     return int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little")
 
 
-def make_suite(suite_id: bytes, h2c_dst: bytes, generator, blinding_base) -> VrfSuiteStruct:
+HASH_IDS = {"sha512": 0, "shake128": 1}
+
+
+def make_suite(suite_id: bytes, h2c_dst: bytes, generator, blinding_base, hash_name: str = "sha512") -> VrfSuiteStruct:
     s = VrfSuiteStruct()
     s.suite_id_len, s.h2c_dst_len = len(suite_id), len(h2c_dst)
+    s.hash_id = HASH_IDS[hash_name]
     _put(s.suite_id, suite_id)
     _put(s.h2c_dst, h2c_dst)
     _put(s.generator, _xy64(generator))
@@ -446,7 +452,7 @@ class RingParamsStruct(ctypes.Structure):
         ("padding_rows", ctypes.c_uint32),
         ("suite_id_len", ctypes.c_uint32),
         ("h2c_dst_len", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32),
+        ("hash_id", ctypes.c_uint32),
         ("omega", c_uint8 * 32),
         ("radix_omega", c_uint8 * 32),
         ("seed", c_uint8 * 64),
@@ -471,12 +477,13 @@ class NativeRing:
     """dr_ring: decoded keys, fixed columns (coefficients + 4x LDE), ring root, transcript prefix."""
 
     def __init__(self, srs: NativeSrs, keys: list[bytes], *, domain_size: int, max_ring_size: int, padding_rows: int, omega: int, radix_omega: int,
-                 seed, blinding_base, padding_point, generator, suite_id: bytes, h2c_dst: bytes):
+                 seed, blinding_base, padding_point, generator, suite_id: bytes, h2c_dst: bytes, hash_name: str = "sha512"):
         self.srs = srs
         self.ctx = srs.ctx
         p = RingParamsStruct()
         p.domain_size, p.max_ring_size, p.padding_rows = domain_size, max_ring_size, padding_rows
         p.suite_id_len, p.h2c_dst_len = len(suite_id), len(h2c_dst)
+        p.hash_id = HASH_IDS[hash_name]
         _fill(p.omega, int(omega).to_bytes(32, "little"))
         _fill(p.radix_omega, int(radix_omega).to_bytes(32, "little"))
         _fill(p.seed, _xy(seed))

@@ -108,6 +108,8 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     memcpy(d.suite_id, prm->suite_id, 32);
     d.dst_len = prm->h2c_dst_len;
     memcpy(d.dst, prm->h2c_dst, 64);
+    if (prm->hash_id > 1) throw Error(DR_EINVAL, "unknown suite hash");
+    d.hash_kind = prm->hash_id;
     d.n_inv = Fr::from_u32(N).inv();
     d.quarter = Fr::from_u32(4).inv();
 
@@ -221,6 +223,7 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     memcpy(ring->suite.suite_id, d.suite_id, 32);
     ring->suite.dst_len = d.dst_len;
     memcpy(ring->suite.dst, d.dst, 64);
+    ring->suite.hash_kind = d.hash_kind;
     *out = (dr_ring*)ring.release();
     DR_API_END
 }

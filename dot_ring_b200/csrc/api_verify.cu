@@ -87,7 +87,7 @@ static TEAffine te_param(const uint8_t* xy) {
     return p;
 }
 static SuiteDev suite_from_abi(const dr_vrf_suite* s) {
-    if (!s || s->suite_id_len > 32 || s->h2c_dst_len > 64) throw Error(DR_EINVAL, "bad suite");
+    if (!s || s->suite_id_len > 32 || s->h2c_dst_len > 64 || s->hash_id > 1) throw Error(DR_EINVAL, "bad suite");
     SuiteDev d{};
     d.generator = te_param(s->generator);
     d.blinding_base = te_param(s->blinding_base);
@@ -95,6 +95,7 @@ static SuiteDev suite_from_abi(const dr_vrf_suite* s) {
     memcpy(d.suite_id, s->suite_id, 32);
     d.dst_len = s->h2c_dst_len;
     memcpy(d.dst, s->h2c_dst, 64);
+    d.hash_kind = s->hash_id;
     return d;
 }
 

@@ -44,6 +44,7 @@ struct RingDev {
     uint8_t suite_id[32];
     uint32_t dst_len;
     uint8_t dst[64];  // hash-to-curve DST (without the trailing length byte)
+    uint32_t hash_kind;  // 0: SHA-512 suite (XMD h2c, counter-mode squeeze), 1: SHAKE128 suite (XOF h2c, direct squeeze)
 };
 
 // Per-proof state (one element of an array in HBM).
@@ -105,40 +106,63 @@ DR_HD void shake_absorb_g1(Shake128& s, const G1Affine& p) {
     s.absorb(b, 96);
 }
 
-// SHA-512 counter-mode squeeze of the VRF transcript (primitives.py:165-174): seed = H(absorbed),
-// block c = H(seed | le64(c)).  `st` already holds the absorbed bytes.
-DR_HD_COLD void vrf_squeeze(const Sha512& st, uint8_t* out, uint32_t size) {
-    Sha512 h = st;
-    uint8_t seed[64];
-    h.final(seed);
-    uint32_t done = 0;
-    for (uint64_t c = 0; done < size; c++) {
-        Sha512 b;
-        b.init();
-        b.update(seed, 64);
-        uint8_t ctr[8];
-        for (int i = 0; i < 8; i++) ctr[i] = (uint8_t)(c >> (8 * i));
-        b.update(ctr, 8);
-        uint8_t blk[64];
-        b.final(blk);
-        for (uint32_t i = 0; i < 64 && done < size; i++) out[done++] = blk[i];
+// The suite's transcript hash (primitives.py:26-55).  Absorb-only until squeezed; squeezing never disturbs the state, so a
+// copy can keep absorbing.  SHA-512 suites squeeze in counter mode (primitives.py:165-174: seed = H(absorbed),
+// block c = H(seed | le64(c))); the SHAKE128 suite squeezes the XOF directly.
+struct VrfHash {
+    uint32_t kind;
+    union {
+        Sha512 sha;
+        Shake128 shake;
+    };
+    DR_HD void init(uint32_t k) {
+        kind = k;
+        if (kind == 0) sha.init();
+        else shake.init();
     }
-}
+    DR_HD void update(const uint8_t* data, uint32_t len) {
+        if (kind == 0) sha.update(data, len);
+        else shake.absorb(data, len);
+    }
+    DR_HD void update_byte(uint8_t b) { update(&b, 1); }
+    DR_HD_COLD void squeeze(uint8_t* out, uint32_t size) const {
+        if (kind != 0) {
+            shake.squeeze_snapshot(out, size);
+            return;
+        }
+        Sha512 h = sha;
+        uint8_t seed[64];
+        h.final(seed);
+        uint32_t done = 0;
+        for (uint64_t c = 0; done < size; c++) {
+            Sha512 b;
+            b.init();
+            b.update(seed, 64);
+            uint8_t ctr[8];
+            for (int i = 0; i < 8; i++) ctr[i] = (uint8_t)(c >> (8 * i));
+            b.update(ctr, 8);
+            uint8_t blk[64];
+            b.final(blk);
+            for (uint32_t i = 0; i < 64 && done < size; i++) out[done++] = blk[i];
+        }
+    }
+};
+DR_HD void vrf_squeeze(const VrfHash& st, uint8_t* out, uint32_t size) { st.squeeze(out, size); }
 DR_HD void fn_to_le_bytes(uint8_t* out, const Fn& x_mont) {
     Fn x = x_mont.from_mont();
     for (int i = 0; i < 8; i++)
         for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(x.v[i] >> (8 * b));
 }
 // primitives.py:66-82 `nonce`
-DR_HD_COLD Fn vrf_nonce(const Sha512& t, const Fn& secret) {
-    Sha512 te = t;
+DR_HD_COLD Fn vrf_nonce(const VrfHash& t, const Fn& secret) {
+    VrfHash te = t;
     te.update_byte(0x10);
     uint8_t sb[32];
     fn_to_le_bytes(sb, secret);
     te.update(sb, 32);
     uint8_t secret_hash[64];
     vrf_squeeze(te, secret_hash, 64);
-    Sha512 tn = t;
+    VrfHash tn = t;
     tn.update_byte(0x11);
     tn.update(secret_hash, 64);
     uint8_t wide[48];
@@ -154,7 +178,7 @@ DR_HD_COLD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {
     fn_raw_limbs(kr, k);
     return te_to_affine(te_mul_raw(p, kr, 8));
 }
-DR_HD void sha_absorb_point(Sha512& s, const TEAffine& p) {
+DR_HD void sha_absorb_point(VrfHash& s, const TEAffine& p) {
     uint8_t b[32];
     te_encode(b, p);
     s.update(b, 32);
@@ -164,6 +188,17 @@ DR_HD void sha_absorb_point(Sha512& s, const TEAffine& p) {
 template <class S>
 DR_HD_COLD void h2c_uniform_bytes(const S& rg, const uint8_t* msg, uint32_t msg_len, uint8_t* out96) {
     uint8_t dst_prime_len = (uint8_t)rg.dst_len;
+    if (rg.hash_kind != 0) {  // expand_message_xof: SHAKE128(msg | I2OSP(96, 2) | DST | I2OSP(len(DST), 1))
+        Shake128 x;
+        x.init();
+        x.absorb(msg, msg_len);
+        uint8_t lib2[2] = {0, 96};
+        x.absorb(lib2, 2);
+        x.absorb(rg.dst, rg.dst_len);
+        x.absorb_byte(dst_prime_len);
+        x.squeeze_snapshot(out96, 96);
+        return;
+    }
     Sha512 h;
     h.init();
     uint8_t zero[48];
@@ -207,8 +242,8 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     TEAffine input = vrf_encode_to_curve(rg, msg, msg_len);
     TEAffine output = te_mul_fn(input, x);
     // vrf_transcript (primitives.py:102-144) with one I/O pair
-    Sha512 tr;
-    tr.init();
+    VrfHash tr;
+    tr.init(rg.hash_kind);
     tr.update(rg.suite_id, rg.suite_id_len);
     tr.update_byte(0x02);
     uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
@@ -219,7 +254,7 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     tr.update(le, 8);
     tr.update(ad, ad_len);
     // blinding factor
-    Sha512 tb = tr;
+    VrfHash tb = tr;
     tb.update_byte(0x12);
     Fn b = vrf_nonce(tb, x);
     TEAffine bb = te_mul_fn(rg.blinding_base, b);
@@ -231,7 +266,7 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     TEAffine kbb = te_mul_fn(rg.blinding_base, kb);
     TEAffine R = te_to_affine(te_add(TEExt::from_affine(kg), TEExt::from_affine(kbb)));
     TEAffine ok = te_mul_fn(input, k);
-    Sha512 tc = tr;
+    VrfHash tc = tr;
     tc.update_byte(0x40);
     sha_absorb_point(tc, R);
     sha_absorb_point(tc, ok);

@@ -24,6 +24,7 @@ struct SuiteDev {  // VRF suite constants (dot_ring/curve/specs/bandersnatch.py:
     uint8_t suite_id[32];
     uint32_t dst_len;
     uint8_t dst[64];
+    uint32_t hash_kind;  // 0 SHA-512, 1 SHAKE128 (ring.cuh: VrfHash)
 };
 
 struct VerifyInput {  // host-packed per item: salt|alpha and ad inside the blob
@@ -64,8 +65,8 @@ DR_HD_COLD uint32_t pedersen_verify_core(const S& su, const TEAffine* pts, const
     load_le_limbs8(ks[1], proof192 + 160, 32);  // sb
     if (Fn::geq_mod(ks[0]) || Fn::geq_mod(ks[1])) return ST_MALFORMED;
     TEAffine input = vrf_encode_to_curve(su, msg, msg_len);
-    Sha512 tr;
-    tr.init();
+    VrfHash tr;
+    tr.init(su.hash_kind);
     tr.update(su.suite_id, su.suite_id_len);
     tr.update_byte(0x02);
     uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
@@ -138,8 +139,8 @@ struct TinyVerifyBody {
                 if (!st) {
                     const TEAffine out = pts[2 * (size_t)i], pk = pts[2 * (size_t)i + 1];
                     TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
-                    Sha512 tr;
-                    tr.init();
+                    VrfHash tr;
+                    tr.init(su.hash_kind);
                     tr.update(su.suite_id, su.suite_id_len);
                     tr.update_byte(0x00);
                     uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
@@ -152,7 +153,7 @@ struct TinyVerifyBody {
                     tr.update(le, 8);
                     tr.update(blob + vi.ad_off, vi.ad_len);
                     // delinearisation scalar z (primitives.py:128-144), merged pair (G + z I, PK + z O)
-                    Sha512 td = tr;
+                    VrfHash td = tr;
                     td.update_byte(0x30);
                     uint8_t zb[16];
                     vrf_squeeze(td, zb, 16);
@@ -201,8 +202,8 @@ struct TinyProveBody {
                 TEAffine pk = te_mul_fn(su.generator, x);
                 TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
                 TEAffine output = te_mul_fn(input, x);
-                Sha512 tr;
-                tr.init();
+                VrfHash tr;
+                tr.init(su.hash_kind);
                 tr.update(su.suite_id, su.suite_id_len);
                 tr.update_byte(0x00);
                 uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
@@ -214,7 +215,7 @@ struct TinyProveBody {
                 for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
                 tr.update(le, 8);
                 tr.update(blob + vi.ad_off, vi.ad_len);
-                Sha512 td = tr;
+                VrfHash td = tr;
                 td.update_byte(0x30);
                 uint8_t zb[16];
                 vrf_squeeze(td, zb, 16);

@@ -44,10 +44,11 @@ class BandersnatchParams:
     hash_to_curve: HashToCurve
     encoding: Encoding
     auxiliary_points: AuxiliaryPoints
+    hash_name: str = "sha512"  # "sha512" | "shake128" (specs/bandersnatch.py:48-144)
 
     @property
     def hash_fn(self):
-        return hashlib.sha512
+        return hashlib.sha512 if self.hash_name == "sha512" else hashlib.shake_128
 
 
 @dataclass(frozen=True)
@@ -128,3 +129,28 @@ BANDERSNATCH_PARAMS = BandersnatchParams(
 )
 
 Bandersnatch = CurveVariant("Bandersnatch", BANDERSNATCH_PARAMS)
+
+# specs/bandersnatch.py:108-144: same curve and auxiliary points, SHAKE128 transcripts and XOF hash-to-curve
+import dataclasses as _dc
+
+BANDERSNATCH_SHAKE128_PARAMS = _dc.replace(
+    BANDERSNATCH_PARAMS,
+    suite_id=b"Bandersnatch-SHAKE128-ELL2-v1",
+    hash_to_curve=HashToCurve(dst=b"Bandersnatch-SHAKE128-ELL2-v1\x60"),
+    hash_name="shake128",
+    auxiliary_points=AuxiliaryPoints(  # derived with the suite's own hash-to-curve (specs/bandersnatch.py:128-139)
+        blinding_base=(
+            6153734995852631824944342602386415873379775188383988340041079006556670120775,
+            27204351599954061630605768787803524395123895650061061132592995395630473050754,
+        ),
+        accumulator_base=(
+            27631238720955528589004064829276283990465032040945349648037876197995278250917,
+            37605358688136619817560700742505556266961225274493904038881144193539047100140,
+        ),
+        padding_point=(
+            1834402953989431481748983728202937234471322740714585873803966488035889514523,
+            52100941849053769665273763352270294131006971127418863694682093199651869272752,
+        ),
+    ),
+)
+Bandersnatch_SHAKE128 = CurveVariant("Bandersnatch_SHAKE128", BANDERSNATCH_SHAKE128_PARAMS)

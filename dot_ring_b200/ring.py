@@ -37,6 +37,7 @@ def _native_ring(engine: Engine, keys: Sequence[bytes], params: RingProofParams)
         generator=p.generator,
         suite_id=p.suite_id,
         h2c_dst=p.hash_to_curve.dst,
+        hash_name=p.hash_name,
     )
 
 

@@ -73,14 +73,14 @@ def _suite_struct(cv: CurveVariant):
     from . import _native
 
     p = cv.curve.params
-    return _native.make_suite(p.suite_id, p.hash_to_curve.dst, p.generator, p.auxiliary_points.blinding_base)
+    return _native.make_suite(p.suite_id, p.hash_to_curve.dst, p.generator, p.auxiliary_points.blinding_base, p.hash_name)
 
 
 def _point_to_hash(cv: CurveVariant, point: bytes, size: int = 32) -> bytes:
     """primitives.py:91-96 over the 32-byte encoding of the output point."""
     from .transcript import _squeeze
 
-    return _squeeze(cv.curve.params.suite_id + bytes([0x20]) + bytes(point), size)
+    return _squeeze(cv.curve.params.suite_id + bytes([0x20]) + bytes(point), size, cv.curve.params.hash_name)
 
 
 @dataclass(frozen=True)

@@ -108,7 +108,7 @@ typedef struct dr_ring_params {
     uint32_t padding_rows;     /* must be 4 (params.py:196-197) */
     uint32_t suite_id_len;
     uint32_t h2c_dst_len;
-    uint32_t reserved;
+    uint32_t hash_id;          /* suite hash: 0 = SHA-512 (Bandersnatch-SHA512-ELL2-v1), 1 = SHAKE128 (Bandersnatch-SHAKE128-ELL2-v1) */
     uint8_t omega[32];         /* params.omega: primitive N-th root of unity */
     uint8_t radix_omega[32];   /* params.radix_omega: primitive 4N-th root (sqrt-extended for 4N > 2048) */
     uint8_t seed[64];          /* accumulator_base */
@@ -170,6 +170,8 @@ int dr_te_mul_batch(dr_ctx* ctx, const uint8_t* points32, size_t n_points, const
 typedef struct dr_vrf_suite {
     uint32_t suite_id_len;
     uint32_t h2c_dst_len;
+    uint32_t hash_id;          /* 0 = SHA-512 suite, 1 = SHAKE128 suite (specs/bandersnatch.py:48-144) */
+    uint32_t pad;
     uint8_t suite_id[32];
     uint8_t h2c_dst[64];
     uint8_t generator[64];     /* affine x | y, 32-byte little-endian each */

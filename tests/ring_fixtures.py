@@ -18,5 +18,5 @@ def native_ring(srs, keys, params: rp.Params):
     return _native.NativeRing(
         srs, list(keys), domain_size=params.domain_size, max_ring_size=params.max_ring_size, padding_rows=params.padding_rows,
         omega=params.omega, radix_omega=params.radix_omega, seed=s.accumulator_base, blinding_base=s.blinding_base,
-        padding_point=s.padding_point, generator=bs.GENERATOR, suite_id=s.suite_id, h2c_dst=s.dst,
+        padding_point=s.padding_point, generator=bs.GENERATOR, suite_id=s.suite_id, h2c_dst=s.dst, hash_name=s.hash_name,
     )  # fmt: skip

@@ -137,3 +137,23 @@ def test_sparse_and_dense_witness_commitments_give_identical_proofs(api):
     assert sparse == dense and sparse[0] != sparse[1]
     root = api.RingRoot.from_ring(ring, params)
     assert cls.verify_batch(sparse, [hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], ring, root) == [1, 1]
+
+
+def test_shake128_suite_through_the_api(api):
+    """Bandersnatch_SHAKE128 (specs/bandersnatch.py:108-144): SHAKE128 transcripts + XOF hash-to-curve, ark-vrf vectors."""
+    cv = api.Bandersnatch_SHAKE128
+    v = load("bandersnatch_shake128_ell2_ring.json")[1]
+    keys = split_keys(hx(v, "ring_pks"))
+    params = api.RingProofParams(test_vectors=True, cv=cv)
+    ring = api.Ring(keys, params)
+    root = api.RingRoot.from_ring(ring, params)
+    assert root.encode().hex() == v["ring_pks_com"]
+    assert cv.public_key_from_secret(hx(v, "sk")) == hx(v, "pk")
+    proof = api.RingVRF[cv].prove(hx(v, "alpha"), hx(v, "ad"), hx(v, "sk"), hx(v, "pk"), ring, root)
+    assert proof.encode() == ring_proof_bytes(v)
+    assert proof.verify(hx(v, "alpha"), hx(v, "ad"), ring, root)
+    assert api.RingVRF[cv].proof_to_hash(proof.pedersen_proof.output_point).hex() == v["beta"]
+    vt = load("bandersnatch_shake128_ell2_tiny.json")[0]
+    tp = api.TinyVRF[cv].prove(hx(vt, "alpha"), hx(vt, "sk"), hx(vt, "ad"))
+    assert tp.encode() == hx(vt, "gamma", "proof_c", "proof_s") and tp.verify(hx(vt, "pk"), hx(vt, "alpha"), hx(vt, "ad"))
+    assert not api.TinyVRF[api.Bandersnatch].decode(tp.encode()).verify(hx(vt, "pk"), hx(vt, "alpha"), hx(vt, "ad"))
