@@ -11,7 +11,7 @@ from .curve import Bandersnatch, Bandersnatch_SHAKE128
 from .kzg import KZG
 from .params import RingProofParams
 from .ring import Ring, RingRoot
-from .vrf import PedersenVRF, RingVRF, TinyVRF
+from .vrf import PedersenVRF, RingVRF, ThinVRF, TinyVRF
 
-__all__ = ["Bandersnatch", "Bandersnatch_SHAKE128", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "TinyVRF", "__version__"]
+__all__ = ["Bandersnatch", "Bandersnatch_SHAKE128", "KZG", "RingProofParams", "Ring", "RingRoot", "RingVRF", "PedersenVRF", "TinyVRF", "ThinVRF", "__version__"]
 __version__ = "0.1.0"

@@ -93,6 +93,8 @@ class Library:
         L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
         L.dr_pedersen_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_tiny_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_thin_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_thin_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
         L.dr_ring_proof_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int)]
         L.dr_ring_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7 + [c_int, c_void_p, POINTER(c_int)]
         L.dr_pairing_check_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
@@ -309,17 +311,20 @@ class Context:
         self.library.check(self.library.lib.dr_pedersen_verify_batch(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(proofs), out))
         return list(out.raw[:n])
 
-    def tiny_verify(self, suite: VrfSuiteStruct, public_keys: list[bytes], inputs: list[bytes], ads: list[bytes], proofs: list[bytes]) -> list[int]:
+    def thin_verify(self, suite: VrfSuiteStruct, public_keys: list[bytes], inputs: list[bytes], ads: list[bytes], proofs: list[bytes]) -> list[int]:
+        return self.tiny_verify(suite, public_keys, inputs, ads, proofs, thin=True)
+
+    def tiny_verify(self, suite: VrfSuiteStruct, public_keys: list[bytes], inputs: list[bytes], ads: list[bytes], proofs: list[bytes], thin: bool = False) -> list[int]:
         n = len(proofs)
-        if any(len(p) != 80 for p in proofs):
-            raise ValueError("invalid Tiny VRF proof length: expected 80")
+        size = 96 if thin else 80
+        if any(len(p) != size for p in proofs):
+            raise ValueError(f"invalid {'Thin' if thin else 'Tiny'} VRF proof length: expected {size}")
         if len(public_keys) != n or any(len(k) != 32 for k in public_keys):
             raise ValueError("public keys must be 32 bytes, one per proof")
         blob, a, b, c, d = pack_items(inputs, ads)
         out = ctypes.create_string_buffer(max(n, 1))
-        self.library.check(
-            self.library.lib.dr_tiny_verify_batch(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(public_keys), b"".join(proofs), out)
-        )
+        fn = self.library.lib.dr_thin_verify_batch if thin else self.library.lib.dr_tiny_verify_batch
+        self.library.check(fn(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(public_keys), b"".join(proofs), out))
         return list(out.raw[:n])
 
     def vrf_prove(self, scheme: str, suite: VrfSuiteStruct, inputs: list[bytes], ads: list[bytes], secret_keys: list[bytes]) -> list[bytes]:
@@ -327,8 +332,8 @@ class Context:
         n = len(inputs)
         if len(secret_keys) != n or any(len(k) != 32 for k in secret_keys):
             raise ValueError("secret keys must be 32 bytes, one per item")
-        size = {"pedersen": 192, "tiny": 80}[scheme]
-        fn = self.library.lib.dr_pedersen_prove_batch if scheme == "pedersen" else self.library.lib.dr_tiny_prove_batch
+        size = {"pedersen": 192, "tiny": 80, "thin": 96}[scheme]
+        fn = {"pedersen": self.library.lib.dr_pedersen_prove_batch, "tiny": self.library.lib.dr_tiny_prove_batch, "thin": self.library.lib.dr_thin_prove_batch}[scheme]
         blob, a, b, c, d = pack_items(inputs, ads)
         out = ctypes.create_string_buffer(size * max(n, 1))
         self.library.check(fn(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(secret_keys), out))

@@ -237,39 +237,51 @@ int dr_pedersen_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, con
     DR_API_END
 }
 
-int dr_tiny_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
-                         const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs80, uint8_t* verdict) {
-    DR_API_BEGIN
-    Ctx* ctx = (Ctx*)c;
-    if (!ctx || (n && (!public_keys32 || !proofs80 || !verdict))) throw Error(DR_EINVAL, "bad argument");
+// thin == 0: Tiny (80-byte proofs, points O | PK per item); thin != 0: Thin (96-byte proofs, points O | R | PK)
+static void ietf_verify_batch(Ctx* ctx, const dr_vrf_suite* suite, uint32_t thin, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len,
+                              const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs, uint8_t* verdict) {
+    if (!ctx || (n && (!public_keys32 || !proofs || !verdict))) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
-    if (!n) return DR_OK;
+    if (!n) return;
     SuiteDev su = suite_from_abi(suite);
     ItemsDev items;
     upload_items(ctx, items, n, blob, in_off, in_len, ad_off, ad_len);
-    const uint32_t m = (uint32_t)n;
-    // interleave (output point, public key) so one decode launch covers both
-    std::vector<uint8_t> enc(64 * n);
+    const uint32_t m = (uint32_t)n, npts = thin ? 3 : 2, plen = thin ? 96 : 80;
+    // interleave the proof's points and the public key so one decode launch covers them all
+    std::vector<uint8_t> enc((size_t)32 * npts * n);
     for (size_t i = 0; i < n; i++) {
-        memcpy(&enc[64 * i], proofs80 + 80 * i, 32);
-        memcpy(&enc[64 * i + 32], public_keys32 + 32 * i, 32);
+        memcpy(&enc[32 * npts * i], proofs + plen * i, 32 * (npts - 1));
+        memcpy(&enc[32 * npts * i + 32 * (npts - 1)], public_keys32 + 32 * i, 32);
     }
-    DevBuf<uint8_t> denc(64 * n), dpr(80 * n), dok(2 * n);
-    DevBuf<TEAffine> pts(2 * n);
+    DevBuf<uint8_t> denc(enc.size()), dpr((size_t)plen * n), dok((size_t)npts * n);
+    DevBuf<TEAffine> pts((size_t)npts * n);
     DevBuf<uint32_t> dst(n);
-    h2d(ctx->stream, denc.p, enc.data(), 64 * n);
-    h2d(ctx->stream, dpr.p, proofs80, 80 * n);
-    launch(ctx->stream, Dim3((2 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)denc.p, 64u, 2u, 2 * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, TinyVerifyBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p,
+    h2d(ctx->stream, denc.p, enc.data(), enc.size());
+    h2d(ctx->stream, dpr.p, proofs, (size_t)plen * n);
+    launch(ctx->stream, Dim3((npts * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)denc.p, 32u * npts, npts, npts * m, pts.p, dok.p);
+    launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfVerifyBody(), su, thin, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p,
            (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
     status_to_verdict(st, verdict);
+}
+
+int dr_tiny_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                         const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs80, uint8_t* verdict) {
+    DR_API_BEGIN
+    ietf_verify_batch((Ctx*)c, suite, 0, n, blob, in_off, in_len, ad_off, ad_len, public_keys32, proofs80, verdict);
     DR_API_END
 }
 
-// kind 0: Pedersen (192-byte proofs), 1: Tiny (80-byte proofs)
+int dr_thin_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                         const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs96, uint8_t* verdict) {
+    DR_API_BEGIN
+    ietf_verify_batch((Ctx*)c, suite, 1, n, blob, in_off, in_len, ad_off, ad_len, public_keys32, proofs96, verdict);
+    DR_API_END
+}
+
+// kind 0: Pedersen (192-byte proofs), 1: Tiny (80-byte proofs), 2: Thin (96-byte proofs)
 static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len,
                             const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* sks32, uint8_t* out) {
     if (!ctx || (n && (!sks32 || !out))) throw Error(DR_EINVAL, "bad argument");
@@ -278,14 +290,15 @@ static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_
     SuiteDev su = suite_from_abi(suite);
     ItemsDev items;
     upload_items(ctx, items, n, blob, in_off, in_len, ad_off, ad_len);
-    const size_t len = kind == 0 ? 192 : 80;
+    const size_t len = kind == 0 ? 192 : kind == 1 ? 80 : 96;
     DevBuf<uint8_t> dsk(n * 32), dout(n * len);
     h2d(ctx->stream, dsk.p, sks32, n * 32);
     const uint32_t m = (uint32_t)n;
     if (kind == 0)
         launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenProveStandaloneBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dsk.p, m, dout.p);
     else
-        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, TinyProveBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dsk.p, m, dout.p);
+        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfProveBody(), su, kind == 2 ? 1u : 0u, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p,
+               (const uint8_t*)dsk.p, m, dout.p);
     d2h(ctx->stream, out, dout.p, n * len);
     stream_sync(ctx->stream);
 }
@@ -301,6 +314,13 @@ int dr_tiny_prove_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const ui
                         const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs80) {
     DR_API_BEGIN
     vrf_prove_batch((Ctx*)c, suite, 1, n, blob, in_off, in_len, ad_off, ad_len, secret_keys32, proofs80);
+    DR_API_END
+}
+
+int dr_thin_prove_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                        const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs96) {
+    DR_API_BEGIN
+    vrf_prove_batch((Ctx*)c, suite, 2, n, blob, in_off, in_len, ad_off, ad_len, secret_keys32, proofs96);
     DR_API_END
 }
 

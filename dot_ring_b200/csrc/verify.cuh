@@ -121,28 +121,33 @@ struct PedersenVerifyBody {
     }
 };
 
-// Tiny (IETF) verification, one thread per item; pts = [O_i, PK_i] decoded by TeDecodeManyBody.
-// proofs80: O (32) | c (16) | s (32).  status bit0 malformed, bit1 invalid.
-struct TinyVerifyBody {
-    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs80, const TEAffine* pts, const uint8_t* ok,
-                          uint32_t count, uint32_t* status) const {
+// Tiny (ietf/tiny.py:72-83) and Thin (ietf/thin.py:84-99) verification, one thread per item.  Both schemes share the
+// transcript over the two I/O pairs (G, PK), (I, O) and the delinearised pair (G + z I, PK + z O); they differ in the
+// scheme byte and in what the proof carries:  tiny  O (32) | c (16) | s (32): recompute R, compare the challenge;
+//                                              thin  O (32) | R (32) | s (32): derive c from R, check s I' - c O' == R.
+// pts = decoded points per item: [O, PK] (tiny) or [O, R, PK] (thin).  status bit0 malformed, bit1 invalid.
+struct IetfVerifyBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, uint32_t thin, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, const TEAffine* pts,
+                          const uint8_t* ok, uint32_t count, uint32_t* status) const {
+        const uint32_t npts = thin ? 3 : 2, plen = thin ? 96 : 80;
         DR_THREAD_LOOP(t, ctx) {
             uint32_t i = ctx.bx * ctx.nthreads + t;
             if (i < count) {
                 const VerifyInput& vi = in[i];
-                const uint8_t* pr = proofs80 + 80 * (size_t)i;
+                const uint8_t* pr = proofs + (size_t)plen * i;
                 uint32_t st = 0;
                 uint32_t ks[2][8];
-                load_le_limbs8(ks[0], pr + 48, 32);  // s
-                load_le_limbs8(ks[1], pr + 32, 16);  // c
-                if (!ok[2 * (size_t)i] || !ok[2 * (size_t)i + 1] || Fn::geq_mod(ks[0])) st = ST_MALFORMED;
+                load_le_limbs8(ks[0], pr + (thin ? 64 : 48), 32);  // s
+                bool decoded = true;
+                for (uint32_t j = 0; j < npts; j++) decoded = decoded && ok[(size_t)npts * i + j];
+                if (!decoded || Fn::geq_mod(ks[0])) st = ST_MALFORMED;
                 if (!st) {
-                    const TEAffine out = pts[2 * (size_t)i], pk = pts[2 * (size_t)i + 1];
+                    const TEAffine out = pts[(size_t)npts * i], pk = pts[(size_t)npts * i + npts - 1];
                     TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
                     VrfHash tr;
                     tr.init(su.hash_kind);
                     tr.update(su.suite_id, su.suite_id_len);
-                    tr.update_byte(0x00);
+                    tr.update_byte(thin ? 0x01 : 0x00);
                     uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
                     tr.update(le, 8);
                     sha_absorb_point(tr, su.generator);
@@ -162,14 +167,24 @@ struct TinyVerifyBody {
                     TEExt min = te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4));
                     TEExt mout = te_add(TEExt::from_affine(pk), te_mul_raw(out, z, 4));
                     TEAffine p2[2] = {te_to_affine(min), te_neg(te_to_affine(mout))};
-                    TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
                     tr.update_byte(0x40);
-                    sha_absorb_point(tr, r);
-                    uint8_t cb[16];
-                    vrf_squeeze(tr, cb, 16);
-                    bool same = true;
-                    for (int b = 0; b < 16; b++) same = same && (cb[b] == pr[32 + b]);
-                    if (!same) st = ST_PEDERSEN_BAD;
+                    if (thin) {
+                        const TEAffine r = pts[(size_t)npts * i + 1];
+                        sha_absorb_point(tr, r);
+                        uint8_t cb[16];
+                        vrf_squeeze(tr, cb, 16);
+                        load_le_limbs8(ks[1], cb, 16);
+                        if (!te_ext_eq_affine(te_msm_small(p2, ks, 2), r)) st = ST_PEDERSEN_BAD;
+                    } else {
+                        load_le_limbs8(ks[1], pr + 32, 16);  // c
+                        TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
+                        sha_absorb_point(tr, r);
+                        uint8_t cb[16];
+                        vrf_squeeze(tr, cb, 16);
+                        bool same = true;
+                        for (int b = 0; b < 16; b++) same = same && (cb[b] == pr[32 + b]);
+                        if (!same) st = ST_PEDERSEN_BAD;
+                    }
                 }
                 status[i] = st;
             }
@@ -192,8 +207,10 @@ struct PedersenProveStandaloneBody {
     }
 };
 
-struct TinyProveBody {
-    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count, uint8_t* out80) const {
+struct IetfProveBody {  // thin == 0: O | c | s (80 bytes);  thin != 0: O | R | s (96 bytes)
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, uint32_t thin, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count,
+                          uint8_t* out) const {
+        const uint32_t plen = thin ? 96 : 80;
         DR_THREAD_LOOP(t, ctx) {
             uint32_t i = ctx.bx * ctx.nthreads + t;
             if (i < count) {
@@ -205,7 +222,7 @@ struct TinyProveBody {
                 VrfHash tr;
                 tr.init(su.hash_kind);
                 tr.update(su.suite_id, su.suite_id_len);
-                tr.update_byte(0x00);
+                tr.update_byte(thin ? 0x01 : 0x00);
                 uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
                 tr.update(le, 8);
                 sha_absorb_point(tr, su.generator);
@@ -226,11 +243,18 @@ struct TinyProveBody {
                 TEAffine r = te_mul_fn(min, k);
                 tr.update_byte(0x40);
                 sha_absorb_point(tr, r);
-                uint8_t* o = out80 + 80 * (size_t)i;
-                vrf_squeeze(tr, o + 32, 16);
-                Fn c = fp_from_le_bytes_mod<Fn>(o + 32, 16);
+                uint8_t* o = out + (size_t)plen * i;
+                uint8_t cb[16];
+                vrf_squeeze(tr, cb, 16);
+                Fn c = fp_from_le_bytes_mod<Fn>(cb, 16);
                 te_encode(o, output);
-                fn_to_le_bytes(o + 48, k + c * x);
+                if (thin) {
+                    te_encode(o + 32, r);
+                    fn_to_le_bytes(o + 64, k + c * x);
+                } else {
+                    for (int b = 0; b < 16; b++) o[32 + b] = cb[b];
+                    fn_to_le_bytes(o + 48, k + c * x);
+                }
             }
         }
     }

@@ -149,6 +149,84 @@ class TinyVRF(VRF):
 
 
 @dataclass(frozen=True)
+class ThinVRF(VRF):
+    """ietf/thin.py:38-152: gamma (32) | R (32) | s (32)."""
+
+    output_point: bytes
+    r: bytes
+    s: int
+
+    @classmethod
+    def proof_len(cls) -> int:
+        return 96
+
+    @classmethod
+    def decode(cls, proof: bytes) -> "ThinVRF":
+        if len(proof) != 96:
+            raise ValueError(f"invalid Thin VRF proof length: expected 96, got {len(proof)}")
+        from .engine import default_engine
+
+        proof = bytes(proof)
+        if any(p is None for p in default_engine().ctx.te_decode([proof[:32], proof[32:64]], checked=True)):
+            raise ValueError("Invalid point encoding")
+        return cls(proof[:32], proof[32:64], _dec_scalar(cls.cv, proof[64:96]))
+
+    def encode(self) -> bytes:
+        return self.output_point + self.r + self.s.to_bytes(32, "little")
+
+    @classmethod
+    def prove(cls, alpha: bytes, secret_key: bytes, additional_data: bytes, salt: bytes = b"") -> "ThinVRF":
+        return cls.prove_batch([alpha], [secret_key], [additional_data], [salt])[0]
+
+    @classmethod
+    def prove_batch(cls, alphas, secret_keys, additional_data, salts=None, as_bytes: bool = False):
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(alphas)
+        raw = default_engine().ctx.vrf_prove(
+            "thin", _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, alphas, strict=True)], [bytes(d) for d in additional_data], [bytes(k) for k in secret_keys]
+        )
+        if as_bytes:
+            return raw
+        return [cls(p[:32], p[32:64], int.from_bytes(p[64:], "little")) for p in raw]
+
+    def verify(self, public_key: bytes, input: bytes, additional_data: bytes, salt: bytes = b"") -> bool:
+        """ietf/thin.py:84-99; an undecodable public key raises ValueError as in the reference."""
+        if len(public_key) != 32:
+            raise ValueError("Invalid public key")
+        from .engine import default_engine
+
+        if default_engine().ctx.te_decode([bytes(public_key)], checked=True)[0] is None:
+            raise ValueError("Invalid public key")
+        return self.verify_batch([self], [public_key], [input], [additional_data], [salt])[0] == 1
+
+    @classmethod
+    def verify_batch(cls, proofs, public_keys, inputs, additional_data, salts=None) -> list[int]:
+        """Per-item verdicts: 1 valid, 0 invalid, 2 malformed."""
+        from .engine import default_engine
+
+        salts = salts or [b""] * len(proofs)
+        raw = [bytes(p) if isinstance(p, (bytes, bytearray)) else p.encode() for p in proofs]
+        return default_engine().ctx.thin_verify(
+            _suite_struct(cls.cv), [bytes(k) for k in public_keys], [bytes(s) + bytes(a) for s, a in zip(salts, inputs, strict=True)], [bytes(d) for d in additional_data], raw
+        )
+
+    @classmethod
+    def batch_verify(cls, proofs, public_keys, inputs, additional_data, salts=None) -> bool:
+        """ietf/thin.py:108-152: True iff every proof verifies; malformed input / mismatched lengths -> False."""
+        try:
+            if not (len(proofs) == len(public_keys) == len(inputs) == len(additional_data)) or (salts is not None and len(salts) != len(proofs)):
+                return False
+            return all(v == 1 for v in cls.verify_batch(proofs, public_keys, inputs, additional_data, salts))
+        except (AssertionError, AttributeError, TypeError, ValueError):
+            return False
+
+    @classmethod
+    def proof_to_hash(cls, gamma: bytes, mul_cofactor: bool = False) -> bytes:
+        return PedersenVRF[cls.cv].proof_to_hash(gamma, mul_cofactor)
+
+
+@dataclass(frozen=True)
 class PedersenVRF(VRF):
     """gamma || Y_bar || R || O_k || s || s_b (points as 32-byte encodings)."""
 

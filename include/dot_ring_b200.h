@@ -182,6 +182,13 @@ int dr_pedersen_verify_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, c
 int dr_tiny_verify_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
                          const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs80, uint8_t* verdict);
 
+/* Thin VRF (dot_ring/vrf/ietf/thin.py:38-152): proofs96 = O | R | s.  dr_thin_verify_batch replaces `ThinVRF.decode` + `.verify` per item and,
+ * as the conjunction of the verdicts, `ThinVRF.batch_verify`; dr_thin_prove_batch replaces `ThinVRF.prove`. */
+int dr_thin_verify_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                         const uint32_t* ad_len, const uint8_t* public_keys32, const uint8_t* proofs96, uint8_t* verdict);
+int dr_thin_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                        const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs96);
+
 /* Batched provers for the two plain schemes: `PedersenVRF.prove` (dot_ring/vrf/pedersen/vrf.py:86-126) and `TinyVRF.prove`
  * (dot_ring/vrf/ietf/tiny.py:35-70); nonces are the reference's deterministic transcript nonces (primitives.py:66-82). */
 int dr_pedersen_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,

@@ -70,6 +70,48 @@ def tiny_verify(suite: bs.Suite, proof: TinyProof, public_key: bytes, alpha: byt
     return proof.c == tr.challenge(suite, [r], t)
 
 
+# ---- Thin (ietf/thin.py:38-106) ---------------------------------------------------
+
+
+@dataclass
+class ThinProof:
+    output_point: tuple
+    r: tuple
+    s: int
+
+    def encode(self) -> bytes:
+        return bs.point_to_string(self.output_point) + bs.point_to_string(self.r) + tr.enc_scalar(self.s)
+
+    @classmethod
+    def decode(cls, data: bytes) -> "ThinProof":
+        if len(data) != 96:
+            raise ValueError(f"invalid Thin VRF proof length: expected 96, got {len(data)}")
+        return cls(bs.dec_point(data[:32]), bs.dec_point(data[32:64]), dec_scalar(data[64:]))
+
+
+def thin_prove(suite: bs.Suite, alpha: bytes, secret_key: bytes, ad: bytes, salt: bytes = b"") -> ThinProof:
+    x = tr.dec_scalar_mod(secret_key)
+    pk = bs.mul(bs.GENERATOR, x)
+    inp = bs.encode_to_curve(suite, alpha, salt)
+    out = bs.mul(inp, x)
+    t, merged = tr.vrf_transcript(suite, tr.THIN_VRF, [(bs.GENERATOR, pk), (inp, out)], ad)
+    k = tr.nonce(suite, x, t)
+    r = bs.mul(merged[0], k)
+    c = tr.challenge(suite, [r], t)
+    return ThinProof(out, r, (k + c * x) % bs.N)
+
+
+def thin_verify(suite: bs.Suite, proof: ThinProof, public_key: bytes, alpha: bytes, ad: bytes, salt: bytes = b"") -> bool:
+    inp = bs.encode_to_curve(suite, alpha, salt)
+    try:
+        pk = bs.dec_point(public_key)
+    except ValueError as exc:
+        raise ValueError("Invalid public key") from exc
+    t, merged = tr.vrf_transcript(suite, tr.THIN_VRF, [(bs.GENERATOR, pk), (inp, proof.output_point)], ad)
+    c = tr.challenge(suite, [proof.r], t)
+    return bs.msm([merged[0], merged[1]], [proof.s, -c]) == proof.r
+
+
 # ---- Pedersen ------------------------------------------------------------------
 
 

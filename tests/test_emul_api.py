@@ -157,3 +157,23 @@ def test_shake128_suite_through_the_api(api):
     tp = api.TinyVRF[cv].prove(hx(vt, "alpha"), hx(vt, "sk"), hx(vt, "ad"))
     assert tp.encode() == hx(vt, "gamma", "proof_c", "proof_s") and tp.verify(hx(vt, "pk"), hx(vt, "alpha"), hx(vt, "ad"))
     assert not api.TinyVRF[api.Bandersnatch].decode(tp.encode()).verify(hx(vt, "pk"), hx(vt, "alpha"), hx(vt, "ad"))
+
+
+def test_thin_vrf_api(api):
+    cls = api.ThinVRF[api.Bandersnatch]
+    vs = load("bandersnatch_sha-512_ell2_thin.json")
+    v = vs[2]
+    proof = cls.prove(hx(v, "alpha"), hx(v, "sk"), hx(v, "ad"))
+    assert proof.encode() == hx(v, "gamma", "proof_r", "proof_s")
+    assert cls.decode(proof.encode()).verify(hx(v, "pk"), hx(v, "alpha"), hx(v, "ad"))
+    assert not proof.verify(hx(v, "pk"), b"other", hx(v, "ad"))
+    assert cls.proof_to_hash(proof.output_point).hex() == v["beta"]
+    two = [cls.decode(hx(x, "gamma", "proof_r", "proof_s")) for x in vs[:2]]
+    args = ([hx(x, "pk") for x in vs[:2]], [hx(x, "alpha") for x in vs[:2]], [hx(x, "ad") for x in vs[:2]])
+    assert cls.batch_verify(two, *args)
+    flipped = cls(two[1].output_point, two[1].r, (two[1].s + 1) % api.Bandersnatch.curve.params.subgroup_order)
+    assert not cls.batch_verify([two[0], flipped], *args)  # tests/test_ark_vrf.py:135-165
+    with pytest.raises(ValueError):
+        cls.decode(b"\x00" * 95)
+    with pytest.raises(ValueError):
+        proof.verify(b"\xff" * 32, hx(v, "alpha"), hx(v, "ad"))

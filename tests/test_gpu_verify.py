@@ -43,6 +43,10 @@ def test_tiny_vectors(ctx):
     cases.tiny_vectors(ctx)
 
 
+def test_thin_vectors(ctx):
+    cases.thin_vectors(ctx)
+
+
 def test_vrf_batch_fixtures(ctx):
     cases.vrf_batch_fixtures(ctx)
 

@@ -35,6 +35,15 @@ def test_tiny_vectors(suite, prefix):
         assert vrf.TinyProof.decode(proof.encode()).encode() == proof.encode()
 
 
+def test_thin_vectors():
+    """tests/test_ark_vrf.py:38-88 for the Thin scheme (only the SHA-512 vector file exists)."""
+    for v in load("bandersnatch_sha-512_ell2_thin.json"):
+        proof = vrf.thin_prove(bs.SHA512, hx(v, "alpha"), hx(v, "sk"), hx(v, "ad"))
+        assert proof.encode() == hx(v, "gamma", "proof_r", "proof_s")
+        assert vrf.thin_verify(bs.SHA512, vrf.ThinProof.decode(proof.encode()), hx(v, "pk"), hx(v, "alpha"), hx(v, "ad"))
+        assert not vrf.thin_verify(bs.SHA512, proof, hx(v, "pk"), hx(v, "alpha"), b"x" + hx(v, "ad"))
+
+
 @pytest.mark.parametrize("suite,prefix", SUITES)
 def test_pedersen_vectors(suite, prefix):
     vecs = load(f"{prefix}_pedersen.json")
