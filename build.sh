@@ -11,27 +11,31 @@ SOURCES=$(ls $SRC/api_*.cu)
 if [ "${1:-}" = "--emul" ]; then
   mkdir -p tests/host
   objs=""
+  pids=""
   for f in $SOURCES; do
     o=tests/host/.emul_$(basename "$f" .cu).o
     g++ -O2 -std=c++17 -fPIC -DDR_HOST_EMULATION -x c++ -c "$f" -o "$o" &
+    pids="$pids $!"
     objs="$objs $o"
   done
-  wait
+  for p in $pids; do wait $p; done  # a failed compile fails the build (set -e)
   g++ -shared -o tests/host/libdotring_emul.so $objs -lpthread
   echo "built tests/host/libdotring_emul.so"
   exit 0
 fi
 mkdir -p $BUILD_DIR
 objs=""
+pids=""
 for f in $SOURCES; do
   o=$BUILD_DIR/$(basename "$f" .cu).o
   if [ ! -f "$o" ] || [ -n "$(find $SRC include -newer "$o" \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' -o -name '*.inc' \) | head -1)" ]; then
     # 381-bit multiplications are called out of line everywhere (fp.cuh): measured on B200, the commit kernel gains 5 % and the
     # per-proof pairing kernel 13x (instruction-cache footprint); -DDR_FQ_MUL_INLINE in NVCC_EXTRA restores inlining for A/B runs
     $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA:-} -c "$f" -o "$o" &
+    pids="$pids $!"
   fi
   objs="$objs $o"
 done
-wait
+for p in $pids; do wait $p; done  # a failed compile fails the build (set -e)
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $objs -lcudart
 echo "built $OUT"

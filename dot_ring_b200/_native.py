@@ -71,6 +71,8 @@ class Library:
         L.dr_kzg_commit.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
         L.dr_kzg_commit_bench.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_uint64, POINTER(c_float), c_void_p]
         L.dr_g1_msm.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        L.dr_g1_synthetic_srs.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
+        L.dr_fr_ntt_bench.argtypes = [c_void_p, c_size_t, c_size_t, c_int, c_void_p, POINTER(c_float), c_void_p]
         L.dr_g1_msm_bench.argtypes = [c_void_p, c_size_t, c_int, c_uint64, c_int, c_void_p, POINTER(c_float), POINTER(ctypes.c_uint32), c_void_p]
         L.dr_g1_compress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_g1_decompress.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
@@ -373,6 +375,19 @@ class Context:
         ks = b"".join((int(k) % FR_MODULUS).to_bytes(32, "little") for k in scalars)
         self.library.check(self.library.lib.dr_g1_msm(self.handle, points_be96, ks, count, out))
         return out.raw
+
+    def g1_synthetic_srs(self, tau: int, offset: int, n: int) -> bytes:
+        """n x 96 bytes: tau^(offset + i) * G."""
+        out = ctypes.create_string_buffer(96 * max(n, 1))
+        self.library.check(self.library.lib.dr_g1_synthetic_srs(self.handle, int(tau).to_bytes(32, "little"), offset, n, out))
+        return out.raw[: 96 * n]
+
+    def fr_ntt_bench(self, n: int, batch: int, iters: int, omega: int) -> tuple[float, int]:
+        """(ms per batched forward transform, first output element) with operands resident on the device."""
+        ms = c_float()
+        first = ctypes.create_string_buffer(32)
+        self.library.check(self.library.lib.dr_fr_ntt_bench(self.handle, n, batch, iters, int(omega).to_bytes(32, "little"), ctypes.byref(ms), first))
+        return float(ms.value), int.from_bytes(first.raw, "little")
 
     def g1_msm_bench(self, n: int, iters: int, seed: int, distribution: int, tau: int) -> tuple[float, int, bytes]:
         """(ms per MSM, window bits, result) of an n-point MSM over the synthetic SRS tau^i * G, operands on the device."""

@@ -19,24 +19,66 @@ const NttPlan& Ctx::plan(uint32_t n, const Fr& omega_mont) {
     p->logn = 0;
     while ((1u << p->logn) < n) p->logn++;
     p->omega = omega_mont;
-    std::vector<Fr> fwd(n / 2 ? n / 2 : 1), inv(n / 2 ? n / 2 : 1);
-    Fr w = Fr::one(), wi = Fr::one(), omega_inv = omega_mont.inv();
-    for (uint32_t k = 0; k < n / 2; k++) {
-        fwd[k] = w;
-        inv[k] = wi;
-        w = w * omega_mont;
-        wi = wi * omega_inv;
-    }
-    p->tw_fwd.alloc(fwd.size());
-    p->tw_inv.alloc(inv.size());
-    h2d(stream, p->tw_fwd.p, fwd.data(), fwd.size() * sizeof(Fr));
-    h2d(stream, p->tw_inv.p, inv.data(), inv.size() * sizeof(Fr));
+    Fr omega_inv = omega_mont.inv();
     Fr ninv = Fr::from_u32(n).inv();
     p->n_inv.alloc(1);
     h2d(stream, p->n_inv.p, &ninv, sizeof(Fr));
-    stream_sync(stream);
+    if (n <= 4096) {
+        std::vector<Fr> fwd(n / 2 ? n / 2 : 1), inv(n / 2 ? n / 2 : 1);
+        Fr w = Fr::one(), wi = Fr::one();
+        for (uint32_t k = 0; k < n / 2; k++) {
+            fwd[k] = w;
+            inv[k] = wi;
+            w = w * omega_mont;
+            wi = wi * omega_inv;
+        }
+        p->tw_fwd.alloc(fwd.size());
+        p->tw_inv.alloc(inv.size());
+        h2d(stream, p->tw_fwd.p, fwd.data(), fwd.size() * sizeof(Fr));
+        h2d(stream, p->tw_inv.p, inv.data(), inv.size() * sizeof(Fr));
+        stream_sync(stream);
+    } else {
+        p->logn1 = (p->logn + 1) / 2;
+        p->logn2 = p->logn - p->logn1;
+        p->n1 = 1u << p->logn1;
+        p->n2 = 1u << p->logn2;
+        for (int dir = 0; dir < 2; dir++) {
+            const Fr base = dir ? omega_inv : omega_mont;
+            std::vector<Fr> full(n), t1(p->n1 / 2), t2(p->n2 / 2);
+            Fr w = Fr::one();
+            for (uint32_t i = 0; i < n; i++) {
+                full[i] = w;
+                w = w * base;
+            }
+            for (uint32_t k = 0; k < p->n1 / 2; k++) t1[k] = full[(size_t)k * p->n2];  // (w^n2)^k
+            for (uint32_t k = 0; k < p->n2 / 2; k++) t2[k] = full[(size_t)k * p->n1];  // (w^n1)^k
+            p->wfull[dir].alloc(n);
+            p->tw1[dir].alloc(t1.size());
+            p->tw2[dir].alloc(t2.size());
+            h2d(stream, p->wfull[dir].p, full.data(), (size_t)n * sizeof(Fr));
+            h2d(stream, p->tw1[dir].p, t1.data(), t1.size() * sizeof(Fr));
+            h2d(stream, p->tw2[dir].p, t2.data(), t2.size() * sizeof(Fr));
+            stream_sync(stream);
+        }
+    }
     plans.push_back(std::move(p));
     return *plans.back();
+}
+
+void ntt_device(Ctx* ctx, const NttPlan& plan, const Fr* in, Fr* out, size_t batch, bool inverse, DevBuf<Fr>& tmp) {
+    const uint32_t n = plan.n;
+    if (n <= 4096) {
+        uint32_t threads = n / 2 < 256 ? (uint32_t)(n / 2 < 32 ? 32 : n / 2) : 256;
+        launch(ctx->stream, Dim3((uint32_t)batch), threads, ntt_smem_bytes(n), NttPlainBody(), in, out, n, plan.logn, (const Fr*)(inverse ? plan.tw_inv.p : plan.tw_fwd.p),
+               (const Fr*)(inverse ? plan.n_inv.p : nullptr));
+        return;
+    }
+    const int dir = inverse ? 1 : 0;
+    tmp.ensure((size_t)n * batch);
+    launch(ctx->stream, Dim3(plan.n2, (uint32_t)batch), 256, ntt_smem_bytes(plan.n1), NttLargePass1Body(), in, tmp.p, plan.n1, plan.logn1, plan.n2, (const Fr*)plan.tw1[dir].p,
+           (const Fr*)plan.wfull[dir].p);
+    launch(ctx->stream, Dim3(plan.n1, (uint32_t)batch), 256, ntt_smem_bytes(plan.n2), NttLargePass2Body(), (const Fr*)tmp.p, out, plan.n1, plan.n2, plan.logn2,
+           (const Fr*)plan.tw2[dir].p, (const Fr*)(inverse ? plan.n_inv.p : nullptr));
 }
 
 void PhaseTimer::mark(Ctx* ctx, int phase) {
@@ -413,7 +455,7 @@ int dr_fr_ntt(dr_ctx* c, uint8_t* data_le32, size_t n, size_t batch, int inverse
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !data_le32 || !omega_le32) throw Error(DR_EINVAL, "bad argument");
-    if (n < 2 || n > 4096 || (n & (n - 1))) throw Error(DR_EINVAL, "n must be a power of two in [2, 4096]");
+    if (n < 2 || n > (1u << 22) || (n & (n - 1))) throw Error(DR_EINVAL, "n must be a power of two in [2, 2^22]");
     ctx->activate();
     if (!batch) return DR_OK;
     Fr om;
@@ -423,16 +465,52 @@ int dr_fr_ntt(dr_ctx* c, uint8_t* data_le32, size_t n, size_t batch, int inverse
     const NttPlan& plan = ctx->plan((uint32_t)n, om);
     size_t total = n * batch;
     DevBuf<uint8_t> raw(total * 32);
-    DevBuf<Fr> buf(total);
+    DevBuf<Fr> buf(total), tmp;
     h2d(ctx->stream, raw.p, data_le32, total * 32);
     uint32_t blocks = (uint32_t)((total + 255) / 256);
     launch(ctx->stream, Dim3(blocks), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, buf.p, total, (uint32_t*)nullptr);
-    uint32_t threads = n / 2 < 256 ? (uint32_t)(n / 2 < 32 ? 32 : n / 2) : 256;
-    launch(ctx->stream, Dim3((uint32_t)batch), threads, ntt_smem_bytes((uint32_t)n), NttPlainBody(), (const Fr*)buf.p, buf.p, (uint32_t)n, plan.logn,
-           (const Fr*)(inverse ? plan.tw_inv.p : plan.tw_fwd.p), (const Fr*)(inverse ? plan.n_inv.p : nullptr));
+    ntt_device(ctx, plan, buf.p, buf.p, batch, inverse != 0, tmp);
     launch(ctx->stream, Dim3(blocks), 256, 0, FrFromMontBody(), (const Fr*)buf.p, raw.p, total);
     d2h(ctx->stream, data_le32, raw.p, total * 32);
     stream_sync(ctx->stream);
+    DR_API_END
+}
+
+// Device-resident timing of the batched transform (HBM / integer roofline of the NTT passes): `batch` vectors of n
+// pseudo-random elements, `iters` forward transforms; returns ms per iteration and a checksum element.
+int dr_fr_ntt_bench(dr_ctx* c, size_t n, size_t batch, int iters, const uint8_t omega_le32[32], float* ms_per_iter, uint8_t first_le32[32]) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !omega_le32 || iters <= 0 || n < 2 || n > (1u << 22) || (n & (n - 1)) || !batch) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    Fr om;
+    fr_from_le_bytes_raw(om, omega_le32);
+    if (!om.is_canonical_raw()) throw Error(DR_EINVAL, "omega is not canonical");
+    om = om.to_mont();
+    const NttPlan& plan = ctx->plan((uint32_t)n, om);
+    size_t total = n * batch;
+    std::vector<uint8_t> host(total * 32);
+    uint64_t st = 0x1234567ULL + n;
+    for (size_t i = 0; i < total; i++) {
+        uint64_t w[4] = {splitmix64(st), splitmix64(st), splitmix64(st), splitmix64(st) >> 2};
+        memcpy(&host[32 * i], w, 32);
+    }
+    DevBuf<uint8_t> raw(total * 32);
+    DevBuf<Fr> a(total), b(total), tmp;
+    h2d(ctx->stream, raw.p, host.data(), total * 32);
+    launch(ctx->stream, Dim3((uint32_t)((total + 255) / 256)), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, a.p, total, (uint32_t*)nullptr);
+    ntt_device(ctx, plan, a.p, b.p, batch, false, tmp);  // warm-up (also sizes tmp)
+    stream_sync(ctx->stream);
+    float ms = 0;
+    dr_ctx_timer_start(c);
+    for (int it = 0; it < iters; it++) ntt_device(ctx, plan, a.p, b.p, batch, false, tmp);
+    dr_ctx_timer_stop(c, &ms);
+    if (ms_per_iter) *ms_per_iter = ms / iters;
+    if (first_le32) {
+        launch(ctx->stream, Dim3(1), 32, 0, FrFromMontBody(), (const Fr*)b.p, raw.p, (size_t)1);
+        d2h(ctx->stream, first_le32, raw.p, 32);
+        stream_sync(ctx->stream);
+    }
     DR_API_END
 }
 

@@ -26,8 +26,12 @@ int set_error(int code, const std::string& msg);
 struct NttPlan {
     uint32_t n = 0, logn = 0;
     Fr omega;
-    DevBuf<Fr> tw_fwd, tw_inv, n_inv;
+    DevBuf<Fr> tw_fwd, tw_inv, n_inv;  // n <= 4096: [w^k], [w^-k] for k < n/2
+    // n > 4096 (two-pass transform, ntt.cuh): n = n1 * n2; index 0 forward, 1 inverse
+    uint32_t n1 = 0, n2 = 0, logn1 = 0, logn2 = 0;
+    DevBuf<Fr> wfull[2], tw1[2], tw2[2];
 };
+
 
 struct Ctx;
 
@@ -84,6 +88,9 @@ struct Ctx {
         prove_scratch.reset();
     }
 };
+
+// batch transforms of `n` Montgomery elements each, in place (or in -> out); n a power of two up to 2^22
+void ntt_device(Ctx* ctx, const NttPlan& plan, const Fr* in, Fr* out, size_t batch, bool inverse, DevBuf<Fr>& tmp);
 
 // Window table of S_j = sum_{i<j} [L_i(tau)]_1, j = 1..N, for one evaluation domain (sparse witness commitments).
 struct LagrangeTable {

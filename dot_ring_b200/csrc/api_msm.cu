@@ -130,6 +130,27 @@ int dr_g1_msm(dr_ctx* c, const uint8_t* points_be96, const uint8_t* scalars_le32
     DR_API_END
 }
 
+int dr_g1_synthetic_srs(dr_ctx* c, const uint8_t tau_le32[32], size_t offset, size_t n, uint8_t* out_be96) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !tau_le32 || (n && !out_be96) || offset + n >= (1u << 31)) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    if (!n) return DR_OK;
+    Fr tau;
+    fr_from_le_bytes_raw(tau, tau_le32);
+    if (!tau.is_canonical_raw()) throw Error(DR_EINVAL, "tau is not canonical");
+    tau = tau.to_mont();
+    G1Affine gen;
+    if (!g1_decode(gen, G1_GENERATOR_BE96, 96)) throw Error(DR_ESTATE, "generator decode failed");
+    DevBuf<G1Affine> pts(n);
+    DevBuf<uint8_t> enc(n * 96);
+    launch(ctx->stream, Dim3((uint32_t)((n + 63) / 64)), 64, 0, SyntheticSrsBody(), gen, tau, (uint32_t)offset, (uint32_t)n, pts.p);
+    launch(ctx->stream, Dim3((uint32_t)((n + 63) / 64)), 64, 0, G1EncodeBody(), (const G1Affine*)pts.p, (uint32_t)n, enc.p, (uint8_t*)nullptr);
+    d2h(ctx->stream, out_be96, enc.p, n * 96);
+    stream_sync(ctx->stream);
+    DR_API_END
+}
+
 int dr_g1_msm_bench(dr_ctx* c, size_t n, int iters, uint64_t seed, int distribution, const uint8_t tau_le32[32], float* ms_per_iter, uint32_t* window_bits,
                     uint8_t out_be96[96]) {
     DR_API_BEGIN
@@ -143,7 +164,7 @@ int dr_g1_msm_bench(dr_ctx* c, size_t n, int iters, uint64_t seed, int distribut
     G1Affine gen;
     if (!g1_decode(gen, G1_GENERATOR_BE96, 96)) throw Error(DR_ESTATE, "generator decode failed");
     DevBuf<G1Affine> pts(n);
-    launch(ctx->stream, Dim3((uint32_t)((n + 63) / 64)), 64, 0, SyntheticSrsBody(), gen, tau, (uint32_t)n, pts.p);
+    launch(ctx->stream, Dim3((uint32_t)((n + 63) / 64)), 64, 0, SyntheticSrsBody(), gen, tau, 0u, (uint32_t)n, pts.p);
     // scalars: 0 uniform below 2^254, 1 all ones, 2 bits {0, 1} (witness-like worst case for bucket skew)
     std::vector<uint8_t> host(n * 32, 0);
     uint64_t st = seed;

@@ -76,6 +76,37 @@ struct NttPlainBody {
     }
 };
 
+// ---- transforms larger than one CTA's shared memory (n = n1 * n2, both <= 4096): two passes ----------------------
+//   X[k1 + n1 k2] = sum_{j2} w_{n2}^{j2 k2} * [ w^{j2 k1} * sum_{j1} x[j1 n2 + j2] w_{n1}^{j1 k1} ]
+// Pass 1 (grid n2 x batch): column j2 -> n1-point transform (stride-n2 gather), times w^{j2 k1}, into tmp[j2 n1 + k1].
+// Pass 2 (grid n1 x batch): row k1 -> n2-point transform over tmp[j2 n1 + k1], natural-order scatter to out[k1 + n1 k2].
+// Every element is a full 32-byte sector, so the strided accesses cost no sector efficiency; HBM traffic is two reads and
+// two writes per element.  wfull[i] = w^i for i < n; tw1 / tw2 are the half-size twiddle tables of the two sub-transforms.
+struct NttLargePass1Body {
+    DR_HD void operator()(const BlockCtx& ctx, const Fr* in, Fr* tmp, uint32_t n1, uint32_t logn1, uint32_t n2, const Fr* tw1, const Fr* wfull) const {
+        const size_t n = (size_t)n1 * n2;
+        const Fr* src = in + (size_t)ctx.by * n;
+        Fr* dst = tmp + (size_t)ctx.by * n;
+        const uint32_t j2 = ctx.bx;
+        ntt_block(
+            ctx, n1, logn1, tw1, [&](uint32_t k) { return src[(size_t)k * n2 + j2]; },
+            [&](uint32_t k1, const Fr& v) { dst[(size_t)j2 * n1 + k1] = (j2 && k1) ? v * wfull[(size_t)j2 * k1] : v; });
+    }
+};
+struct NttLargePass2Body {
+    DR_HD void operator()(const BlockCtx& ctx, const Fr* tmp, Fr* out, uint32_t n1, uint32_t n2, uint32_t logn2, const Fr* tw2, const Fr* scale) const {
+        const size_t n = (size_t)n1 * n2;
+        const Fr* src = tmp + (size_t)ctx.by * n;
+        Fr* dst = out + (size_t)ctx.by * n;
+        const uint32_t k1 = ctx.bx;
+        bool has_scale = scale != nullptr;
+        Fr sc = has_scale ? *scale : Fr::one();
+        ntt_block(
+            ctx, n2, logn2, tw2, [&](uint32_t j2) { return src[(size_t)j2 * n1 + k1]; },
+            [&](uint32_t k2, const Fr& v) { dst[k1 + (size_t)n1 * k2] = has_scale ? v * sc : v; });
+    }
+};
+
 // canonical little-endian bytes <-> Montgomery limbs, elementwise
 struct FrToMontBody {
     DR_HD void operator()(const BlockCtx& ctx, const uint8_t* in, Fr* out, size_t count, uint32_t* bad_flag) const {

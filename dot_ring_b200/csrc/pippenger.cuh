@@ -266,13 +266,13 @@ struct MsmFinalBody {
 };
 
 // ---- synthetic SRS for the sweep: P_i = tau^i * G ----------------------------------------------------------------
-struct SyntheticSrsBody {
-    DR_HD void operator()(const BlockCtx& ctx, G1Affine gen, Fr tau, uint32_t n, G1Affine* out) const {
+struct SyntheticSrsBody {  // out[i] = tau^(offset + i) * G
+    DR_HD void operator()(const BlockCtx& ctx, G1Affine gen, Fr tau, uint32_t offset, uint32_t n, G1Affine* out) const {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t i = ctx.bx * ctx.nthreads + t;
             if (i < n) {
                 Fr e = Fr::one(), base = tau;
-                uint32_t k = i;
+                uint32_t k = offset + i;
 #pragma unroll 1
                 while (k) {
                     if (k & 1) e = e * base;

@@ -80,6 +80,9 @@ int dr_kzg_commit_bench(dr_ctx* ctx, dr_srs* srs, size_t n, size_t batch, int it
  * (distribution 0: uniform scalars from splitmix64(seed), 1: all ones, 2: random bits), so the result is checkable as
  * (sum_i k_i tau^i) * G at any size. */
 int dr_g1_msm(dr_ctx* ctx, const uint8_t* points_be96, const uint8_t* scalars_le32, size_t n, uint8_t out_be96[96]);
+/* n points tau^(offset + i) * G, i < n, as 96-byte uncompressed encodings (synthetic SRS slices for sizes the bundled 6145-point
+ * SRS does not cover: the 2^11 .. 2^20 sweep and MSMs split by point range across GPUs). */
+int dr_g1_synthetic_srs(dr_ctx* ctx, const uint8_t tau_le32[32], size_t offset, size_t n, uint8_t* out_be96);
 int dr_g1_msm_bench(dr_ctx* ctx, size_t n, int iters, uint64_t seed, int distribution, const uint8_t tau_le32[32], float* ms_per_iter, uint32_t* window_bits,
                     uint8_t out_be96[96]);
 
@@ -93,8 +96,12 @@ int dr_g1_decompress(dr_ctx* ctx, const uint8_t* in_be48, size_t count, uint8_t*
  * Replaces `BlsScalarNTTPlan.transform/transform_scaled` (ring_proof/polynomial/ntt.pyx:104-163) behind
  * `inverse_fft` / `evaluate_poly_fft` (ring_proof/polynomial/fft.py:87-144): natural order in and out,
  * out[k] = scale * sum_j in[j] * omega^(j*k).  inverse != 0 uses omega^-1 and scale 1/n.
- * data_le32: batch x n elements, transformed in place.  n is a power of two, 2 <= n <= 4096. */
+ * data_le32: batch x n elements, transformed in place.  n is a power of two, 2 <= n <= 2^22 (the reference's plans stop at 4096). */
 int dr_fr_ntt(dr_ctx* ctx, uint8_t* data_le32, size_t n, size_t batch, int inverse, const uint8_t omega_le32[32]);
+/* Same transform with operands resident on the device (`batch` pseudo-random vectors, `iters` forward transforms): ms per
+ * iteration for the HBM / integer roofline of the NTT passes.  n <= 4096: one CTA per transform in shared memory; larger n
+ * (up to 2^22, e.g. the 2^16 / 2^18 domains of a 65k-key ring): two passes n = n1 * n2 through HBM. */
+int dr_fr_ntt_bench(dr_ctx* ctx, size_t n, size_t batch, int iters, const uint8_t omega_le32[32], float* ms_per_iter, uint8_t first_le32[32]);
 
 /* ---- ring: key ingestion, fixed columns, ring root ---------------------------------------------------
  * Replaces `Ring.__init__` (dot_ring/vrf/ring/members.py:22-55: per-key decode + subgroup check, padding,

@@ -76,3 +76,24 @@ def synthetic_property(ctx, sizes, distributions=(0, 1, 2), seed: int = 7):
         for dist in distributions:
             _, _, out = ctx.g1_msm_bench(n, 1, seed, dist, TAU)
             assert out == expected_synthetic(n, seed, dist), (n, dist)
+
+
+def large_ntt(ctx, sizes, oracle_sizes):
+    """dr_fr_ntt beyond one CTA's shared memory (two-pass transform): against the oracle NTT with the root the reference's
+    `_extend_root_to_size` walk gives (params.py:63-115), plus forward/inverse round trips at the larger sizes."""
+    import random as _random
+
+    from dot_ring_b200.params import ROOT_OF_UNITY_2048, _extend_root_to_size, _omega_for_domain
+
+    rng = _random.Random(4)
+    for n in sizes:
+        root, size = _extend_root_to_size(ROOT_OF_UNITY_2048, 2048, n, fr.R)
+        om = _omega_for_domain(n, fr.R, root, size)
+        vals = [rng.randrange(fr.R) for _ in range(2 * n)]  # batch of two
+        got = ctx.fr_ntt(vals, n, om)
+        if n in oracle_sizes:
+            assert got == fr.ntt(vals[:n], om) + fr.ntt(vals[n:], om), n
+        assert ctx.fr_ntt(got, n, om, inverse=True) == vals, n
+    pts = ctx.g1_synthetic_srs(TAU, 5, 3)
+    gen = (bls.G1_GEN[0], bls.G1_GEN[1], 1)
+    assert pts == b"".join(bls.g1_serialize(bls.g1_mul(gen, pow(TAU, 5 + i, fr.R))) for i in range(3))

@@ -55,6 +55,7 @@ def test_w3f_verifier_vectors(ctx):
 def test_g1_msm_vs_oracle(ctx):
     msm_cases.msm_vs_oracle(ctx, [1, 5, 130, 700])
     msm_cases.synthetic_property(ctx, [300])
+    msm_cases.large_ntt(ctx, [8192], {8192})
 
 
 def test_edge_cases(ctx, srs):

@@ -115,3 +115,10 @@ def test_g1_msm_vs_oracle_and_sweep_property(ctx):
     msm_cases.msm_vs_oracle(ctx, [1, 33, 2048, 6145])
     msm_cases.synthetic_property(ctx, [1 << 11, 1 << 14], (0, 1, 2))
     msm_cases.synthetic_property(ctx, [1 << 17, 1 << 20], (0, 2))
+
+
+def test_large_ntt_two_pass(ctx):
+    """n = 2^13, 2^16 against the oracle; 2^18 forward/inverse round trip (the 4x LDE domain of a 65k-key ring)."""
+    from tests import msm_cases
+
+    msm_cases.large_ntt(ctx, [1 << 13, 1 << 16, 1 << 18], {1 << 13, 1 << 16})
