@@ -369,10 +369,15 @@ class Context:
     def g1_msm(self, points_be96: bytes, scalars: list[int]) -> bytes:
         """`KZG.msm_g1` (kzg.py:147-149) over arbitrary points: 96-byte uncompressed result."""
         count = len(points_be96) // 96
-        if len(scalars) != count:
-            raise ValueError("points and scalars must have the same length")
+        if isinstance(scalars, (bytes, bytearray)):  # already 32-byte little-endian each
+            ks = bytes(scalars)
+            if len(ks) != 32 * count:
+                raise ValueError("points and scalars must have the same length")
+        else:
+            if len(scalars) != count:
+                raise ValueError("points and scalars must have the same length")
+            ks = b"".join((int(k) % FR_MODULUS).to_bytes(32, "little") for k in scalars)
         out = ctypes.create_string_buffer(96)
-        ks = b"".join((int(k) % FR_MODULUS).to_bytes(32, "little") for k in scalars)
         self.library.check(self.library.lib.dr_g1_msm(self.handle, points_be96, ks, count, out))
         return out.raw
 
