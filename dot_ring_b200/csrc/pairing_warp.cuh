@@ -71,7 +71,8 @@ DR_HD Fq2* fq12_coeffs(Fq12* a) { return &a->c0.c0; }
 DR_HD const Fq2* fq12_coeffs(const Fq12* a) { return &a->c0.c0; }
 
 // dst = a * b (dst may alias a or b)
-DR_HD void fq12w_mul(const BlockCtx& ctx, PairingWarpState* st, Fq12* dst, const Fq12* a, const Fq12* b) {
+// out of line: called ~600 times per pairing; inlining it everywhere costs registers and instruction-cache misses
+DR_HD_COLD void fq12w_mul(const BlockCtx& ctx, PairingWarpState* st, Fq12* dst, const Fq12* a, const Fq12* b) {
     const Fq2* ca = fq12_coeffs(a);
     const Fq2* cb = fq12_coeffs(b);
     DR_THREAD_LOOP(t, ctx) {
@@ -146,7 +147,7 @@ DR_HD void fq12w_conj(const BlockCtx& ctx, Fq12* dst, const Fq12* src) {
     DR_BLOCK_SYNC();
 }
 // Frobenius: coefficient t is conjugated and scaled by 1, gv1, gv2, gw, gw*gv1, gw*gv2
-DR_HD void fq12w_frob(const BlockCtx& ctx, Fq12* dst, const Fq12* src, const PairingConsts& k) {
+DR_HD_COLD void fq12w_frob(const BlockCtx& ctx, Fq12* dst, const Fq12* src, const PairingConsts& k) {
     DR_THREAD_LOOP(t, ctx) {
         if (t < 6) {
             Fq2 c = fq2_conj(fq12_coeffs(src)[t]);
@@ -159,7 +160,7 @@ DR_HD void fq12w_frob(const BlockCtx& ctx, Fq12* dst, const Fq12* src, const Pai
     DR_BLOCK_SYNC();
 }
 // dst = a^x (x = -|x|; a in the cyclotomic subgroup).  tmp must differ from dst and a.
-DR_HD void fq12w_exp_x(const BlockCtx& ctx, PairingWarpState* st, Fq12* dst, const Fq12* a, Fq12* tmp) {
+DR_HD_COLD void fq12w_exp_x(const BlockCtx& ctx, PairingWarpState* st, Fq12* dst, const Fq12* a, Fq12* tmp) {
     fq12w_copy(ctx, tmp, a);
     for (int b = 62; b >= 0; b--) {
         fq12w_mul(ctx, st, tmp, tmp, tmp);
@@ -170,7 +171,7 @@ DR_HD void fq12w_exp_x(const BlockCtx& ctx, PairingWarpState* st, Fq12* dst, con
 
 // The whole check for one block.  P[i] in XYZZ (infinity allowed: that pair contributes 1); P[1] is negated by the caller
 // when the check is an equality  e(P0, Q0) == e(P1', Q1).  lines: [2][MILLER_LINES] in device memory.  Result in st->verdict.
-DR_HD void pairing_product_is_one_warp(const BlockCtx& ctx, PairingWarpState* st, const G1* P, const LineCoeffs* lines, const PairingConsts& k) {
+DR_HD_COLD void pairing_product_is_one_warp(const BlockCtx& ctx, PairingWarpState* st, const G1* P, const LineCoeffs* lines, const PairingConsts& k) {
     DR_THREAD_LOOP(t, ctx) {
         if (t < 2) {
             const G1& p = P[t];

@@ -37,7 +37,6 @@ DR_HD void load_le_limbs8(uint32_t* out, const uint8_t* in, int nbytes) {
     for (int i = 0; i < 8; i++) out[i] = 0;
     for (int b = 0; b < nbytes; b++) out[b >> 2] |= (uint32_t)in[b] << (8 * (b & 3));
 }
-DR_HD void neg_affine_inplace(TEAffine& p) { p.x = p.x.neg(); }
 
 // ---- decode + subgroup check, one thread per point (vrf/codec.py:39-45) ------------------------------------
 // in: count encodings of 32 bytes at in + stride*(i / per_item) + 32*(i % per_item)

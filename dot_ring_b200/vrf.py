@@ -17,7 +17,6 @@ from dataclasses import dataclass
 from typing import Any, ClassVar
 
 from .curve import Bandersnatch, CurveVariant
-from .params import RingProofParams
 from .ring import Column, Ring, RingRoot
 
 PEDERSEN_LEN = 192

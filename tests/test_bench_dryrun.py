@@ -9,8 +9,6 @@ import subprocess
 import sys
 from pathlib import Path
 
-import pytest
-
 ROOT = Path(__file__).resolve().parents[1]
 KA1_ROOT_SHA256_PREFIX = "963f1e262eba87d5"  # ring 1023 root of the unmodified reference (tests/golden/ring1023_reference.json)
 

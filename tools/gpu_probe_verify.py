@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dot_ring_b200 import _native  # noqa: E402
 from oracle import fr, ring_proof as rp  # noqa: E402
 from tests import verify_cases as cases  # noqa: E402
-from tests.helpers import bench_ring_keys, le64, seed  # noqa: E402
+from tests.helpers import bench_ring_keys, le64  # noqa: E402
 from tests.ring_fixtures import native_ring, native_srs  # noqa: E402
 
 out = {}

@@ -8,6 +8,8 @@ from tests import verify_cases as cases
 from tests.helpers import bench_ring_keys, le64
 from tests.ring_fixtures import native_ring, native_srs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+if os.environ.get("DR_LIB"):
+    _native.set_default_library(_native.Library(os.environ["DR_LIB"]))
 ctx = _native.Context(0)
 srs = native_srs(ctx, None, 10)
 pk, sk, keys = bench_ring_keys(1023)
