@@ -284,7 +284,10 @@ def run_ours(args) -> None:
             "executed_frac": executed / imad_peak,
             "executed_note": f"{madds_per_proof} mixed G1 additions per proof actually issued (fixed-base tables + sparse witness columns) x 6000 IMAD; 'achieved' counts the canonical Pippenger work of all 7 MSMs",
             "peak_source": "measured live: dependent-free mad.lo.u32 on all SMs (dr_microbench); IMAD.WIDE measured " + f"{imad_wide_peak / 1e12:.2f} T/s",
-            "traffic": None,
+            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, 14-bit windows;
+            # profiles/r01_ncu_full_CommitBody_c14.csv) against 11.5 GB of table entries it must touch: 96-byte entries straddle sectors
+            "traffic": 23.1e9,
+            "traffic_launch": "CommitBody grid (2, 1024) x 128 threads, 46.8 ms under ncu; algorithmic table bytes of that launch 11.5e9",
             "algorithmic_table_bytes": table_traffic,
             "hbm_gbs_for_table_reads": table_traffic / (commit_ms * 1e-3) / 1e9,
             "kernel_share_of_step": commit_ms / sum(phases),
