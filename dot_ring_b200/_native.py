@@ -101,6 +101,7 @@ class Library:
         L.dr_ring_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7 + [c_int, c_void_p, POINTER(c_int)]
         L.dr_pairing_check_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_te_decode_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]
+        L.dr_te_msm.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_te_mul_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]
 
     def check(self, code: int) -> None:
@@ -365,6 +366,15 @@ class Context:
         out = ctypes.create_string_buffer(max(n, 1))
         self.library.check(self.library.lib.dr_pairing_check_batch(self.handle, a1_be96, b1_be192, a2_be96, b2_be192, n, out))
         return [bool(b) for b in out.raw[:n]]
+
+    def te_msm(self, points: list[bytes], scalars: list[int]) -> bytes:
+        """`BandersnatchPoint.msm`: sum_i k_i * P_i on 32-byte encodings (ValueError on an undecodable point)."""
+        if len(points) != len(scalars) or any(len(p) != 32 for p in points):
+            raise ValueError("points and scalars must have the same length; points are 32 bytes")
+        out = ctypes.create_string_buffer(32)
+        ks = b"".join((int(k) % BANDERSNATCH_ORDER).to_bytes(32, "little") for k in scalars)
+        self.library.check(self.library.lib.dr_te_msm(self.handle, b"".join(points), ks, len(points), out))
+        return out.raw
 
     def g1_msm(self, points_be96: bytes, scalars: list[int]) -> bytes:
         """`KZG.msm_g1` (kzg.py:147-149) over arbitrary points: 96-byte uncompressed result."""

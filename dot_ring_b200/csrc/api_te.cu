@@ -40,6 +40,56 @@ struct TeMulBody {
     }
 };
 
+// sum_i (k_i mod n) * P_i: one scalar multiplication per thread, shared-memory tree per block -> partial[block] (extended coords)
+struct TeMsmBody {
+    DR_HD void operator()(const BlockCtx& ctx, const uint8_t* pts, const uint8_t* ks, uint32_t n, TEExt* partial, uint32_t* bad) const {
+        TEExt* sm = (TEExt*)ctx.smem;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            TEExt acc = TEExt::identity();
+            if (i < n) {
+                TEAffine p;
+                if (te_decode(p, pts + 32 * (size_t)i)) {
+                    Fn k = fp_from_le_bytes_mod<Fn>(ks + 32 * (size_t)i, 32);
+                    uint32_t kr[8];
+                    fn_raw_limbs(kr, k);
+                    acc = te_mul_raw(p, kr, 8);
+                } else {
+                    *bad = 1;  // racing writers store the same value
+                }
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) { sm[t] = te_add(sm[t], sm[t + stride]); }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) partial[ctx.bx] = sm[0];
+        }
+    }
+};
+struct TeMsmFinishBody {  // one block folds the per-block partial sums and encodes the result
+    DR_HD void operator()(const BlockCtx& ctx, const TEExt* partial, uint32_t nparts, uint8_t* out32) const {
+        TEExt* sm = (TEExt*)ctx.smem;
+        DR_THREAD_LOOP(t, ctx) {
+            TEExt acc = TEExt::identity();
+#pragma unroll 1
+            for (uint32_t i = t; i < nparts; i += ctx.nthreads) acc = te_add(acc, partial[i]);
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) { sm[t] = te_add(sm[t], sm[t + stride]); }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) te_encode(out32, te_to_affine(sm[0]));
+        }
+    }
+};
+
 }  // namespace dr
 
 using namespace dr;
@@ -84,6 +134,37 @@ int dr_te_mul_batch(dr_ctx* c, const uint8_t* points32, size_t n_points, const u
         d2h(ctx->stream, out32, dout.p, n * 32);
         d2h(ctx->stream, ok, dok.p, n);
         stream_sync(ctx->stream);
+    } catch (const Error& e) {
+        return set_error(e.code, e.what());
+    } catch (const std::exception& e) {
+        return set_error(DR_ECUDA, e.what());
+    }
+    return DR_OK;
+}
+
+// Replaces `BandersnatchPoint.msm` (dot_ring/curve/specs/bandersnatch.py:194-286: GLV joint windows for n <= 3,
+// `msm_pippenger_signed_native_cy` above; native_field/bandersnatch_te.pyx:257-418): out = sum_i (scalars[i] mod order) * points[i].
+// Every point is one thread's windowed multiplication, the partial sums are tree-folded.  DR_EINVAL on an undecodable point.
+int dr_te_msm(dr_ctx* c, const uint8_t* points32, const uint8_t* scalars32, size_t n, uint8_t out32[32]) {
+    try {
+        Ctx* ctx = (Ctx*)c;
+        if (!ctx || !out32 || (n && (!points32 || !scalars32))) throw Error(DR_EINVAL, "bad argument");
+        ctx->activate();
+        const uint32_t threads = 64;
+        const uint32_t blocks = n ? (uint32_t)((n + threads - 1) / threads) : 1;
+        DevBuf<uint8_t> dp(n ? n * 32 : 32), dk(n ? n * 32 : 32), dout(32);
+        DevBuf<TEExt> partial(blocks);
+        DevBuf<uint32_t> bad(1);
+        dev_zero(ctx->stream, bad.p, 4);
+        h2d(ctx->stream, dp.p, points32, n * 32);
+        h2d(ctx->stream, dk.p, scalars32, n * 32);
+        launch(ctx->stream, Dim3(blocks), threads, threads * sizeof(TEExt), TeMsmBody(), (const uint8_t*)dp.p, (const uint8_t*)dk.p, (uint32_t)n, partial.p, bad.p);
+        launch(ctx->stream, Dim3(1), threads, threads * sizeof(TEExt), TeMsmFinishBody(), (const TEExt*)partial.p, blocks, dout.p);
+        uint32_t bad_h = 0;
+        d2h(ctx->stream, &bad_h, bad.p, 4);
+        d2h(ctx->stream, out32, dout.p, 32);
+        stream_sync(ctx->stream);
+        if (bad_h) throw Error(DR_EINVAL, "Invalid point encoding");
     } catch (const Error& e) {
         return set_error(e.code, e.what());
     } catch (const std::exception& e) {

@@ -79,6 +79,12 @@ class CurveVariant:
         out = default_engine().ctx.te_mul([gen], [int.from_bytes(sk, "little") for sk in secret_keys])
         return [bytes(o) for o in out]
 
+    def msm(self, points: list[bytes], scalars: list[int]) -> bytes:
+        """`BandersnatchPoint.msm` (specs/bandersnatch.py:194-286) on 32-byte encodings: sum_i k_i * P_i on the device."""
+        from .engine import default_engine
+
+        return default_engine().ctx.te_msm([bytes(p) for p in points], [int(k) for k in scalars])
+
     # dot_ring/curve/curve.py:386-399 + dot_ring/vrf/primitives.py:147-162
     def secret_from_seed(self, seed: bytes) -> tuple[bytes, bytes]:
         if not isinstance(seed, (bytes, bytearray)):

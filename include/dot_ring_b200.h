@@ -166,6 +166,9 @@ int dr_ctx_set_dense_witness_commit(dr_ctx* ctx, int enabled);
  * out[i] = (scalars[i] mod order) * points[i] (or points[0] when n_points == 1). */
 int dr_te_decode_batch(dr_ctx* ctx, const uint8_t* in32, size_t n, int checked, uint8_t* out_xy64, uint8_t* ok);
 int dr_te_mul_batch(dr_ctx* ctx, const uint8_t* points32, size_t n_points, const uint8_t* scalars32, size_t n, uint8_t* out32, uint8_t* ok);
+/* dr_te_msm replaces `BandersnatchPoint.msm` (dot_ring/curve/specs/bandersnatch.py:194-286; native signed Pippenger at
+ * native_field/bandersnatch_te.pyx:257-418): out = sum_i (scalars[i] mod order) * points[i], 32-byte encodings. */
+int dr_te_msm(dr_ctx* ctx, const uint8_t* points32, const uint8_t* scalars32, size_t n, uint8_t out32[32]);
 
 /* ---- VRF verification, batched -------------------------------------------------------------------------------
  * Item i: input = blob[in_off[i] .. +in_len[i]) (salt | alpha), ad = blob[ad_off[i] .. +ad_len[i]).

@@ -101,3 +101,23 @@ def ring_capacity_and_bad_keys(srs):
     v, ok = full.verify_batch([alpha], [ad], proofs, cases.coeffs_for(1))
     assert ok and v == [1]
     full.close()
+
+
+def te_msm_matches_oracle(ctx):
+    """`BandersnatchPoint.msm` sizes 0, 1, 2, 3 (GLV joint-window paths in the reference), 5 and 200 (its Pippenger path);
+    negative / zero / over-order scalars; an undecodable point is a ValueError."""
+    rng = random.Random(17)
+    base = [bs.mul(bs.GENERATOR, rng.randrange(1, bs.N)) for _ in range(200)]
+    enc = [bs.point_to_string(p) for p in base]
+    for n in (0, 1, 2, 3, 5, 200):
+        ks = [rng.randrange(bs.N) for _ in range(n)]
+        if n >= 3:
+            ks[0], ks[1], ks[2] = 0, bs.N - 1, bs.N + 5
+        want = bs.msm(base[:n], [k % bs.N for k in ks]) if n else bs.IDENTITY
+        assert ctx.te_msm(enc[:n], ks) == bs.point_to_string(want), n
+    try:
+        ctx.te_msm([b"\xff" * 32], [1])
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("undecodable point accepted")

@@ -60,5 +60,6 @@ def test_g1_msm_vs_oracle(ctx):
 
 def test_edge_cases(ctx, srs):
     edge_cases.empty_batches(ctx, srs)
+    edge_cases.te_msm_matches_oracle(ctx)
     edge_cases.ring_capacity_and_bad_keys(srs)
     edge_cases.ragged_inputs_match_oracle(srs, ((512, 5),), n_items=2)

@@ -146,5 +146,6 @@ def test_edge_cases_and_domain_1024(ctx, srs):
     from tests import edge_cases
 
     edge_cases.empty_batches(ctx, srs)
+    edge_cases.te_msm_matches_oracle(ctx)
     edge_cases.ring_capacity_and_bad_keys(srs)
     edge_cases.ragged_inputs_match_oracle(srs, ((512, 5), (1024, 300)), n_items=4)
