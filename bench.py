@@ -174,6 +174,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py measures the CUDA build only")
     eng_mod.set_default_engine(eng, local)
     _ = eng.srs
+    eng.ctx.set_commit_mode(args.commit_mode)
     eng.ctx.sync()
     table_s = time.perf_counter() - t0
     info = eng.ctx.device_info()
@@ -411,6 +412,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "14")))
+    ap.add_argument("--commit-mode", type=int, default=int(os.environ.get("DOT_RING_B200_COMMIT_MODE", "0")), help="0 XYZZ accumulation, 1 batched-affine rounds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()

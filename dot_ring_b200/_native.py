@@ -90,6 +90,7 @@ class Library:
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
         L.dr_ctx_set_dense_witness_commit.argtypes = [c_void_p, c_int]
+        L.dr_ctx_set_commit_mode.argtypes = [c_void_p, c_int]
 
         L.dr_pedersen_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
@@ -227,6 +228,10 @@ class Context:
 
     def sync(self) -> None:
         self.library.check(self.library.lib.dr_ctx_sync(self.handle))
+
+    def set_commit_mode(self, mode: int) -> None:
+        """0: XYZZ accumulation, 1: batched-affine pairing rounds (same commitments, cheaper additions)."""
+        self.library.check(self.library.lib.dr_ctx_set_commit_mode(self.handle, mode))
 
     def set_dense_witness_commit(self, enabled: bool) -> None:
         """Commit witness columns from interpolated coefficients (the reference's route) instead of the sparse Lagrange form."""

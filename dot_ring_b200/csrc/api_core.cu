@@ -149,9 +149,37 @@ const LagrangeTable& Srs::lagrange_table(uint32_t N, uint32_t logN, const Fr& om
     return *lagrange.back();
 }
 
+#ifndef DR_COMMIT_MINB
+#define DR_COMMIT_MINB 4
+#endif
+
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
     if (n == 0 || batch == 0) return;
     if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
+    if (ctx->commit_mode == 1 && ((size_t)(n + 31) / 32) * srs->geom.W >= 2 * AFFINE_MIN_PAIRS) {
+        // batched-affine rounds: one warp per (polynomial, slice), persistent CTAs of 4 warps, HBM scratch per resident lane
+        const uint32_t warps = COMMIT_THREADS / 32;
+        const uint32_t resident = 148 * 4;
+        // slices: enough warps to fill the machine, while a lane keeps >= 4 rounds' worth of references
+        uint32_t slices = 1;
+        while (batch * slices < resident * warps && ((size_t)(n + 32 * slices * 2 - 1) / (32 * slices * 2)) * srs->geom.W >= 8 * AFFINE_MIN_PAIRS) slices *= 2;
+        const uint32_t items = batch * slices;
+        uint32_t ctas = (items + warps - 1) / warps;
+        if (ctas > resident) ctas = resident;
+        const uint32_t slots = ctas * warps;
+        uint32_t cap = ((n + 32 * slices - 1) / (32 * slices)) * srs->geom.W;
+        cap = (cap + 3) & ~3u;
+        ctx->aff_refs.ensure((size_t)slots * cap * 32);
+        ctx->aff_prefix.ensure((size_t)slots * (cap / 2) * 32);
+        ctx->aff_a.ensure((size_t)slots * (cap / 2) * 32);
+        ctx->aff_b.ensure((size_t)slots * (cap / 4) * 32);
+        AffineScratch sc{ctx->aff_refs.p, ctx->aff_prefix.p, ctx->aff_a.p, ctx->aff_b.p, cap};
+        ctx->partials.ensure(items);
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(ctas), COMMIT_THREADS, COMMIT_THREADS * sizeof(G1), CommitAffineBody(), (const G1Affine*)srs->table.p,
+                                                  srs->geom, scalars, stride, n, batch, slices, sc, ctx->partials.p);
+        launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
+        return;
+    }
     // enough CTAs to fill the machine: batch * slices >= ~2 waves of 148 SMs x 4 resident CTAs
     uint32_t slices = 1;
     const uint32_t target = 148 * 8;
@@ -163,9 +191,6 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
     }
     ctx->partials.ensure((size_t)batch * slices);
     const uint32_t threads = COMMIT_THREADS;
-#ifndef DR_COMMIT_MINB
-#define DR_COMMIT_MINB 4
-#endif
     launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
     launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
 }
@@ -240,6 +265,14 @@ void dr_ctx_destroy(dr_ctx* c) {
     cudaStreamDestroy(ctx->stream);
 #endif
     delete ctx;
+}
+
+int dr_ctx_set_commit_mode(dr_ctx* c, int mode) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || mode < 0 || mode > 1) throw Error(DR_EINVAL, "bad argument");
+    ctx->commit_mode = mode;
+    DR_API_END
 }
 
 int dr_ctx_sync(dr_ctx* c) {

@@ -66,6 +66,10 @@ struct Ctx {
     PhaseTimer phases;
     std::shared_ptr<void> prove_scratch;
     size_t prove_chunk = 0;
+    int commit_mode = 0;  // 0: XYZZ accumulation (CommitBody), 1: batched-affine pairing rounds (CommitAffineBody)
+    DevBuf<uint32_t> aff_refs;
+    DevBuf<Fq> aff_prefix;
+    DevBuf<G1Affine> aff_a, aff_b;
     bool dense_witness_commit = false;  // A/B + cross-check: commit witness columns from coefficients like the reference
     bool have_pairing_consts = false;
     PairingConsts pairing_k;
@@ -85,6 +89,10 @@ struct Ctx {
     const NttPlan& plan(uint32_t n, const Fr& omega_mont);
     void release_scratch() {
         partials.release();
+        aff_refs.release();
+        aff_prefix.release();
+        aff_a.release();
+        aff_b.release();
         prove_scratch.reset();
     }
 };

@@ -309,6 +309,178 @@ struct CommitBody {
     }
 };
 
+// ---- batched-affine commit --------------------------------------------------------------------------------
+// Same sum as CommitBody, cheaper additions.  Adding two affine points costs 2M + 1S once 1/(x2 - x1) is known, and
+// Montgomery's trick turns P inversions into one inversion + 3(P - 1) multiplications, so a round that adds P independent
+// pairs costs 6 multiplications per addition + 570 / P for the one Fermat inversion, against 10 for an XYZZ mixed addition.
+// The table entries one lane must sum (its points x W windows, ~3.6 k for a 6145-coefficient polynomial over 32 lanes) are
+// independent, so the lane sums them as a binary tree: round 1 pairs table entries, round k pairs the results of round
+// k - 1 (ping-pong buffers in HBM scratch), and once fewer than AFFINE_MIN_PAIRS pairs remain the rest is accumulated in XYZZ
+// coordinates as before.  One warp per polynomial; a persistent grid of CTAs walks the batch so that the scratch is per
+// resident lane.  All exceptional cases of the affine law (infinity operands, P == Q, P == -Q) are exact: the denominator is
+// replaced by 2y (doubling) or 1 (no arithmetic needed) so that they share the batch inversion.
+constexpr uint32_t AFFINE_MIN_PAIRS = 160;
+
+struct AffineScratch {  // per lane, interleaved by lane within the warp: element j of lane l at [j * 32 + l]
+    uint32_t* refs;     // table entry | sign << 31
+    Fq* prefix;
+    G1Affine* buf_a;
+    G1Affine* buf_b;
+    uint32_t cap_refs;  // per lane
+};
+
+DR_HD Fq affine_pair_den(const G1Affine& P, const G1Affine& Q) {
+    if (P.is_inf() || Q.is_inf()) return Fq::one();
+    Fq dx = Q.x - P.x;
+    if (!dx.is_zero()) return dx;
+    if (P.y == Q.y) return P.y.dbl();  // doubling: lambda = 3 x^2 / (2 y); y != 0 in a prime-order group
+    return Fq::one();                  // P == -Q
+}
+DR_HD G1Affine affine_pair_sum(const G1Affine& P, const G1Affine& Q, const Fq& dinv) {
+    if (P.is_inf()) return Q;
+    if (Q.is_inf()) return P;
+    Fq dx = Q.x - P.x;
+    Fq lam;
+    if (!dx.is_zero()) {
+        lam = (Q.y - P.y) * dinv;
+    } else if (P.y == Q.y) {
+        Fq xx = P.x.sqr();
+        lam = (xx.dbl() + xx) * dinv;
+    } else {
+        return G1Affine::inf();
+    }
+    Fq x3 = lam.sqr() - P.x - Q.x;
+    return {x3, lam * (P.x - x3) - P.y};
+}
+
+// out[i] = in(2i) + in(2i + 1) for i < pairs, one inversion for the whole round.  The first sweep needs only the x
+// coordinates (the rare x1 == x2 / x == 0 cases reload the full points); both sweeps fetch the next pair before they use
+// the current one so that the gathers overlap the multiplications.
+template <class Load, class LoadX>
+DR_HD void affine_round(uint32_t pairs, uint32_t lane, const Load& load, const LoadX& load_x, Fq* prefix, G1Affine* out) {
+    Fq acc = Fq::one();
+    Fq nx1 = load_x(0), nx2 = load_x(1);
+#pragma unroll 1
+    for (uint32_t i = 0; i < pairs; i++) {
+        Fq x1 = nx1, x2 = nx2;
+        if (i + 1 < pairs) {
+            nx1 = load_x(2 * i + 2);
+            nx2 = load_x(2 * i + 3);
+        }
+        Fq den = x2 - x1;
+        if (den.is_zero() || x1.is_zero() || x2.is_zero()) den = affine_pair_den(load(2 * i), load(2 * i + 1));  // exact exceptional cases
+        prefix[(size_t)i * 32 + lane] = acc;
+        acc = acc * den;
+    }
+    Fq inv = acc.inv();
+    G1Affine nP = load(2 * (pairs - 1)), nQ = load(2 * (pairs - 1) + 1);
+#pragma unroll 1
+    for (uint32_t i = pairs; i-- > 0;) {
+        G1Affine P = nP, Q = nQ;
+        if (i > 0) {
+            nP = load(2 * i - 2);
+            nQ = load(2 * i - 1);
+        }
+        Fq dinv = inv * prefix[(size_t)i * 32 + lane];
+        inv = inv * affine_pair_den(P, Q);
+        out[(size_t)i * 32 + lane] = affine_pair_sum(P, Q, dinv);
+    }
+}
+
+// grid = persistent CTAs; block = warps_per_cta x 32 lanes.  Work item = (polynomial, slice): the points of a polynomial are
+// dealt to `slices` warps (point i belongs to lane i % 32 of slice (i / 32) % slices), so that small batches still fill the
+// machine.  Warp `wq` of CTA `bx` owns scratch slot bx * warps + wq and walks the work items slot, slot + total_slots, ...
+// partials[msm * slices + slice] = XYZZ sum (CommitFinishBody with `slices` follows).
+struct CommitAffineBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, const Fr* scalars, size_t scalar_stride, uint32_t n, uint32_t batch,
+                          uint32_t slices, AffineScratch sc, G1* partials) const {
+        G1* sm = (G1*)ctx.smem;  // nthreads entries
+        const uint32_t warps = ctx.nthreads / 32;
+        const uint32_t total_slots = ctx.gx * warps;
+        const uint32_t items = batch * slices;
+        const uint32_t sweeps = (items + total_slots - 1) / total_slots;
+        for (uint32_t it = 0; it < sweeps; it++) {
+            DR_THREAD_LOOP(t, ctx) {
+                const uint32_t wq = t / 32, lane = t % 32;
+                const uint32_t slot = ctx.bx * warps + wq;
+                const uint32_t item = it * total_slots + slot;
+                G1 acc = G1::inf();
+                if (item < items) {
+                    const uint32_t msm = item / slices, slice = item % slices;
+                    const size_t base = (size_t)slot * sc.cap_refs * 32;
+                    uint32_t* refs = sc.refs + base;
+                    Fq* prefix = sc.prefix + base / 2;
+                    G1Affine* buf_a = sc.buf_a + base / 2;
+                    G1Affine* buf_b = sc.buf_b + base / 4;
+                    const Fr* sv = scalars + (size_t)msm * scalar_stride;
+                    // 1. table references of this lane's points
+                    uint32_t count = 0;
+#pragma unroll 1
+                    for (uint32_t i = slice * 32 + lane; i < n; i += 32 * slices) {
+                        Fr kc = sv[i].from_mont();
+                        uint32_t carry = 0;
+#pragma unroll 1
+                        for (uint32_t w = 0; w < g.W; w++) {
+                            int d = msm_digit(kc.v, w, g.c, carry);
+                            if (d) {
+                                refs[(size_t)count * 32 + lane] = (uint32_t)g.entry(i, w, (uint32_t)(d < 0 ? -d : d)) | (d < 0 ? 0x80000000u : 0u);
+                                count++;
+                            }
+                        }
+                    }
+                    auto load_ref = [&](uint32_t j) {
+                        uint32_t r = refs[(size_t)j * 32 + lane];
+                        G1Affine a = table[r & 0x7FFFFFFFu];
+                        if (r >> 31) a.y = a.y.neg();
+                        return a;
+                    };
+                    auto load_ref_x = [&](uint32_t j) { return table[refs[(size_t)j * 32 + lane] & 0x7FFFFFFFu].x; };
+                    // 2. pairing rounds; an odd element out goes straight to the accumulator
+                    uint32_t level = 0;
+                    G1Affine* cur = nullptr;
+                    while (count / 2 >= AFFINE_MIN_PAIRS) {
+                        const uint32_t pairs = count / 2;
+                        G1Affine* dst = (level & 1) ? buf_b : buf_a;
+                        if (level == 0) {
+                            if (count & 1) g1_madd(acc, load_ref(count - 1));
+                            affine_round(pairs, lane, load_ref, load_ref_x, prefix, dst);
+                        } else {
+                            const G1Affine* src = cur;
+                            auto load_buf = [&](uint32_t j) { return src[(size_t)j * 32 + lane]; };
+                            auto load_buf_x = [&](uint32_t j) { return src[(size_t)j * 32 + lane].x; };
+                            if (count & 1) g1_madd(acc, load_buf(count - 1));
+                            affine_round(pairs, lane, load_buf, load_buf_x, prefix, dst);
+                        }
+                        cur = dst;
+                        count = pairs;
+                        level++;
+                    }
+                    // 3. the rest in XYZZ coordinates
+#pragma unroll 1
+                    for (uint32_t j = 0; j < count; j++) g1_madd(acc, level == 0 ? load_ref(j) : cur[(size_t)j * 32 + lane]);
+                }
+                sm[t] = acc;
+            }
+            DR_BLOCK_SYNC();
+            for (uint32_t stride = 16; stride > 0; stride >>= 1) {  // fold the 32 lanes of every warp
+                DR_THREAD_LOOP(t, ctx) {
+                    if ((t % 32) < stride) {
+                        G1 a = sm[t];
+                        g1_add(a, sm[t + stride]);
+                        sm[t] = a;
+                    }
+                }
+                DR_BLOCK_SYNC();
+            }
+            DR_THREAD_LOOP(t, ctx) {
+                const uint32_t item = it * total_slots + ctx.bx * warps + t / 32;
+                if ((t % 32) == 0 && item < items) partials[item] = sm[t];
+            }
+            DR_BLOCK_SYNC();
+        }
+    }
+};
+
 // Sum `slices` partials per MSM and normalise to affine.  One thread per MSM.
 struct CommitFinishBody {
     DR_HD void operator()(const BlockCtx& ctx, const G1* partials, uint32_t slices, uint32_t batch, G1Affine* out) const {

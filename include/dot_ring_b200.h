@@ -69,6 +69,10 @@ size_t dr_srs_table_bytes(const dr_srs* srs);
  * values >= r are reduced (kzg.py passes unreduced quotient coefficients, ops.py:215-220); all-zero ->
  * infinity (kzg.py:167-168).  Output: batch x 96-byte uncompressed commitments. */
 int dr_kzg_commit(dr_ctx* ctx, dr_srs* srs, const uint8_t* coeffs_le32, size_t n, size_t batch, uint8_t* out_be96);
+/* How the table entries of a commitment are summed: 0 = XYZZ mixed additions (10 multiplications each), 1 = batched-affine
+ * pairing rounds (one inversion per round of independent additions, ~6.3 multiplications each) for polynomials long enough to
+ * fill a round.  Same group element either way; tests cross-check the two. */
+int dr_ctx_set_commit_mode(dr_ctx* ctx, int mode);
 /* Same with operands already resident on the device (Montgomery limbs); used for roofline timing. */
 int dr_kzg_commit_bench(dr_ctx* ctx, dr_srs* srs, size_t n, size_t batch, int iters, uint64_t seed, float* ms_per_iter, uint8_t* out_first_be96);
 

@@ -7,6 +7,7 @@
 #include "../../dot_ring_b200/csrc/fp.cuh"
 #include "../../dot_ring_b200/csrc/g1.cuh"
 #include "../../dot_ring_b200/csrc/hash.cuh"
+#include "../../dot_ring_b200/csrc/msm.cuh"
 #include "../../dot_ring_b200/csrc/te.cuh"
 
 using namespace dr;
@@ -149,6 +150,17 @@ void ht_te_msm(const uint8_t* pts32, const uint8_t* ks32, int n, uint8_t* out32)
 // u0, u1: 48-byte big-endian hash_to_field outputs
 void ht_te_ell2(const uint8_t* u0_be48, const uint8_t* u1_be48, uint8_t* out32) {
     te_encode(out32, te_encode_to_curve_from_u(fr_from_be48_mod(u0_be48), fr_from_be48_mod(u1_be48)));
+}
+// One batched-affine round (msm.cuh: affine_round) over `n` points given as 96-byte encodings (pairs (0,1), (2,3), ...):
+// out = n/2 sums.  Exercises the exceptional cases of the affine law that real SRS data never produces.
+void ht_affine_round(const uint8_t* in96, int n, uint8_t* out96) {
+    std::vector<G1Affine> pts(n);
+    for (int i = 0; i < n; i++) g1_decode(pts[i], in96 + 96 * i, 96);
+    const uint32_t pairs = n / 2;
+    std::vector<Fq> prefix((size_t)pairs * 32);
+    std::vector<G1Affine> out((size_t)pairs * 32);
+    affine_round(pairs, 0, [&](uint32_t j) { return pts[j]; }, [&](uint32_t j) { return pts[j].x; }, prefix.data(), out.data());
+    for (uint32_t i = 0; i < pairs; i++) g1_serialize(out96 + 96 * i, out[(size_t)i * 32]);
 }
 void ht_sha512(const uint8_t* msg, uint32_t len, uint8_t* out64) {
     Sha512 s;

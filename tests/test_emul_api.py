@@ -135,6 +135,12 @@ def test_sparse_and_dense_witness_commitments_give_identical_proofs(api):
     finally:
         ctx.set_dense_witness_commit(False)
     assert sparse == dense and sparse[0] != sparse[1]
+    ctx.set_commit_mode(1)  # batched-affine summation of the table entries (msm.cuh CommitAffineBody)
+    try:
+        affine = cls.prove_batch(*args, zk_rows=zk, as_bytes=True)
+    finally:
+        ctx.set_commit_mode(0)
+    assert affine == sparse
     root = api.RingRoot.from_ring(ring, params)
     assert cls.verify_batch(sparse, [hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], ring, root) == [1, 1]
 

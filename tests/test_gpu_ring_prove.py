@@ -134,4 +134,10 @@ def test_sparse_and_dense_witness_commitments_agree_at_full_size(ctx, srs):
     finally:
         ctx.set_dense_witness_commit(False)
     assert st1 == st2 == [0] * n and sparse == dense
+    ctx.set_commit_mode(1)  # batched-affine summation of the table entries
+    try:
+        affine, st3 = ring.prove_batch(alphas, ads, [sk] * n, [3] * n, zk_rows=zk)
+    finally:
+        ctx.set_commit_mode(0)
+    assert st3 == [0] * n and affine == sparse
     ring.close()

@@ -24,7 +24,7 @@ def lib():
     src = HERE / "hosttest.cpp"
     hdrs = list((HERE.parents[1] / "dot_ring_b200" / "csrc").glob("*.cuh")) + list((HERE.parents[1] / "dot_ring_b200" / "csrc" / "gen").glob("*"))
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src, *hdrs]):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(src)])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DDR_HOST_EMULATION", "-shared", "-fPIC", "-o", str(so), str(src)])
     return ctypes.CDLL(str(so))
 
 
@@ -124,6 +124,19 @@ def test_g1_group_law_and_codecs(lib):
     assert not lib.ht_g1_decode(bytes(bad), 96, _buf(96))
     out96 = _buf(96)
     assert lib.ht_g1_decode(bytes([0xC0]) + bytes(47), 48, out96) and out96.raw == inf
+
+
+def test_batched_affine_round_exceptional_cases(lib):
+    """msm.cuh affine_round: generic pairs share one inversion with P + P (denominator 2y), P - P and infinity operands."""
+    rng = random.Random(9)
+    g = (bls.G1_GEN[0], bls.G1_GEN[1], 1)
+    p = [bls.g1_mul(g, rng.randrange(1, bls.R)) for _ in range(8)]
+    pairs = [(p[0], p[1]), (p[2], p[2]), (p[3], bls.g1_neg(p[3])), (None, p[4]), (p[5], None), (None, None), (p[6], p[7]), (p[1], p[0]), (p[7], p[7])]
+    data = b"".join(bls.g1_serialize(x) + bls.g1_serialize(y) for x, y in pairs)
+    out = _buf(96 * len(pairs))
+    lib.ht_affine_round(data, 2 * len(pairs), out)
+    for i, (x, y) in enumerate(pairs):
+        assert out.raw[96 * i : 96 * i + 96] == bls.g1_serialize(bls.g1_add(x, y)), i
 
 
 def test_bandersnatch_against_reference_goldens(lib):

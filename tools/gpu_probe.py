@@ -14,6 +14,7 @@ out = {}
 if os.environ.get("DR_LIB"):  # A/B builds of the same sources (tools only)
     _native.set_default_library(_native.Library(os.environ["DR_LIB"]))
 ctx = _native.Context(0)
+ctx.set_commit_mode(int(os.environ.get("COMMIT_MODE", "0")))
 out["device"] = ctx.device_info()
 for kind, iters in (("imad", 20000), ("imad_wide", 20000), ("fq_mul", 2000), ("fr_mul", 4000), ("g1_madd", 300)):
     ops, ms = ctx.microbench(kind, iters)
