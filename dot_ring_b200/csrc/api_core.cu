@@ -68,16 +68,16 @@ const NttPlan& Ctx::plan(uint32_t n, const Fr& omega_mont) {
 void ntt_device(Ctx* ctx, const NttPlan& plan, const Fr* in, Fr* out, size_t batch, bool inverse, DevBuf<Fr>& tmp) {
     const uint32_t n = plan.n;
     if (n <= 4096) {
-        uint32_t threads = n / 2 < 256 ? (uint32_t)(n / 2 < 32 ? 32 : n / 2) : 256;
+        const uint32_t threads = ntt_threads(n);
         launch(ctx->stream, Dim3((uint32_t)batch), threads, ntt_smem_bytes(n), NttPlainBody(), in, out, n, plan.logn, (const Fr*)(inverse ? plan.tw_inv.p : plan.tw_fwd.p),
                (const Fr*)(inverse ? plan.n_inv.p : nullptr));
         return;
     }
     const int dir = inverse ? 1 : 0;
     tmp.ensure((size_t)n * batch);
-    launch(ctx->stream, Dim3(plan.n2, (uint32_t)batch), 256, ntt_smem_bytes(plan.n1), NttLargePass1Body(), in, tmp.p, plan.n1, plan.logn1, plan.n2, (const Fr*)plan.tw1[dir].p,
+    launch(ctx->stream, Dim3(plan.n2, (uint32_t)batch), ntt_threads(plan.n1), ntt_smem_bytes(plan.n1), NttLargePass1Body(), in, tmp.p, plan.n1, plan.logn1, plan.n2, (const Fr*)plan.tw1[dir].p,
            (const Fr*)plan.wfull[dir].p);
-    launch(ctx->stream, Dim3(plan.n1, (uint32_t)batch), 256, ntt_smem_bytes(plan.n2), NttLargePass2Body(), (const Fr*)tmp.p, out, plan.n1, plan.n2, plan.logn2,
+    launch(ctx->stream, Dim3(plan.n1, (uint32_t)batch), ntt_threads(plan.n2), ntt_smem_bytes(plan.n2), NttLargePass2Body(), (const Fr*)tmp.p, out, plan.n1, plan.n2, plan.logn2,
            (const Fr*)plan.tw2[dir].p, (const Fr*)(inverse ? plan.n_inv.p : nullptr));
 }
 
@@ -343,7 +343,21 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !g1_be96 || !g2_be192 || !out || n_g1 == 0) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
-    uint32_t cbits = window_bits <= 0 ? 12 : (uint32_t)window_bits;
+    uint32_t cbits = (uint32_t)window_bits;
+    if (window_bits <= 0) {
+        // largest window whose table fits in half of the free device memory (14 bits = 92 GB for 6145 points on a 180 GB part)
+        cbits = 8;
+#if !defined(DR_HOST_EMULATION)
+        size_t free_b = 0, total_b = 0;
+        DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        for (uint32_t c = 14; c >= 8; c--) {
+            if (make_geom(c, (uint32_t)n_g1).total_entries() * sizeof(G1Affine) <= free_b / 2) {
+                cbits = c;
+                break;
+            }
+        }
+#endif
+    }
     if (cbits < 2 || cbits > 15) throw Error(DR_EINVAL, "window_bits must be in [2, 15]");
     auto srs = std::make_unique<Srs>();
     srs->ctx = ctx;

@@ -168,8 +168,8 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     // ---- fixed columns: evaluations -> coefficients -> commitments ----
     ring->fixed_coef.alloc(3 * N);
     launch(ctx->stream, Dim3((N + 127) / 128), 128, 0, FixedColumnsBody(), (const TEAffine*)ring->nm.p, N, d.max_ring, ring->fixed_coef.p);
-    uint32_t ntt_threads = N / 2 < 256 ? N / 2 : 256;
-    launch(ctx->stream, Dim3(3), ntt_threads, ntt_smem_bytes(N), NttPlainBody(), (const Fr*)ring->fixed_coef.p, ring->fixed_coef.p, N, d.logN, (const Fr*)plan.tw_inv.p,
+    const uint32_t nthr = ntt_threads(N);
+    launch(ctx->stream, Dim3(3), nthr, ntt_smem_bytes(N), NttPlainBody(), (const Fr*)ring->fixed_coef.p, ring->fixed_coef.p, N, d.logN, (const Fr*)plan.tw_inv.p,
            (const Fr*)plan.n_inv.p);
     d.fixed_coef = ring->fixed_coef.p;
     DevBuf<G1Affine> cm(3);
@@ -194,7 +194,7 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
             curl = curl * inv_xl;
         }
         h2d(ctx->stream, coef5.p + 3 * (size_t)N, lag.data(), 2 * N * sizeof(Fr));
-        launch(ctx->stream, Dim3(20), ntt_threads, ntt_smem_bytes(N), PlainLdeBody(), N, d.logN, (const Fr*)plan.tw_fwd.p, (const Fr*)ring->w4.p, (const Fr*)coef5.p,
+        launch(ctx->stream, Dim3(20), nthr, ntt_smem_bytes(N), PlainLdeBody(), N, d.logN, (const Fr*)plan.tw_fwd.p, (const Fr*)ring->w4.p, (const Fr*)coef5.p,
                ring->fixed_lde.p);
         launch(ctx->stream, Dim3((4 * N + 127) / 128), 128, 0, NotLastBody(), N, (const Fr*)ring->w4.p, d.w_last, ring->fixed_lde.p + 5 * 4 * (size_t)N);
         stream_sync(ctx->stream);
@@ -300,7 +300,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     sc.ensure(n < chunk_cap ? n : chunk_cap, N);
     PhaseTimer& pt = ctx->phases;
     pt.reset();
-    const uint32_t ntt_threads = N / 2 < 256 ? N / 2 : 256;
+    const uint32_t nthr = ntt_threads(N);
     const size_t ntt_smem = ntt_smem_bytes(N);
     std::vector<ProveInput> hin;
 
@@ -330,7 +330,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         launch(ctx->stream, Dim3(pb), tb, 0, PedersenProveBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
         launch(ctx->stream, Dim3(pb), tb, 0, WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
         pt.mark(ctx, 1);
-        launch(ctx->stream, Dim3(4, m), ntt_threads, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+        launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
         pt.mark(ctx, 2);
         if (ctx->dense_witness_commit) {
             commit_device(ctx, ring->srs, sc.wit_coef.p, N, N, 4 * m, sc.res.p);
@@ -346,9 +346,9 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         pt.mark(ctx, 5);
         launch(ctx->stream, Dim3(pb), tb, 0, Transcript1Body(), sc.st.p, m);
         pt.mark(ctx, 3);
-        launch(ctx->stream, Dim3(16, m), ntt_threads, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
+        launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
         launch(ctx->stream, Dim3((4 * N + 127) / 128, m), 128, 0, ConstraintBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.lde.p, sc.agg.p);
-        launch(ctx->stream, Dim3(4, m), ntt_threads, ntt_smem, QuotientInttBody(), rg, sc.agg.p);
+        launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, QuotientInttBody(), rg, sc.agg.p);
         launch(ctx->stream, Dim3((N + 127) / 128, m), 128, 0, QuotientCombineBody(), rg, (const Fr*)sc.agg.p, sc.cagg.p);
         launch(ctx->stream, Dim3((qlen + 127) / 128, m), 128, 0, QuotientFoldBody(), rg, (const Fr*)sc.cagg.p, sc.quot.p, qlen);
         pt.mark(ctx, 2);

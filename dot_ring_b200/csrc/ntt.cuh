@@ -39,28 +39,60 @@ DR_HD void sm_store(uint32_t* sm, uint32_t n, uint32_t i, const Fr& x) {
 
 // tw[k] = w^k (Montgomery), k < n/2, for the n-th root of unity w of this transform.
 // loader(k): k-th input in natural order.  storer(k, value): k-th output in natural order.
+//
+// Radix-8 passes: a thread pulls 8 elements that are 2^(s-1) apart into registers, runs the three DIT stages s, s+1, s+2 on
+// them (12 butterflies) and writes them back, so the working set crosses shared memory log2(n)/3 times instead of
+// log2(n) times (the radix-2 version was limited by the shared-memory instruction queue and by 2-way bank conflicts in
+// the first stages: ncu mio_throttle / bank-conflict counters in profiles/).  A final pass takes the remaining 1 or 2 stages.
 template <class Loader, class Storer>
 DR_HD void ntt_block(const BlockCtx& ctx, uint32_t n, uint32_t logn, const Fr* tw, const Loader& loader, const Storer& storer) {
     uint32_t* sm = (uint32_t*)ctx.smem;
     DR_STRIDE_LOOP(e, n, ctx) { sm_store(sm, n, e, loader(bit_reverse(e, logn))); }
     DR_BLOCK_SYNC();
-    for (uint32_t s = 1; s <= logn; s++) {
-        uint32_t half = 1u << (s - 1);
-        DR_STRIDE_LOOP(b, n >> 1, ctx) {
-            uint32_t j = b & (half - 1);
-            uint32_t i = ((b >> (s - 1)) << s) + j;
-            Fr u = sm_load(sm, n, i);
-            Fr v = sm_load(sm, n, i + half);
-            if (j) v = v * tw[j << (logn - s)];
-            sm_store(sm, n, i, u + v);
-            sm_store(sm, n, i + half, u - v);
+    uint32_t s = 1;  // next DIT stage (1-based): butterflies of span 2^(s-1)
+    while (s <= logn) {
+        const uint32_t r = (logn - s + 1 >= 3) ? 3 : (logn - s + 1);  // stages in this pass
+        const uint32_t span = 1u << (s - 1);
+        const uint32_t group = 1u << r;  // elements per thread-group
+        DR_STRIDE_LOOP(gidx, n >> r, ctx) {
+            // group index -> (high, j_low): element k of the group sits at high * span * group + k * span + j_low
+            const uint32_t j_low = gidx & (span - 1);
+            const uint32_t base = ((gidx >> (s - 1)) << (s - 1 + r)) + j_low;
+            Fr v[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++)
+                if (k < group) v[k] = sm_load(sm, n, base + k * span);
+#pragma unroll
+            for (uint32_t t = 0; t < 3; t++) {
+                if (t < r) {
+                    const uint32_t hl = 1u << t;  // local span
+#pragma unroll
+                    for (uint32_t bfly = 0; bfly < 4; bfly++) {
+                        if (bfly < (group >> 1)) {
+                            const uint32_t lo = ((bfly >> t) << (t + 1)) + (bfly & (hl - 1));
+                            // position of the pair inside its stage-(s+t) butterfly block
+                            const uint32_t j = (lo & (hl - 1)) * span + j_low;
+                            Fr x = v[lo], y = v[lo + hl];
+                            if (j) y = y * tw[j << (logn - (s + t))];
+                            v[lo] = x + y;
+                            v[lo + hl] = x - y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++)
+                if (k < group) sm_store(sm, n, base + k * span, v[k]);
         }
         DR_BLOCK_SYNC();
+        s += r;
     }
     DR_STRIDE_LOOP(e, n, ctx) { storer(e, sm_load(sm, n, e)); }
 }
 
 inline size_t ntt_smem_bytes(uint32_t n) { return (size_t)n * 32; }
+// one thread per radix-8 group: n / 8 threads keep every lane busy in the butterfly passes (at least one warp, at most 256)
+inline uint32_t ntt_threads(uint32_t n) { return n / 8 < 32 ? 32 : (n / 8 > 256 ? 256 : n / 8); }
 
 // ---- plain batched transform (C ABI dr_fr_ntt; ring-root fixed columns) -------------------------
 struct NttPlainBody {

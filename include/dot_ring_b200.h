@@ -59,7 +59,8 @@ int dr_ctx_device_info(dr_ctx* ctx, char* name_buf, size_t name_len, int* sm_cou
  * Replaces dot_ring/ring_proof/pcs/srs.py:98-148 (SRS, `blst.P1_Affines.as_memory`) and
  * dot_ring/ring_proof/pcs/kzg.py:152-175 (`KZG.commit` -> `blst.P1_Affines.mult_pippenger`).
  * g1_be96: n_g1 uncompressed points [tau^i]_1; g2_be192: [1]_2 and [tau]_2 (srs.py:57-88 layout).
- * window_bits selects the fixed-base table (0 = default 12; table bytes = n_g1*ceil(256/c)*2^(c-1)*96).
+ * window_bits selects the fixed-base table (table bytes = n_g1*ceil(256/c)*2^(c-1)*96; 0 = the largest window in 8..14 whose
+ * table fits in half of the free device memory: 14 bits = 92 GB for the bundled 6145-point SRS on a 180 GB B200).
  */
 int dr_srs_load(dr_ctx* ctx, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g2_be192, int window_bits, dr_srs** out);
 void dr_srs_destroy(dr_srs* srs);
