@@ -145,6 +145,9 @@ VerifierKeyDev make_verifier_key(Ctx* ctx, uint32_t N, const Fr& omega, const TE
 // Fixed-base window table (msm.cuh) for n affine points already on the device.
 void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table);
 
+// Variable-base MSM (pippenger.cuh) over operands resident on the device: *out = sum_i scalars[i] * points[i].
+void msm_points_device(Ctx* ctx, const G1Affine* points, const uint8_t* scalars_le32, size_t n, G1Affine* out);
+
 // scalars: `batch` vectors of n Montgomery Fr, vector b at scalars + b*stride.  Result: affine points.
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine);
 

@@ -71,6 +71,15 @@ static void msm_device(Ctx* ctx, MsmWork& w, const G1Affine* points, const uint8
     launch(st, Dim3(1), 64, 64 * sizeof(G1), MsmFinalBody(), g, (const G1*)w.window_sum.p, w.result.p);
 }
 
+// sum_i scalars[i] * points[i] with every operand already on the device; result (affine) written to *out (device memory)
+void msm_points_device(Ctx* ctx, const G1Affine* points, const uint8_t* scalars_le32, size_t n, G1Affine* out) {
+    MsmWork w;
+    w.prepare(n);
+    msm_device(ctx, w, points, scalars_le32);
+    d2d(ctx->stream, out, w.result.p, sizeof(G1Affine));
+    stream_sync(ctx->stream);  // the work buffers are released on return
+}
+
 }  // namespace dr
 
 using namespace dr;

@@ -126,6 +126,10 @@ static void status_to_verdict(const std::vector<uint32_t>& st, uint8_t* verdict)
     for (size_t i = 0; i < st.size(); i++) verdict[i] = (st[i] & ST_MALFORMED) ? 2 : st[i] ? 0 : 1;
 }
 
+// aggregated batches of at least this many proofs fold their sides with two bucket-method MSMs (the MSM pipeline has a
+// latency floor of a few ms, below this size the per-proof scalar multiplications are faster); tests lower it
+static size_t RING_VERIFY_MSM_THRESHOLD = 8192;
+
 // shared tail of the two ring-verification entry points; relations / payloads already on the device
 static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t n, const uint8_t* payloads, uint32_t stride, const TEAffine* relations, uint32_t rel_stride,
                                      const uint8_t* coeffs_le32, const uint32_t* extra_status, int aggregate, uint8_t* verdict, int* all_ok) {
@@ -143,9 +147,29 @@ static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t 
     const uint32_t m = (uint32_t)n;
     launch(ctx->stream, Dim3((7 * m + 63) / 64), 64, 0, PayloadG1DecodeBody(), payloads, stride, m, vs.p);
     launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, RingVerifyAlgebraBody(), vk, payloads, stride, relations, rel_stride, (const uint8_t*)dco.p, m, vs.p);
-    launch(ctx->stream, Dim3((VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
     uint32_t all = 0;
-    if (aggregate) {
+    const bool by_msm = aggregate && n >= RING_VERIFY_MSM_THRESHOLD;
+    if (!by_msm) launch(ctx->stream, Dim3((VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
+    if (by_msm) {
+        // two variable-base MSMs instead of 13 scalar multiplications per proof
+        const uint32_t threads = 64, nparts = (m + threads - 1) / threads;
+        DevBuf<G1Affine> lhs_pts(7 * n + 4), rhs_pts(2 * n), sides(2);
+        DevBuf<uint8_t> lhs_sc(32 * (7 * n + 4)), rhs_sc(32 * 2 * n);
+        DevBuf<Fr> fixed_partial(4 * (size_t)nparts);
+        DevBuf<G1> partial(2);
+        DevBuf<uint32_t> bad(1);
+        dev_zero(ctx->stream, bad.p, 4);
+        launch(ctx->stream, Dim3(nparts), threads, 4 * threads * sizeof(Fr), RingVerifyGatherBody(), m, (const VerifyState*)vs.p, extra_status, dverdict.p, lhs_pts.p, lhs_sc.p,
+               rhs_pts.p, rhs_sc.p, fixed_partial.p, bad.p);
+        launch(ctx->stream, Dim3(1), 32, 0, RingVerifyFixedBody(), vk, m, (const Fr*)fixed_partial.p, nparts, lhs_pts.p, lhs_sc.p);
+        msm_points_device(ctx, lhs_pts.p, lhs_sc.p, 7 * n + 4, sides.p);
+        msm_points_device(ctx, rhs_pts.p, rhs_sc.p, 2 * n, sides.p + 1);
+        launch(ctx->stream, Dim3(1), 32, 0, RingVerifySidesFromAffineBody(), (const G1Affine*)sides.p, partial.p);
+        launch(ctx->stream, Dim3(1), 32, ring_verify_warp_smem(), RingVerifyAggregateBody(), vk, (const G1*)partial.p, 1u, (const uint32_t*)bad.p, dall.p);
+        d2h(ctx->stream, &all, dall.p, 4);
+        d2h(ctx->stream, verdict, dverdict.p, n);
+        stream_sync(ctx->stream);
+    } else if (aggregate) {
         const uint32_t threads = 64;
         uint32_t nparts = (m + 4 * threads - 1) / (4 * threads);
         if (nparts > 64) nparts = 64;
@@ -189,6 +213,11 @@ using namespace dr;
     return DR_OK;
 
 extern "C" {
+
+int dr_ring_verify_set_msm_threshold(size_t n) {
+    RING_VERIFY_MSM_THRESHOLD = n;
+    return DR_OK;
+}
 
 int dr_pairing_check_batch(dr_ctx* c, const uint8_t* a1_be96, const uint8_t* b1_be192, const uint8_t* a2_be96, const uint8_t* b2_be192, size_t n, uint8_t* equal) {
     DR_API_BEGIN

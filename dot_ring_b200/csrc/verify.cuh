@@ -558,6 +558,68 @@ struct RingVerifyPartialSumBody {
         }
     }
 };
+// Large aggregated batches: instead of 13 scalar multiplications per proof (RingVerifyTermsBody), the two sides become two
+// variable-base MSMs (pippenger.cuh): lhs over 7 points per proof + the 4 fixed points, rhs over 2 points per proof.
+// This kernel lays out the operands: points, canonical little-endian scalars, and per-block sums of the fixed scalars.
+struct RingVerifyGatherBody {
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t count, const VerifyState* vs, const uint32_t* extra_status, uint8_t* verdict, G1Affine* lhs_pts, uint8_t* lhs_sc,
+                          G1Affine* rhs_pts, uint8_t* rhs_sc, Fr* fixed_partial, uint32_t* any_bad) const {
+        Fr* sm = (Fr*)ctx.smem;  // 4 * nthreads
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = ctx.bx * ctx.nthreads + t;
+            Fr f[4] = {Fr::zero(), Fr::zero(), Fr::zero(), Fr::zero()};
+            if (p < count) {
+                const VerifyState& s = vs[p];
+                uint32_t st = s.status | (extra_status ? extra_status[p] : 0u);
+                verdict[p] = (st & ST_MALFORMED) ? 2 : st ? 0 : 1;
+                if (st) *any_bad = 1;  // racing writers store the same value
+                for (int j = 0; j < 7; j++) {
+                    lhs_pts[7 * (size_t)p + j] = st ? G1Affine::inf() : s.g1[j];
+                    fr_to_le_bytes_raw(lhs_sc + 32 * (7 * (size_t)p + j), st ? Fr::zero() : s.sc[j].from_mont());
+                }
+                for (int j = 0; j < 2; j++) {
+                    rhs_pts[2 * (size_t)p + j] = st ? G1Affine::inf() : s.g1[5 + j];
+                    fr_to_le_bytes_raw(rhs_sc + 32 * (2 * (size_t)p + j), st ? Fr::zero() : s.sc[7 + j].from_mont());
+                }
+                if (!st)
+                    for (int j = 0; j < 4; j++) f[j] = s.sc[9 + j];
+            }
+            for (int j = 0; j < 4; j++) sm[j * ctx.nthreads + t] = f[j];
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                for (int j = 0; j < 4; j++) sm[j * ctx.nthreads + t] = sm[j * ctx.nthreads + t] + sm[j * ctx.nthreads + t + stride];
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < 4) fixed_partial[4 * (size_t)ctx.bx + t] = sm[t * ctx.nthreads];
+        }
+    }
+};
+// appends the 4 fixed points with their summed scalars after the 7 * count per-proof entries
+struct RingVerifyFixedBody {
+    DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, const Fr* fixed_partial, uint32_t nparts, G1Affine* lhs_pts, uint8_t* lhs_sc) const {
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < 4) {
+                Fr acc = Fr::zero();
+                for (uint32_t i = 0; i < nparts; i++) acc = acc + fixed_partial[4 * (size_t)i + t];
+                lhs_pts[7 * (size_t)count + t] = vk.fixed[t];
+                fr_to_le_bytes_raw(lhs_sc + 32 * (7 * (size_t)count + t), acc.from_mont());
+            }
+        }
+    }
+};
+// the two MSM results as the (lhs, rhs) pair RingVerifyAggregateBody folds
+struct RingVerifySidesFromAffineBody {
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* sides, G1* partial) const {
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < 2) partial[t] = G1::from_affine(sides[t]);
+        }
+    }
+};
+
 // stage 2: one block folds the partial pairs and runs the single pairing check
 struct RingVerifyAggregateBody {
     DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, const G1* partial, uint32_t nparts, const uint32_t* any_bad, uint32_t* all_ok) const {

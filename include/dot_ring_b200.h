@@ -236,6 +236,10 @@ int dr_ring_proof_verify_batch(dr_ctx* ctx, const dr_verifier_key* key, size_t n
 int dr_ring_verify_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
                          const uint32_t* ad_len, const uint8_t* proofs784, const uint8_t* coeffs_le32, int aggregate, uint8_t* verdict, int* all_ok);
 
+/* Aggregated batches of at least `n` proofs fold the two sides with two variable-base MSMs instead of 13 scalar multiplications
+ * per proof (default 8192; same verdicts, tests lower it to exercise the path on small batches). */
+int dr_ring_verify_set_msm_threshold(size_t n);
+
 /* ---- pairing check ------------------------------------------------------------------------------------------
  * Replaces `blst_miller_loop` + `blst_final_verify` (dot_ring/ring_proof/pcs/pairing.py:24-31) for a batch:
  * equal[i] = ( e(a1_i, b1_i) == e(a2_i, b2_i) ), G1 as 96-byte and G2 as 192-byte zcash uncompressed encodings
