@@ -58,6 +58,7 @@ class Library:
         L.dr_ctx_destroy.argtypes = [c_void_p]
         L.dr_ctx_destroy.restype = None
         L.dr_ctx_sync.argtypes = [c_void_p]
+        L.dr_ctx_trim.argtypes = [c_void_p]
         L.dr_ctx_timer_start.argtypes = [c_void_p]
         L.dr_ctx_timer_stop.argtypes = [c_void_p, POINTER(c_float)]
         L.dr_ctx_device_info.argtypes = [c_void_p, c_char_p, c_size_t, POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t)]
@@ -237,6 +238,10 @@ class Context:
     def set_dense_witness_commit(self, enabled: bool) -> None:
         """Commit witness columns from interpolated coefficients (the reference's route) instead of the sparse Lagrange form."""
         self.library.check(self.library.lib.dr_ctx_set_dense_witness_commit(self.handle, 1 if enabled else 0))
+
+    def trim(self) -> None:
+        """Return cached device scratch to the driver."""
+        self.library.check(self.library.lib.dr_ctx_trim(self.handle))
 
     def timer_start(self) -> None:
         self.library.check(self.library.lib.dr_ctx_timer_start(self.handle))

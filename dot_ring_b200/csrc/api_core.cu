@@ -275,6 +275,18 @@ int dr_ctx_set_commit_mode(dr_ctx* c, int mode) {
     DR_API_END
 }
 
+int dr_ctx_trim(dr_ctx* c) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx) throw Error(DR_EINVAL, "bad argument");
+    ctx->activate();
+    stream_sync(ctx->stream);
+#if !defined(DR_HOST_EMULATION)
+    dev_cache_trim();
+#endif
+    DR_API_END
+}
+
 int dr_ctx_sync(dr_ctx* c) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
@@ -350,6 +362,7 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
 #if !defined(DR_HOST_EMULATION)
         size_t free_b = 0, total_b = 0;
         DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += dev_cache().cached;
         for (uint32_t c = 14; c >= 8; c--) {
             if (make_geom(c, (uint32_t)n_g1).total_entries() * sizeof(G1Affine) <= free_b / 2) {
                 cbits = c;

@@ -289,6 +289,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     if (!ctx->prove_chunk) {
         size_t free_b = 0, total_b = 0;
         DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += dev_cache().cached;  // recycled blocks are available to this call
         ProveScratch& cur = scratch_for(ctx);
         size_t per_proof = 35 * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
         size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -113,15 +115,80 @@ inline void launch_lb(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body b
     launch_counter()++;
 }
 
+// Device allocations go through a small caching layer: every C-ABI call allocates its scratch with DevBuf and frees it on
+// return, and cudaMalloc / cudaFree of 100 MB-class buffers cost milliseconds each (and, measured on B200, occasional
+// stalls of hundreds of ms).  Freed blocks are kept per device (up to DR_DEV_CACHE_CAP bytes) and reused for requests of a
+// similar size; on an out-of-memory error the cache is emptied and the allocation retried.  Blocks are only recycled after
+// the owning call has synchronised its stream (the ABI is synchronous), the same guarantee cudaFree gives.
+struct DevCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, size) -> block
+    std::map<void*, std::pair<int, size_t>> live;               // block -> (device, size)
+    size_t cached = 0;
+    size_t cap = (size_t)24 << 30;
+};
+inline DevCache& dev_cache() {
+    static DevCache c;
+    return c;
+}
+inline void dev_cache_trim() {
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lock(c.m);
+    for (auto& kv : c.free_blocks) cudaFree(kv.second);
+    c.free_blocks.clear();
+    c.cached = 0;
+}
 inline void* dev_alloc(size_t bytes) {
-    void* p = nullptr;
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) throw Error(DR_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    // size classes: 4 KiB granules below 1 MiB, 1 MiB granules above
+    const size_t gran = bytes < ((size_t)1 << 20) ? 4096 : ((size_t)1 << 20);
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevCache& c = dev_cache();
+    {
+        std::lock_guard<std::mutex> lock(c.m);
+        auto it = c.free_blocks.lower_bound({dev, size});
+        if (it != c.free_blocks.end() && it->first.first == dev && it->first.second <= size + size / 4) {
+            void* p = it->second;
+            c.live[p] = it->first;
+            c.cached -= it->first.second;
+            c.free_blocks.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, size);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dev_cache_trim();
+        e = cudaMalloc(&p, size);
+    }
+    if (e != cudaSuccess) throw Error(DR_ENOMEM, std::string("cudaMalloc(") + std::to_string(size) + "): " + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(c.m);
+    c.live[p] = {dev, size};
     return p;
 }
 inline void dev_free(void* p) {
-    if (p) cudaFree(p);
+    if (!p) return;
+    DevCache& c = dev_cache();
+    std::unique_lock<std::mutex> lock(c.m);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) {
+        lock.unlock();
+        cudaFree(p);
+        return;
+    }
+    auto key = it->second;
+    c.live.erase(it);
+    // very large blocks (window tables) go back to the driver; the rest is kept for the next call
+    if (key.second > ((size_t)4 << 30) || c.cached + key.second > c.cap) {
+        lock.unlock();
+        cudaFree(p);
+        return;
+    }
+    c.free_blocks.insert({key, p});
+    c.cached += key.second;
 }
 inline void h2d(Stream s, void* dst, const void* src, size_t bytes) {
     if (bytes) DR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));

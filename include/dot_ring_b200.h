@@ -47,6 +47,8 @@ int dr_is_cuda_build(void);
 int dr_ctx_create(int device, dr_ctx** out);
 void dr_ctx_destroy(dr_ctx* ctx);
 int dr_ctx_sync(dr_ctx* ctx);
+/* Device scratch freed by earlier calls is kept for reuse (up to 24 GB per process); this returns it to the driver. */
+int dr_ctx_trim(dr_ctx* ctx);
 /* Device-side timing with CUDA events on the ctx stream (bench.py): start, then stop -> ms. */
 int dr_ctx_timer_start(dr_ctx* ctx);
 int dr_ctx_timer_stop(dr_ctx* ctx, float* ms_out);
