@@ -66,6 +66,7 @@ static void msm_device(Ctx* ctx, MsmWork& w, const G1Affine* points, const uint8
     launch(st, Dim3((uint32_t)((max_units + 63) / 64)), 64, 0, MsmUnitSumBody(), g, points, (const uint32_t*)w.count.p, (const uint32_t*)w.offset.p,
            (const uint32_t*)w.unit_offset.p, (const uint32_t*)w.totals.p, (const uint32_t*)w.refs.p, w.unit_sum.p);
     launch(st, Dim3((nb + 63) / 64), 64, 0, MsmBucketFoldBody(), g, (const uint32_t*)w.count.p, (const uint32_t*)w.unit_offset.p, (const G1*)w.unit_sum.p, w.bucket.p);
+    launch(st, Dim3(nb), 64, 64 * sizeof(G1), MsmBucketFoldHeavyBody(), (const uint32_t*)w.count.p, (const uint32_t*)w.unit_offset.p, (const G1*)w.unit_sum.p, w.bucket.p);
     launch(st, Dim3((g.W * w.segs + 63) / 64), 64, 0, MsmSegmentReduceBody(), g, (const G1*)w.bucket.p, w.segs, w.seg_sum.p);
     launch(st, Dim3(g.W), 64, 64 * sizeof(G1), MsmWindowFoldBody(), (const G1*)w.seg_sum.p, w.segs, w.window_sum.p);
     launch(st, Dim3(1), 64, 64 * sizeof(G1), MsmFinalBody(), g, (const G1*)w.window_sum.p, w.result.p);

@@ -166,17 +166,49 @@ struct MsmUnitSumBody {
     }
 };
 
+// Buckets with few units are folded by one thread; a bucket that received a large share of the points (the top window only
+// spans the few leading bits of the scalars, and skewed scalar distributions concentrate everything in a handful of buckets)
+// gets a whole CTA: strided partial sums, then a shared-memory tree.
+constexpr uint32_t MSM_FOLD_SERIAL = 32;
 struct MsmBucketFoldBody {
     DR_HD void operator()(const BlockCtx& ctx, MsmGeom g, const uint32_t* count, const uint32_t* unit_offset, const G1* unit_sum, G1* bucket) const {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t b = ctx.bx * ctx.nthreads + t;
             if (b < g.buckets()) {
                 uint32_t units = (count[b] + MSM_UNIT - 1) / MSM_UNIT;
-                G1 acc = G1::inf();
+                if (units <= MSM_FOLD_SERIAL) {
+                    G1 acc = G1::inf();
 #pragma unroll 1
-                for (uint32_t u = 0; u < units; u++) g1_add(acc, unit_sum[unit_offset[b] + u]);
-                bucket[b] = acc;
+                    for (uint32_t u = 0; u < units; u++) g1_add(acc, unit_sum[unit_offset[b] + u]);
+                    bucket[b] = acc;
+                }
             }
+        }
+    }
+};
+struct MsmBucketFoldHeavyBody {  // grid = buckets; CTAs of light buckets exit at once
+    DR_HD void operator()(const BlockCtx& ctx, const uint32_t* count, const uint32_t* unit_offset, const G1* unit_sum, G1* bucket) const {
+        const uint32_t b = ctx.bx;
+        const uint32_t units = (count[b] + MSM_UNIT - 1) / MSM_UNIT;
+        if (units <= MSM_FOLD_SERIAL) return;
+        G1* sm = (G1*)ctx.smem;
+        DR_THREAD_LOOP(t, ctx) {
+            G1 acc = G1::inf();
+#pragma unroll 1
+            for (uint32_t u = t; u < units; u += ctx.nthreads) g1_add(acc, unit_sum[unit_offset[b] + u]);
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+            DR_STRIDE_LOOP(t, stride, ctx) {
+                G1 a = sm[t];
+                g1_add(a, sm[t + stride]);
+                sm[t] = a;
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            if (t == 0) bucket[b] = sm[0];
         }
     }
 };
