@@ -92,6 +92,7 @@ class Library:
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
         L.dr_ctx_set_dense_witness_commit.argtypes = [c_void_p, c_int]
         L.dr_ctx_set_commit_mode.argtypes = [c_void_p, c_int]
+        L.dr_ctx_set_generic_ntt_path.argtypes = [c_void_p, c_int]
 
         L.dr_pedersen_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
@@ -234,6 +235,10 @@ class Context:
     def set_commit_mode(self, mode: int) -> None:
         """0: XYZZ accumulation, 1: batched-affine pairing rounds (same commitments, cheaper additions)."""
         self.library.check(self.library.lib.dr_ctx_set_commit_mode(self.handle, mode))
+
+    def set_generic_ntt_path(self, enabled: bool) -> None:
+        """Force the large-domain route (element-wise twists around the batched NTT) at any domain size (tests)."""
+        self.library.check(self.library.lib.dr_ctx_set_generic_ntt_path(self.handle, 1 if enabled else 0))
 
     def set_dense_witness_commit(self, enabled: bool) -> None:
         """Commit witness columns from interpolated coefficients (the reference's route) instead of the sparse Lagrange form."""

@@ -70,7 +70,8 @@ struct Ctx {
     DevBuf<uint32_t> aff_refs;
     DevBuf<Fq> aff_prefix;
     DevBuf<G1Affine> aff_a, aff_b;
-    bool dense_witness_commit = false;  // A/B + cross-check: commit witness columns from coefficients like the reference
+    bool dense_witness_commit = false;
+    bool generic_ntt_path = false;  // force the large-domain route (element-wise twists + ntt_device) at any N: tests  // A/B + cross-check: commit witness columns from coefficients like the reference
     bool have_pairing_consts = false;
     PairingConsts pairing_k;
     const PairingConsts& pairing_consts() {

@@ -21,7 +21,7 @@ struct ProveScratch {
     uint32_t N = 0;
     DevBuf<ProofState> st;
     DevBuf<ProveInput> in;
-    DevBuf<Fr> wit_coef, lde, agg, cagg, quot, aggopen, lin;
+    DevBuf<Fr> wit_coef, lde, agg, cagg, quot, aggopen, lin, ntt_tmp;
     DevBuf<G1Affine> res;
     DevBuf<uint8_t> out, zraw;
     DevBuf<uint32_t> status;
@@ -75,7 +75,8 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     if (!ctx || !srs || !prm || !out || (n_keys && !keys32)) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
     const uint32_t N = prm->domain_size;
-    if (N < 512 || N > 4096 || (N & (N - 1))) throw Error(DR_EINVAL, "domain_size must be a power of two in [512, 4096]");
+    // the reference stops at 4096 (params.py:172-173); larger domains (to 2^16) run the same pipeline over the two-pass NTT
+    if (N < 512 || N > 65536 || (N & (N - 1))) throw Error(DR_EINVAL, "domain_size must be a power of two in [512, 65536]");
     if (prm->padding_rows != 4) throw Error(DR_EINVAL, "padding_rows must be 4 to match the 3 hidden rows");
     if (prm->max_ring_size + SCALAR_BITS + 4 > N) throw Error(DR_EINVAL, "max_ring_size exceeds supported size for this domain");
     if (n_keys > prm->max_ring_size) throw Error(DR_EINVAL, "ring size exceeds max supported size");
@@ -169,8 +170,8 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     ring->fixed_coef.alloc(3 * N);
     launch(ctx->stream, Dim3((N + 127) / 128), 128, 0, FixedColumnsBody(), (const TEAffine*)ring->nm.p, N, d.max_ring, ring->fixed_coef.p);
     const uint32_t nthr = ntt_threads(N);
-    launch(ctx->stream, Dim3(3), nthr, ntt_smem_bytes(N), NttPlainBody(), (const Fr*)ring->fixed_coef.p, ring->fixed_coef.p, N, d.logN, (const Fr*)plan.tw_inv.p,
-           (const Fr*)plan.n_inv.p);
+    DevBuf<Fr> ntt_tmp;
+    ntt_device(ctx, plan, ring->fixed_coef.p, ring->fixed_coef.p, 3, true, ntt_tmp);
     d.fixed_coef = ring->fixed_coef.p;
     DevBuf<G1Affine> cm(3);
     commit_device(ctx, srs, ring->fixed_coef.p, N, N, 3, cm.p);
@@ -194,8 +195,13 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
             curl = curl * inv_xl;
         }
         h2d(ctx->stream, coef5.p + 3 * (size_t)N, lag.data(), 2 * N * sizeof(Fr));
-        launch(ctx->stream, Dim3(20), nthr, ntt_smem_bytes(N), PlainLdeBody(), N, d.logN, (const Fr*)plan.tw_fwd.p, (const Fr*)ring->w4.p, (const Fr*)coef5.p,
-               ring->fixed_lde.p);
+        if (N <= 4096 && !ctx->generic_ntt_path) {
+            launch(ctx->stream, Dim3(20), nthr, ntt_smem_bytes(N), PlainLdeBody(), N, d.logN, (const Fr*)plan.tw_fwd.p, (const Fr*)ring->w4.p, (const Fr*)coef5.p,
+                   ring->fixed_lde.p);
+        } else {
+            launch(ctx->stream, Dim3((N + 127) / 128, 4, 5), 128, 0, CosetTwistBody(), N, (const Fr*)ring->w4.p, (const Fr*)coef5.p, ring->fixed_lde.p);
+            ntt_device(ctx, plan, ring->fixed_lde.p, ring->fixed_lde.p, 20, false, ntt_tmp);
+        }
         launch(ctx->stream, Dim3((4 * N + 127) / 128), 128, 0, NotLastBody(), N, (const Fr*)ring->w4.p, d.w_last, ring->fixed_lde.p + 5 * 4 * (size_t)N);
         stream_sync(ctx->stream);
     }
@@ -291,7 +297,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
         free_b += dev_cache().cached;  // recycled blocks are available to this call
         ProveScratch& cur = scratch_for(ctx);
-        size_t per_proof = 35 * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
+        size_t per_proof = (35 + (N > 4096 ? 16 : 0)) * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
         size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
         size_t fit = have / 2 / per_proof;
         if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
@@ -303,6 +309,8 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     pt.reset();
     const uint32_t nthr = ntt_threads(N);
     const size_t ntt_smem = ntt_smem_bytes(N);
+    const bool large = N > 4096 || ctx->generic_ntt_path;  // two-pass transforms + element-wise twists instead of the fused single-CTA kernels
+    const NttPlan* big_plan = large ? &ctx->plan(N, rg.omega) : nullptr;
     std::vector<ProveInput> hin;
 
     for (size_t base = 0; base < n; base += sc.cap) {
@@ -331,9 +339,14 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         launch(ctx->stream, Dim3(pb), tb, 0, PedersenProveBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
         launch(ctx->stream, Dim3(pb), tb, 0, WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
         pt.mark(ctx, 1);
-        launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+        if (!large) {
+            launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+        } else {
+            launch(ctx->stream, Dim3((N + 127) / 128, 4, m), 128, 0, WitnessEvalBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+            ntt_device(ctx, *big_plan, sc.wit_coef.p, sc.wit_coef.p, 4 * (size_t)m, true, sc.ntt_tmp);
+        }
         pt.mark(ctx, 2);
-        if (ctx->dense_witness_commit) {
+        if (ctx->dense_witness_commit || large) {
             commit_device(ctx, ring->srs, sc.wit_coef.p, N, N, 4 * m, sc.res.p);
         } else {
             if (!ring->lag) ring->lag = &ring->srs->lagrange_table(N, rg.logN, rg.omega, rg.tw_inv, rg.n_inv);
@@ -347,9 +360,19 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         pt.mark(ctx, 5);
         launch(ctx->stream, Dim3(pb), tb, 0, Transcript1Body(), sc.st.p, m);
         pt.mark(ctx, 3);
-        launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
+        if (!large) {
+            launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
+        } else {
+            launch(ctx->stream, Dim3((N + 127) / 128, 4, 4 * m), 128, 0, CosetTwistBody(), N, rg.w4, (const Fr*)sc.wit_coef.p, sc.lde.p);
+            ntt_device(ctx, *big_plan, sc.lde.p, sc.lde.p, 16 * (size_t)m, false, sc.ntt_tmp);
+        }
         launch(ctx->stream, Dim3((4 * N + 127) / 128, m), 128, 0, ConstraintBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.lde.p, sc.agg.p);
-        launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, QuotientInttBody(), rg, sc.agg.p);
+        if (!large) {
+            launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, QuotientInttBody(), rg, sc.agg.p);
+        } else {
+            ntt_device(ctx, *big_plan, sc.agg.p, sc.agg.p, 4 * (size_t)m, true, sc.ntt_tmp);
+            launch(ctx->stream, Dim3((N + 127) / 128, 4, m), 128, 0, CosetUntwistBody(), N, rg.w4inv, sc.agg.p);
+        }
         launch(ctx->stream, Dim3((N + 127) / 128, m), 128, 0, QuotientCombineBody(), rg, (const Fr*)sc.agg.p, sc.cagg.p);
         launch(ctx->stream, Dim3((qlen + 127) / 128, m), 128, 0, QuotientFoldBody(), rg, (const Fr*)sc.cagg.p, sc.quot.p, qlen);
         pt.mark(ctx, 2);
@@ -387,6 +410,14 @@ int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !out) throw Error(DR_EINVAL, "bad argument");
     for (int i = 0; i < 6; i++) out[i] = ctx->phases.total[i];
+    DR_API_END
+}
+
+int dr_ctx_set_generic_ntt_path(dr_ctx* c, int enabled) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx) throw Error(DR_EINVAL, "bad argument");
+    ctx->generic_ntt_path = enabled != 0;
     DR_API_END
 }
 

@@ -504,6 +504,43 @@ struct PlainLdeBody {
     }
 };
 
+// ---- large domains (N > 4096, outside the reference: params.py:172-173 rejects them) -----------------------------------
+// The transform no longer fits one CTA, so the fused loaders / storers above become element-wise passes around the
+// two-pass NTT of ntt.cuh: materialise the witness evaluations, pre-twist the cosets, untwist after the inverse transform.
+struct WitnessEvalBody {  // grid (ceil(N / threads), 4 columns, proofs): out[(p*4 + col)*N + r] = column value at row r
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, Fr* out) const {
+        const ProofState& ps = st[ctx.bz];
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t r = ctx.bx * ctx.nthreads + t;
+            if (r < rg.N) out[((size_t)ctx.bz * 4 + ctx.by) * rg.N + r] = witness_eval(rg, ps, ctx.by, r);
+        }
+    }
+};
+struct CosetTwistBody {  // grid (ceil(N / threads), 4 cosets, vectors): out[(v*4 + j)*N + k] = in[v*N + k] * w4^(j k)
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t N, const Fr* w4, const Fr* in, Fr* out) const {
+        const uint32_t j = ctx.by, mask = 4 * N - 1;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t k = ctx.bx * ctx.nthreads + t;
+            if (k < N) {
+                Fr x = in[(size_t)ctx.bz * N + k];
+                out[((size_t)ctx.bz * 4 + j) * N + k] = j ? x * w4[((uint64_t)j * k) & mask] : x;
+            }
+        }
+    }
+};
+struct CosetUntwistBody {  // grid (ceil(N / threads), 4 cosets, vectors): buf[(v*4 + j)*N + k] *= w4^(-j k)
+    DR_HD void operator()(const BlockCtx& ctx, uint32_t N, const Fr* w4inv, Fr* buf) const {
+        const uint32_t j = ctx.by, mask = 4 * N - 1;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t k = ctx.bx * ctx.nthreads + t;
+            if (k < N && j) {
+                Fr* e = buf + ((size_t)ctx.bz * 4 + j) * N + k;
+                *e = *e * w4inv[((uint64_t)j * k) & mask];
+            }
+        }
+    }
+};
+
 // ---- G. constraints c1..c7 and their alpha-aggregation on the 4N domain (constraints.py:64-151,
 //         proof_builder.py:165-179): grid (ceil(4N / threads), proofs) ----------------------------------------
 struct ConstraintBody {

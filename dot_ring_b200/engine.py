@@ -12,21 +12,23 @@ import os
 import threading
 
 from . import _native
-from .srs import read_srs_file
+from .srs import SrsBytes, read_srs_file
 
 _lock = threading.Lock()
 _engines: dict[int, "Engine"] = {}
 
 
 class Engine:
-    def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None):
+    def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None,
+                 srs: "SrsBytes | None" = None):
         self.device = device
         self.ctx = _native.Context(device, library)
         env = os.environ.get("DOT_RING_B200_WINDOW_BITS")
         self.window_bits = int(window_bits) if window_bits is not None else (int(env) if env else None)
         self._srs: _native.NativeSrs | None = None
         self._srs_points = srs_points
-        self.srs_bytes = read_srs_file(None, srs_points)
+        # `srs` overrides the bundled 6145-point file (needed for domains above 2048, whose quotient has 3N + 1 coefficients)
+        self.srs_bytes = srs if srs is not None else read_srs_file(None, srs_points)
 
     @property
     def srs(self) -> _native.NativeSrs:

@@ -18,6 +18,7 @@ DEFAULT_DOMAIN_SIZE = 512
 DEFAULT_MAX_RING_SIZE = 255
 ZK_ROWS = 3
 MAX_PIOP_DOMAIN_SIZE = 4096
+EXTENDED_MAX_DOMAIN_SIZE = 65536
 
 
 def _is_power_of_two(n: int) -> bool:
@@ -89,6 +90,9 @@ class RingProofParams:
     pcs: Any = field(default_factory=_default_pcs, compare=False, hash=False, repr=False)
     test_vectors: bool = False
     cv: CurveVariant = field(default_factory=lambda: Bandersnatch, compare=False, hash=False)
+    # The reference stops at 4096 (params.py:20,172-173: its bundled SRS has 6145 points).  The engine itself handles
+    # domains up to 2^16 when the caller brings an SRS with 3N + 1 points; raise this explicitly to use them.
+    max_domain_size: int = MAX_PIOP_DOMAIN_SIZE
 
     @property
     def prime(self) -> int:
@@ -116,8 +120,8 @@ class RingProofParams:
             raise ValueError(f"radix_domain_size must be a power of two, got {radix}")
         if radix % self.domain_size != 0:
             raise ValueError(f"domain_size {self.domain_size} must divide radix_domain_size {radix}")
-        if self.domain_size > MAX_PIOP_DOMAIN_SIZE:
-            raise ValueError(f"domain_size {self.domain_size} exceeds supported SRS domain size {MAX_PIOP_DOMAIN_SIZE}")
+        if self.domain_size > self.max_domain_size or self.domain_size > EXTENDED_MAX_DOMAIN_SIZE:
+            raise ValueError(f"domain_size {self.domain_size} exceeds supported SRS domain size {min(self.max_domain_size, EXTENDED_MAX_DOMAIN_SIZE)}")
         if radix != 4 * self.domain_size:
             raise ValueError("the B200 engine evaluates constraints on exactly the 4N domain")
         if self.base_root_size % radix != 0 and radix <= self.base_root_size:
@@ -194,6 +198,7 @@ class RingProofParams:
         base_root_size: int = 2048,
         test_vectors: bool = False,
         cv: CurveVariant = Bandersnatch,
+        max_domain_size: int = MAX_PIOP_DOMAIN_SIZE,
     ) -> "RingProofParams":
         if ring_size <= 0:
             raise ValueError(f"ring_size must be positive, got {ring_size}")
@@ -207,4 +212,5 @@ class RingProofParams:
             base_root_size=base_root_size,
             test_vectors=test_vectors,
             cv=cv,
+            max_domain_size=max_domain_size,
         )

@@ -117,7 +117,7 @@ int dr_fr_ntt_bench(dr_ctx* ctx, size_t n, size_t batch, int iters, const uint8_
  * reference (constraints.py:43-62: 4x LDE of px, py, s, L_0, L_{N-4}).
  * All field elements are 32-byte little-endian canonical; points are affine (x | y). */
 typedef struct dr_ring_params {
-    uint32_t domain_size;      /* N (params.py:119) */
+    uint32_t domain_size;      /* N (params.py:119); a power of two in [512, 65536] */
     uint32_t max_ring_size;    /* params.py:120 */
     uint32_t padding_rows;     /* must be 4 (params.py:196-197) */
     uint32_t suite_id_len;
@@ -164,6 +164,10 @@ int dr_ctx_set_prove_chunk(dr_ctx* ctx, size_t chunk);
  * (~130 non-zero terms per column instead of N); enabled != 0 switches to the reference's route, KZG.commit of the interpolated
  * coefficients.  Both give the same group element, hence identical proofs (tests cross-check the two). */
 int dr_ctx_set_dense_witness_commit(dr_ctx* ctx, int enabled);
+/* Domains above 4096 (the reference stops there, params.py:172-173; dr_ring_create accepts up to 2^16 when the SRS has 3N+1 points)
+ * cannot use the single-CTA transforms: evaluations are materialised, cosets twisted element-wise and the two-pass NTT runs in
+ * between.  enabled != 0 forces that route at any domain size so that tests can compare it with the fused kernels. */
+int dr_ctx_set_generic_ntt_path(dr_ctx* ctx, int enabled);
 
 /* ---- batched Bandersnatch point operations -------------------------------------------------------------
  * dr_te_decode_batch replaces `dec_point` (dot_ring/vrf/codec.py:39-45) / `CurvePoint.string_to_point`

@@ -91,13 +91,14 @@ class Params:
     suite: bs.Suite = field(default_factory=lambda: bs.SHA512)
     base_root: int = fr.ROOT_OF_UNITY_2048
     base_root_size: int = 2048
+    max_domain_size: int = 4096
 
     def __post_init__(self):
         n = self.domain_size
         if n <= 0 or n & (n - 1):
             raise ValueError(f"domain_size must be a power of two, got {n}")
-        if n > 4096:
-            raise ValueError(f"domain_size {n} exceeds supported SRS domain size 4096")
+        if n > self.max_domain_size:  # the reference's limit (params.py:20,172-173); tests raise it for domains it rejects
+            raise ValueError(f"domain_size {n} exceeds supported SRS domain size {self.max_domain_size}")
         self.radix_domain_size = 4 * n
         if self.radix_domain_size > self.base_root_size:
             self.base_root, self.base_root_size = fr.extend_root_to_size(self.base_root, self.base_root_size, self.radix_domain_size)
@@ -112,12 +113,12 @@ class Params:
             raise ValueError(f"max_ring_size {self.max_ring_size} exceeds supported size {max_supported}")
 
     @classmethod
-    def from_ring_size(cls, ring_size: int, test_vectors: bool = False, suite: bs.Suite = bs.SHA512) -> "Params":
+    def from_ring_size(cls, ring_size: int, test_vectors: bool = False, suite: bs.Suite = bs.SHA512, max_domain_size: int = 4096) -> "Params":
         if ring_size <= 0:
             raise ValueError(f"ring_size must be positive, got {ring_size}")
         overhead = SCALAR_BITS + 4
         n = _next_pow2(ring_size + overhead)
-        return cls(domain_size=n, max_ring_size=n - overhead, test_vectors=test_vectors, suite=suite)
+        return cls(domain_size=n, max_ring_size=n - overhead, test_vectors=test_vectors, suite=suite, max_domain_size=max_domain_size)
 
     @property
     def omega(self) -> int:

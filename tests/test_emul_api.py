@@ -141,6 +141,15 @@ def test_sparse_and_dense_witness_commitments_give_identical_proofs(api):
     finally:
         ctx.set_commit_mode(0)
     assert affine == sparse
+    ctx.set_generic_ntt_path(True)  # the route domains above 4096 take (element-wise twists around the batched NTT)
+    try:
+        ring2 = api.Ring(keys, params)
+        assert api.RingRoot.from_ring(ring2, params).encode() == api.RingRoot.from_ring(ring, params).encode()
+        args2 = ([hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], hx(v, "sk"), hx(v, "pk"), ring2)
+        generic = cls.prove_batch(*args2, zk_rows=zk, as_bytes=True)
+    finally:
+        ctx.set_generic_ntt_path(False)
+    assert generic == sparse
     root = api.RingRoot.from_ring(ring, params)
     assert cls.verify_batch(sparse, [hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], ring, root) == [1, 1]
 

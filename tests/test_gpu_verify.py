@@ -149,3 +149,11 @@ def test_edge_cases_and_domain_1024(ctx, srs):
     edge_cases.te_msm_matches_oracle(ctx)
     edge_cases.ring_capacity_and_bad_keys(srs)
     edge_cases.ragged_inputs_match_oracle(srs, ((512, 5), (1024, 300)), n_items=4)
+
+
+def test_extended_domain_8192_matches_oracle(ctx):
+    """N = 8192 (a domain the reference rejects): the large-domain route (two-pass NTT, element-wise coset twists, dense
+    witness commitments) against the CPU oracle on a synthetic 24 577-point SRS, plus prove -> verify round trips."""
+    from tests import extended_domain
+
+    extended_domain.prove_verify_against_oracle(ctx, domain=8192, n_keys=40, n_proofs=3, oracle_proofs=1, window_bits=8)
