@@ -37,7 +37,7 @@ def prove_verify_against_oracle(ctx, domain: int, n_keys: int, n_proofs: int, or
     t0 = time.time()
     srs, osrs = synthetic_srs(ctx, 3 * domain + 1, window_bits)
     say("srs + table", round(time.time() - t0, 1), "s; table GB", round(srs.table_bytes / 1e9, 1))
-    params = rp.Params(domain_size=domain, max_ring_size=domain - rp.SCALAR_BITS - 4, max_domain_size=65536)
+    params = rp.Params(domain_size=domain, max_ring_size=domain - rp.SCALAR_BITS - 4, max_domain_size=max(domain, 4096))
     pairs = [tr.secret_from_seed(bs.SHA512, hashlib.sha256(b"ext%d" % i).digest()) for i in range(min(n_keys, 64))]
     keys = [pk for pk, _ in pairs]
     if n_keys > len(keys):  # bulk keys: multiples of the generator computed on the device

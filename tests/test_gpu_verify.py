@@ -157,3 +157,12 @@ def test_extended_domain_8192_matches_oracle(ctx):
     from tests import extended_domain
 
     extended_domain.prove_verify_against_oracle(ctx, domain=8192, n_keys=40, n_proofs=3, oracle_proofs=1, window_bits=8)
+
+
+def test_domain_4096_with_a_larger_srs_matches_oracle(ctx):
+    """N = 4096 is the largest domain the reference's parameters allow (params.py:20), but its bundled SRS (6145 points) cannot
+    serve it; with a 12 289-point SRS (DOT_RING_BLS12_381_SRS in the reference, synthetic here) the fused single-CTA kernels
+    and the sparse witness commitments run at their maximum size."""
+    from tests import extended_domain
+
+    extended_domain.prove_verify_against_oracle(ctx, domain=4096, n_keys=40, n_proofs=3, oracle_proofs=1, window_bits=8)
