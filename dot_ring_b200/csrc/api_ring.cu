@@ -361,7 +361,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         launch(ctx->stream, Dim3(pb), tb, 0, Transcript1Body(), sc.st.p, m);
         pt.mark(ctx, 3);
         if (!large) {
-            launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const Fr*)sc.wit_coef.p, sc.lde.p);
+            launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.wit_coef.p, sc.lde.p);
         } else {
             launch(ctx->stream, Dim3((N + 127) / 128, 4, 4 * m), 128, 0, CosetTwistBody(), N, rg.w4, (const Fr*)sc.wit_coef.p, sc.lde.p);
             ntt_device(ctx, *big_plan, sc.lde.p, sc.lde.p, 16 * (size_t)m, false, sc.ntt_tmp);

@@ -482,11 +482,16 @@ struct Transcript1Body {
 
 // ---- F. 4x low-degree extension of the witness columns: grid (16 = 4 cosets x 4 columns, proofs) ---------
 struct WitnessLdeBody {
-    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const Fr* wit_coef, Fr* lde) const {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProofState* st, const Fr* wit_coef, Fr* lde) const {
         uint32_t col = ctx.bx & 3, j = ctx.bx >> 2;
         const Fr* src = wit_coef + ((size_t)ctx.by * 4 + col) * rg.N;
         Fr* dst = lde + (((size_t)ctx.by * 4 + col) * 4 + j) * rg.N;
         const uint32_t mask = 4 * rg.N - 1;
+        if (j == 0) {  // coset 0 is the N-domain itself: the column's own evaluations, no transform needed
+            const ProofState& ps = st[ctx.by];
+            DR_STRIDE_LOOP(i, rg.N, ctx) { dst[i] = witness_eval(rg, ps, col, i); }
+            return;
+        }
         ntt_block(
             ctx, rg.N, rg.logN, rg.tw_fwd, [&](uint32_t k) { return j ? src[k] * rg.w4[(j * k) & mask] : src[k]; }, [&](uint32_t i, const Fr& v) { dst[i] = v; });
     }
@@ -557,6 +562,12 @@ struct ConstraintBody {
             uint32_t p = ctx.bx * ctx.nthreads + t;
             if (p < N4) {
                 uint32_t j = p / N, i = p - j * N;
+                if (j == 0 && i + 3 < N) {
+                    // coset 0 is the N-domain itself: every constraint holds on rows 0 .. N-4 (that is what the quotient's
+                    // divisibility by X^N - 1 expresses), only the three blinding rows contribute
+                    out[p] = Fr::zero();
+                    continue;
+                }
                 uint32_t q = j * N + ((i + 1) & (N - 1));  // row shifted by 4 in the 4N domain
                 Fr one = Fr::one();
                 Fr x1 = ax4[p], y1 = ay4[p], x2 = px4[p], y2 = py4[p], x3 = ax4[q], y3 = ay4[q];
