@@ -98,6 +98,7 @@ class Library:
         L.dr_tiny_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
         L.dr_pedersen_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_tiny_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
+        L.dr_pedersen_prove_batch_ex.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
         L.dr_thin_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7
         L.dr_thin_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 8
         L.dr_ring_proof_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int)]
@@ -358,6 +359,18 @@ class Context:
         self.library.check(fn(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(secret_keys), out))
         raw = out.raw
         return [raw[size * i : size * i + size] for i in range(n)]
+
+    def pedersen_prove_with_blinding(self, suite: VrfSuiteStruct, inputs: list[bytes], ads: list[bytes], secret_keys: list[bytes]):
+        """(192-byte proofs, blinding factors) -- `PedersenVRF.prove` keeping `_blinding_factor`."""
+        n = len(inputs)
+        if len(secret_keys) != n or any(len(k) != 32 for k in secret_keys):
+            raise ValueError("secret keys must be 32 bytes, one per item")
+        blob, a, b, c, d = pack_items(inputs, ads)
+        out = ctypes.create_string_buffer(192 * max(n, 1))
+        bl = ctypes.create_string_buffer(32 * max(n, 1))
+        self.library.check(self.library.lib.dr_pedersen_prove_batch_ex(self.handle, ctypes.byref(suite), n, blob, a, b, c, d, b"".join(secret_keys), out, bl))
+        raw, braw = out.raw, bl.raw
+        return [raw[192 * i : 192 * i + 192] for i in range(n)], [int.from_bytes(braw[32 * i : 32 * i + 32], "little") for i in range(n)]
 
     def ring_proof_verify(self, key: VerifierKeyStruct, relations: list[tuple[int, int]], payloads: list[bytes], coeffs: list[int], aggregate: bool = False):
         """`Verify(...).is_valid()` for a batch under an explicit verifier key -> (verdicts, all_ok)."""

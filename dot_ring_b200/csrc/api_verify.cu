@@ -312,7 +312,7 @@ int dr_thin_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const u
 
 // kind 0: Pedersen (192-byte proofs), 1: Tiny (80-byte proofs), 2: Thin (96-byte proofs)
 static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len,
-                            const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* sks32, uint8_t* out) {
+                            const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* sks32, uint8_t* out, uint8_t* blinding32 = nullptr) {
     if (!ctx || (n && (!sks32 || !out))) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
     if (!n) return;
@@ -320,16 +320,25 @@ static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_
     ItemsDev items;
     upload_items(ctx, items, n, blob, in_off, in_len, ad_off, ad_len);
     const size_t len = kind == 0 ? 192 : kind == 1 ? 80 : 96;
-    DevBuf<uint8_t> dsk(n * 32), dout(n * len);
+    DevBuf<uint8_t> dsk(n * 32), dout(n * len), dbl(blinding32 ? n * 32 : 1);
     h2d(ctx->stream, dsk.p, sks32, n * 32);
     const uint32_t m = (uint32_t)n;
     if (kind == 0)
-        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenProveStandaloneBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dsk.p, m, dout.p);
+        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenProveStandaloneBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dsk.p, m, dout.p,
+               blinding32 ? dbl.p : (uint8_t*)nullptr);
     else
         launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfProveBody(), su, kind == 2 ? 1u : 0u, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p,
                (const uint8_t*)dsk.p, m, dout.p);
     d2h(ctx->stream, out, dout.p, n * len);
+    if (blinding32) d2h(ctx->stream, blinding32, dbl.p, n * 32);
     stream_sync(ctx->stream);
+}
+
+int dr_pedersen_prove_batch_ex(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
+                               const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs192, uint8_t* blinding32) {
+    DR_API_BEGIN
+    vrf_prove_batch((Ctx*)c, suite, 0, n, blob, in_off, in_len, ad_off, ad_len, secret_keys32, proofs192, blinding32);
+    DR_API_END
 }
 
 int dr_pedersen_prove_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,

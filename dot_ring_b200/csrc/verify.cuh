@@ -192,8 +192,9 @@ struct IetfVerifyBody {
 };
 
 // ---- standalone provers (pedersen/vrf.py:86-126, ietf/tiny.py:35-70), one thread per item -------------------------
-struct PedersenProveStandaloneBody {
-    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count, uint8_t* out192) const {
+struct PedersenProveStandaloneBody {  // blinding32: optional n x 32 bytes, the blinding factor b of every proof (vrf.py:144-148)
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* sks32, uint32_t count, uint8_t* out192,
+                          uint8_t* blinding32) const {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t i = ctx.bx * ctx.nthreads + t;
             if (i < count) {
@@ -201,6 +202,8 @@ struct PedersenProveStandaloneBody {
                 TEAffine pk, blinded;
                 uint32_t braw[8];
                 pedersen_prove_core(su, sks32 + 32 * (size_t)i, blob + vi.in_off, vi.in_len, blob + vi.ad_off, vi.ad_len, out192 + 192 * (size_t)i, pk, blinded, braw);
+                if (blinding32)
+                    for (int b = 0; b < 32; b++) blinding32[32 * (size_t)i + b] = (uint8_t)(braw[b >> 2] >> (8 * (b & 3)));
             }
         }
     }

@@ -235,6 +235,7 @@ class PedersenVRF(VRF):
     ok: bytes
     s: int
     sb: int
+    _blinding_factor: int | None = None  # known to the prover only (pedersen/vrf.py:44, 111-126)
 
     @classmethod
     def proof_len(cls) -> int:
@@ -265,12 +266,29 @@ class PedersenVRF(VRF):
         from .engine import default_engine
 
         salts = salts or [b""] * len(alphas)
-        raw = default_engine().ctx.vrf_prove(
-            "pedersen", _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, alphas, strict=True)], [bytes(d) for d in additional_data], [bytes(k) for k in secret_keys]
+        raw, blind = default_engine().ctx.pedersen_prove_with_blinding(
+            _suite_struct(cls.cv), [bytes(s) + bytes(a) for s, a in zip(salts, alphas, strict=True)], [bytes(d) for d in additional_data], [bytes(k) for k in secret_keys]
         )
         if as_bytes:
             return raw
-        return [cls(p[0:32], p[32:64], p[64:96], p[96:128], int.from_bytes(p[128:160], "little"), int.from_bytes(p[160:192], "little")) for p in raw]
+        return [
+            cls(p[0:32], p[32:64], p[64:96], p[96:128], int.from_bytes(p[128:160], "little"), int.from_bytes(p[160:192], "little"), b)
+            for p, b in zip(raw, blind)
+        ]
+
+    def verify_unblinding(self, public_key: bytes, blinding_factor: int) -> bool:
+        """pedersen/vrf.py:144-156: Y_bar == Y + b * B for a revealed blinding factor."""
+        from .engine import default_engine
+
+        params = self.cv.curve.params
+        if not 0 <= blinding_factor < params.subgroup_order:
+            return False
+        ctx = default_engine().ctx
+        if len(public_key) != 32 or ctx.te_decode([bytes(public_key)], checked=True)[0] is None:
+            raise ValueError("Invalid point encoding")
+        from .curve import point_to_string
+
+        return ctx.te_msm([bytes(public_key), point_to_string(params.auxiliary_points.blinding_base)], [1, blinding_factor]) == self.blinded_pk
 
     def verify(self, input: bytes, additional_data: bytes, salt: bytes = b"") -> bool:
         """pedersen/vrf.py:128-143."""

@@ -214,6 +214,10 @@ int dr_thin_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const 
  * (dot_ring/vrf/ietf/tiny.py:35-70); nonces are the reference's deterministic transcript nonces (primitives.py:66-82). */
 int dr_pedersen_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
                             const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs192);
+/* Same, also returning the blinding factor of every proof (`PedersenVRF._blinding_factor`, vrf/pedersen/vrf.py:111-126,144-162) as
+ * n x 32 little-endian bytes when blinding32 != NULL (what `verify_unblinding` is later given). */
+int dr_pedersen_prove_batch_ex(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len,
+                               const uint32_t* ad_off, const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs192, uint8_t* blinding32);
 int dr_tiny_prove_batch(dr_ctx* ctx, const dr_vrf_suite* suite, size_t n, const uint8_t* blob, const uint32_t* in_off, const uint32_t* in_len, const uint32_t* ad_off,
                         const uint32_t* ad_len, const uint8_t* secret_keys32, uint8_t* proofs80);
 

@@ -192,3 +192,14 @@ def test_thin_vrf_api(api):
         cls.decode(b"\x00" * 95)
     with pytest.raises(ValueError):
         proof.verify(b"\xff" * 32, hx(v, "alpha"), hx(v, "ad"))
+
+
+def test_pedersen_blinding_factor_and_unblinding(api):
+    """pedersen/vrf.py:111-126,144-162: the prover keeps its blinding factor; `verify_unblinding` checks Y_bar = Y + b*B."""
+    cls = api.PedersenVRF[api.Bandersnatch]
+    v = load("bandersnatch_sha-512_ell2_pedersen.json")[0]
+    proof = cls.prove(hx(v, "alpha"), hx(v, "sk"), hx(v, "ad"))
+    assert proof._blinding_factor == int.from_bytes(hx(v, "blinding"), "little")
+    assert proof.verify_unblinding(hx(v, "pk"), proof._blinding_factor)
+    assert not proof.verify_unblinding(hx(v, "pk"), proof._blinding_factor + 1)
+    assert cls.decode(proof.encode())._blinding_factor is None
