@@ -237,6 +237,10 @@ class Context:
         """0: XYZZ accumulation, 1: batched-affine pairing rounds (same commitments, cheaper additions)."""
         self.library.check(self.library.lib.dr_ctx_set_commit_mode(self.handle, mode))
 
+    def set_prove_chunk(self, chunk: int) -> None:
+        """Proofs per internal pass of dr_ring_prove_batch (0 = automatic, 4096 or what the free memory allows)."""
+        self.library.check(self.library.lib.dr_ctx_set_prove_chunk(self.handle, chunk))
+
     def set_generic_ntt_path(self, enabled: bool) -> None:
         """Force the large-domain route (element-wise twists around the batched NTT) at any domain size (tests)."""
         self.library.check(self.library.lib.dr_ctx_set_generic_ntt_path(self.handle, 1 if enabled else 0))

@@ -150,6 +150,16 @@ def test_sparse_and_dense_witness_commitments_give_identical_proofs(api):
     finally:
         ctx.set_generic_ntt_path(False)
     assert generic == sparse
+    # batches larger than one internal pass: same proofs whatever the pass size
+    five = ([hx(v, "alpha"), b"b", b"c", b"", b"e" * 70], [hx(v, "ad"), b"", b"x", b"y" * 200, b""], hx(v, "sk"), hx(v, "pk"), ring)
+    zk5 = [rng.randrange(params.prime) for _ in range(60)]
+    whole = cls.prove_batch(*five, zk_rows=zk5, as_bytes=True)
+    ctx.set_prove_chunk(2)
+    try:
+        chunked = cls.prove_batch(*five, zk_rows=zk5, as_bytes=True)
+    finally:
+        ctx.set_prove_chunk(0)
+    assert chunked == whole and len(set(whole)) == 5
     root = api.RingRoot.from_ring(ring, params)
     assert cls.verify_batch(sparse, [hx(v, "alpha"), b"second"], [hx(v, "ad"), b""], ring, root) == [1, 1]
 
