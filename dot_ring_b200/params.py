@@ -1,14 +1,17 @@
-"""RingProofParams: host-side mirror of dot_ring/ring_proof/params.py:118-287 (same fields, same rules).
+"""RingProofParams for the B200 engine.
 
-The only arithmetic here is the derivation of the domain generators: w_N = base_root^(base_size/N) and,
-for 4N > 2048, the square-root extension of the 2048-th root, where the particular root returned by the
-reference's Tonelli-Shanks walk (params.py:63-115) fixes every byte of the proof.
+Drop-in for the parameter object of the reference (dot_ring/ring_proof/params.py:118-287): same field names, defaults,
+derived properties and ValueError conditions, because callers construct it directly.  The only arithmetic that matters here
+is the choice of domain generators: w_N is a power of the fixed 2048-th root of unity, and when the 4N evaluation domain is
+larger than 2048 the root is extended by repeated square roots.  Which of the two square roots is taken decides every byte
+of a proof, so `_tonelli_shanks` below follows the reference's walk (params.py:63-115: least quadratic non-residue as the
+generator of the 2-Sylow subgroup, the textbook order-halving loop) and the tests compare the resulting roots with it.
 """
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from functools import lru_cache
+import dataclasses
+import functools
 from typing import Any
 
 from .curve import Bandersnatch, CurveVariant
@@ -17,60 +20,81 @@ ROOT_OF_UNITY_2048 = 49307615728544765012166121802278658070711169839041683575071
 DEFAULT_DOMAIN_SIZE = 512
 DEFAULT_MAX_RING_SIZE = 255
 ZK_ROWS = 3
-MAX_PIOP_DOMAIN_SIZE = 4096
-EXTENDED_MAX_DOMAIN_SIZE = 65536
+MAX_PIOP_DOMAIN_SIZE = 4096  # the reference's limit (its bundled SRS has 3 * 2048 + 1 points)
+EXTENDED_MAX_DOMAIN_SIZE = 65536  # what the engine itself handles when the caller brings a 3N + 1 point SRS
 
 
-def _is_power_of_two(n: int) -> bool:
-    return n > 0 and n & (n - 1) == 0
+def _pow2(n: int) -> bool:
+    return n >= 1 and (n & (n - 1)) == 0
+
+
+def _ceil_pow2(n: int) -> int:
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+# kept under the reference's helper names: its tests import them
+_is_power_of_two = _pow2
 
 
 def _next_power_of_two(n: int) -> int:
-    if n <= 0:
-        return 1
-    return n if _is_power_of_two(n) else 1 << n.bit_length()
+    return _ceil_pow2(n)
+
+
+def _tonelli_shanks(a: int, p: int) -> int:
+    """A square root of `a` mod the odd prime `p` -- specifically the one the reference's routine returns."""
+    a %= p
+    if a == 0:
+        return 0
+    if p & 3 == 3:
+        return pow(a, (p + 1) >> 2, p)
+    legendre = functools.partial(pow, exp=(p - 1) >> 1, mod=p)
+    if legendre(a) != 1:
+        raise ValueError("No square root exists for provided value")
+    odd, twos = p - 1, 0
+    while not odd & 1:
+        odd >>= 1
+        twos += 1
+    non_residue = next(z for z in range(2, p) if legendre(z) == p - 1)
+    gen, root, rest = pow(non_residue, odd, p), pow(a, (odd + 1) >> 1, p), pow(a, odd, p)
+    level = twos
+    while rest != 1:
+        # order of `rest` is 2^k with k < level; multiply by the matching power of `gen` to halve it
+        k, probe = 0, rest
+        while probe != 1:
+            probe = probe * probe % p
+            k += 1
+        step = pow(gen, 1 << (level - k - 1), p)
+        gen = step * step % p
+        root, rest, level = root * step % p, rest * gen % p, k
+    return root
+
+
+_sqrt_mod_prime = _tonelli_shanks
+
+
+@functools.lru_cache(maxsize=8)
+def _extend_root_to_size(base_root: int, base_size: int, target_size: int, prime: int) -> tuple[int, int]:
+    """(root, size) with size >= target_size, obtained from (base_root, base_size) by successive square roots."""
+    doublings = max(0, (target_size - 1).bit_length() - (base_size - 1).bit_length()) if target_size > base_size else 0
+    root = base_root
+    for _ in range(doublings):
+        root = _tonelli_shanks(root, prime)
+    return root, base_size << doublings
 
 
 def _omega_for_domain(domain_size: int, prime: int, base_root: int, base_size: int = 2048) -> int:
-    if base_size % domain_size != 0:
+    quotient, remainder = divmod(base_size, domain_size)
+    if remainder:
         raise ValueError(f"Domain size {domain_size} must divide {base_size}")
-    return pow(base_root, base_size // domain_size, prime)
+    return pow(base_root, quotient, prime)
 
 
-def _sqrt_mod_prime(n: int, prime: int) -> int:
-    """Square root with the reference's choice of root (Tonelli-Shanks, least non-residue z)."""
-    if n == 0:
-        return 0
-    if prime % 4 == 3:
-        return pow(n, (prime + 1) // 4, prime)
-    if pow(n, (prime - 1) // 2, prime) != 1:
-        raise ValueError("No square root exists for provided value")
-    odd, two_adicity = prime - 1, 0
-    while odd % 2 == 0:
-        odd //= 2
-        two_adicity += 1
-    z = 2
-    while pow(z, (prime - 1) // 2, prime) != prime - 1:
-        z += 1
-    m, c = two_adicity, pow(z, odd, prime)
-    x, t = pow(n, (odd + 1) // 2, prime), pow(n, odd, prime)
-    while t != 1:
-        i, probe = 1, t * t % prime
-        while i < m and probe != 1:
-            probe = probe * probe % prime
-            i += 1
-        b = pow(c, 1 << (m - i - 1), prime)
-        x, t, c, m = x * b % prime, t * b * b % prime, b * b % prime, i
-    return x
-
-
-@lru_cache(maxsize=8)
-def _extend_root_to_size(base_root: int, base_size: int, target_size: int, prime: int) -> tuple[int, int]:
-    root, size = base_root, base_size
-    while size < target_size:
-        root = _sqrt_mod_prime(root, prime)
-        size *= 2
-    return root, size
+def _powers(generator: int, count: int, prime: int) -> list[int]:
+    out, cur = [], 1
+    for _ in range(count):
+        out.append(cur)
+        cur = cur * generator % prime
+    return out
 
 
 def _default_pcs():
@@ -79,7 +103,7 @@ def _default_pcs():
     return KZG
 
 
-@dataclass
+@dataclasses.dataclass
 class RingProofParams:
     domain_size: int = DEFAULT_DOMAIN_SIZE
     max_ring_size: int = DEFAULT_MAX_RING_SIZE
@@ -87,13 +111,13 @@ class RingProofParams:
     radix_domain_size: int | None = None
     base_root: int = ROOT_OF_UNITY_2048
     base_root_size: int = 2048
-    pcs: Any = field(default_factory=_default_pcs, compare=False, hash=False, repr=False)
+    pcs: Any = dataclasses.field(default_factory=_default_pcs, compare=False, hash=False, repr=False)
     test_vectors: bool = False
-    cv: CurveVariant = field(default_factory=lambda: Bandersnatch, compare=False, hash=False)
-    # The reference stops at 4096 (params.py:20,172-173: its bundled SRS has 6145 points).  The engine itself handles
-    # domains up to 2^16 when the caller brings an SRS with 3N + 1 points; raise this explicitly to use them.
+    cv: CurveVariant = dataclasses.field(default_factory=lambda: Bandersnatch, compare=False, hash=False)
+    # Raise explicitly (up to EXTENDED_MAX_DOMAIN_SIZE) to use domains the reference rejects; needs an SRS with 3N + 1 points.
     max_domain_size: int = MAX_PIOP_DOMAIN_SIZE
 
+    # ---- derived quantities ------------------------------------------------------------------------------------
     @property
     def prime(self) -> int:
         return self.cv.curve.params.field_modulus
@@ -106,49 +130,6 @@ class RingProofParams:
     def row_overhead(self) -> int:
         return self.scalar_bits + self.padding_rows
 
-    def __post_init__(self) -> None:
-        aux = self.cv.curve.params.auxiliary_points
-        for name in ("blinding_base", "accumulator_base", "padding_point"):
-            if getattr(aux, name) is None:
-                raise ValueError(f"{self.cv.name} ring proofs require auxiliary point {name}")
-        if self.radix_domain_size is None:
-            self.radix_domain_size = self.domain_size * 4
-        radix = self.radix_domain_size
-        if not _is_power_of_two(self.domain_size):
-            raise ValueError(f"domain_size must be a power of two, got {self.domain_size}")
-        if not _is_power_of_two(radix):
-            raise ValueError(f"radix_domain_size must be a power of two, got {radix}")
-        if radix % self.domain_size != 0:
-            raise ValueError(f"domain_size {self.domain_size} must divide radix_domain_size {radix}")
-        if self.domain_size > self.max_domain_size or self.domain_size > EXTENDED_MAX_DOMAIN_SIZE:
-            raise ValueError(f"domain_size {self.domain_size} exceeds supported SRS domain size {min(self.max_domain_size, EXTENDED_MAX_DOMAIN_SIZE)}")
-        if radix != 4 * self.domain_size:
-            raise ValueError("the B200 engine evaluates constraints on exactly the 4N domain")
-        if self.base_root_size % radix != 0 and radix <= self.base_root_size:
-            raise ValueError(f"radix_domain_size {radix} must divide base_root_size {self.base_root_size}")
-        if pow(self.base_root, self.base_root_size, self.prime) != 1 or pow(self.base_root, self.base_root_size // 2, self.prime) == 1:
-            raise ValueError(f"{self.cv.name} ring proofs require a primitive {self.base_root_size}-th root of unity")
-        if radix > self.base_root_size:
-            self.base_root, self.base_root_size = _extend_root_to_size(self.base_root, self.base_root_size, radix, self.prime)
-        if self.base_root_size % radix != 0:
-            raise ValueError(f"radix_domain_size {radix} must divide base_root_size {self.base_root_size}")
-        if self.padding_rows < 1:
-            raise ValueError("padding_rows must be >= 1 to preserve accumulator structure")
-        if self.padding_rows >= self.domain_size:
-            raise ValueError("padding_rows must be less than domain_size")
-        if self.padding_rows != ZK_ROWS + 1:
-            raise ValueError(f"padding_rows must be {ZK_ROWS + 1} to match the {ZK_ROWS} hidden rows")
-        max_supported = self.domain_size - self.row_overhead
-        if max_supported <= 0:
-            raise ValueError(
-                "domain_size is too small for the scalar bit decomposition: "
-                f"domain_size={self.domain_size}, scalar_bits={self.scalar_bits}, padding_rows={self.padding_rows}"
-            )
-        if self.max_ring_size == DEFAULT_MAX_RING_SIZE and max_supported != DEFAULT_MAX_RING_SIZE:
-            self.max_ring_size = max_supported
-        elif self.max_ring_size > max_supported:
-            raise ValueError(f"max_ring_size {self.max_ring_size} exceeds supported size {max_supported}")
-
     @property
     def omega(self) -> int:
         return _omega_for_domain(self.domain_size, self.prime, self.base_root, self.base_root_size)
@@ -159,19 +140,11 @@ class RingProofParams:
 
     @property
     def domain(self) -> list[int]:
-        w, out, cur = self.omega, [], 1
-        for _ in range(self.domain_size):
-            out.append(cur)
-            cur = cur * w % self.prime
-        return out
+        return _powers(self.omega, self.domain_size, self.prime)
 
     @property
     def radix_domain(self) -> list[int]:
-        w, out, cur = self.radix_omega, [], 1
-        for _ in range(self.radix_domain_size):
-            out.append(cur)
-            cur = cur * w % self.prime
-        return out
+        return _powers(self.radix_omega, self.radix_domain_size, self.prime)
 
     @property
     def radix_shift(self) -> int:
@@ -189,6 +162,45 @@ class RingProofParams:
     def required_srs_degree(self) -> int:
         return max(self.domain_size - 1, self.radix_domain_size - self.domain_size)
 
+    # ---- validation (same conditions and messages as the reference, params.py:142-203) --------------------------------
+    def __post_init__(self) -> None:
+        aux = self.cv.curve.params.auxiliary_points
+        missing = [name for name in ("blinding_base", "accumulator_base", "padding_point") if getattr(aux, name) is None]
+        if missing:
+            raise ValueError(f"{self.cv.name} ring proofs require auxiliary point {missing[0]}")
+        if self.radix_domain_size is None:
+            self.radix_domain_size = 4 * self.domain_size
+        n, radix = self.domain_size, self.radix_domain_size
+        limit = min(self.max_domain_size, EXTENDED_MAX_DOMAIN_SIZE)
+        self._require(_pow2(n), f"domain_size must be a power of two, got {n}")
+        self._require(_pow2(radix), f"radix_domain_size must be a power of two, got {radix}")
+        self._require(radix % n == 0, f"domain_size {n} must divide radix_domain_size {radix}")
+        self._require(n <= limit, f"domain_size {n} exceeds supported SRS domain size {limit}")
+        self._require(radix == 4 * n, "the B200 engine evaluates constraints on exactly the 4N domain")
+        self._require(radix > self.base_root_size or self.base_root_size % radix == 0, f"radix_domain_size {radix} must divide base_root_size {self.base_root_size}")
+        primitive = pow(self.base_root, self.base_root_size, self.prime) == 1 and pow(self.base_root, self.base_root_size // 2, self.prime) != 1
+        self._require(primitive, f"{self.cv.name} ring proofs require a primitive {self.base_root_size}-th root of unity")
+        if radix > self.base_root_size:
+            self.base_root, self.base_root_size = _extend_root_to_size(self.base_root, self.base_root_size, radix, self.prime)
+        self._require(self.base_root_size % radix == 0, f"radix_domain_size {radix} must divide base_root_size {self.base_root_size}")
+        self._require(self.padding_rows >= 1, "padding_rows must be >= 1 to preserve accumulator structure")
+        self._require(self.padding_rows < n, "padding_rows must be less than domain_size")
+        self._require(self.padding_rows == ZK_ROWS + 1, f"padding_rows must be {ZK_ROWS + 1} to match the {ZK_ROWS} hidden rows")
+        capacity = n - self.row_overhead
+        self._require(
+            capacity > 0,
+            "domain_size is too small for the scalar bit decomposition: "
+            f"domain_size={n}, scalar_bits={self.scalar_bits}, padding_rows={self.padding_rows}",
+        )
+        if self.max_ring_size == DEFAULT_MAX_RING_SIZE != capacity:
+            self.max_ring_size = capacity  # the default tracks the domain, as in the reference
+        self._require(self.max_ring_size <= capacity, f"max_ring_size {self.max_ring_size} exceeds supported size {capacity}")
+
+    @staticmethod
+    def _require(condition: bool, message: str) -> None:
+        if not condition:
+            raise ValueError(message)
+
     @classmethod
     def from_ring_size(
         cls,
@@ -200,17 +212,10 @@ class RingProofParams:
         cv: CurveVariant = Bandersnatch,
         max_domain_size: int = MAX_PIOP_DOMAIN_SIZE,
     ) -> "RingProofParams":
+        """Smallest power-of-two domain holding the ring, the scalar bits and the padding rows (params.py:244-287)."""
         if ring_size <= 0:
             raise ValueError(f"ring_size must be positive, got {ring_size}")
-        overhead = cv.curve.params.subgroup_order.bit_length() + padding_rows
-        domain_size = _next_power_of_two(ring_size + overhead)
-        return cls(
-            domain_size=domain_size,
-            max_ring_size=domain_size - overhead,
-            padding_rows=padding_rows,
-            base_root=base_root,
-            base_root_size=base_root_size,
-            test_vectors=test_vectors,
-            cv=cv,
-            max_domain_size=max_domain_size,
-        )
+        rows_besides_keys = cv.curve.params.subgroup_order.bit_length() + padding_rows
+        n = _ceil_pow2(ring_size + rows_besides_keys)
+        return cls(domain_size=n, max_ring_size=n - rows_besides_keys, padding_rows=padding_rows, base_root=base_root, base_root_size=base_root_size,
+                   test_vectors=test_vectors, cv=cv, max_domain_size=max_domain_size)  # fmt: skip
