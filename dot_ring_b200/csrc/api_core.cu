@@ -10,6 +10,20 @@ int set_error(int code, const std::string& msg) {
     return code;
 }
 
+// ---- fixed-base tables for Bandersnatch scalar multiplications (te.cuh: te_mul_fixed) ----------------
+std::shared_ptr<Ctx::FixedTable> Ctx::fixed_table(const TEAffine& base) {
+    for (auto& t : fixed_tables)
+        if (t->base == base) return t;
+    auto t = std::make_shared<FixedTable>();
+    t->base = base;
+    t->tab.alloc(TE_FIXED_ENTRIES);
+    launch(stream, Dim3(TE_FIXED_WINDOWS * 16 / 32), 32, 0, TeFixedTableBody(), base, t->tab.p);
+    stream_sync(stream);
+    if (fixed_tables.size() >= FIXED_TABLE_CAP) fixed_tables.erase(fixed_tables.begin());
+    fixed_tables.push_back(t);
+    return t;
+}
+
 // ---- NTT plans (twiddle tables per (n, omega)) -----------------------------------------------------
 const NttPlan& Ctx::plan(uint32_t n, const Fr& omega_mont) {
     for (auto& p : plans)

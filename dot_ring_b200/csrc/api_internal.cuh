@@ -72,6 +72,15 @@ struct Ctx {
     DevBuf<G1Affine> aff_a, aff_b;
     bool dense_witness_commit = false;
     bool generic_ntt_path = false;  // force the large-domain route (element-wise twists + ntt_device) at any N: tests  // A/B + cross-check: commit witness columns from coefficients like the reference
+    // te_mul_fixed window tables, one per distinct base point seen by this context (generators and blinding bases of the
+    // suites in use); rings and running calls share ownership, the context keeps the most recent FIXED_TABLE_CAP
+    struct FixedTable {
+        TEAffine base;
+        DevBuf<TEPre> tab;
+    };
+    static constexpr size_t FIXED_TABLE_CAP = 16;
+    std::vector<std::shared_ptr<FixedTable>> fixed_tables;
+    std::shared_ptr<FixedTable> fixed_table(const TEAffine& base);
     bool have_pairing_consts = false;
     PairingConsts pairing_k;
     const PairingConsts& pairing_consts() {
@@ -137,6 +146,7 @@ struct Ring {
     VerifierKeyDev vk{};
     DevBuf<LineCoeffs> vk_lines;
     SuiteDev suite{};
+    std::shared_ptr<Ctx::FixedTable> g_table, b_table;
 };
 
 

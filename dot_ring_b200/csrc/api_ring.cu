@@ -104,6 +104,10 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     d.seed = te_from_param(prm->seed);
     d.blinding_base = te_from_param(prm->blinding_base);
     d.generator = te_from_param(prm->generator);
+    ring->g_table = ctx->fixed_table(d.generator);
+    ring->b_table = ctx->fixed_table(d.blinding_base);
+    d.g_tab = ring->g_table->tab.p;
+    d.b_tab = ring->b_table->tab.p;
     ring->padding = te_from_param(prm->padding_point);
     d.suite_id_len = prm->suite_id_len;
     memcpy(d.suite_id, prm->suite_id, 32);
@@ -225,6 +229,8 @@ int dr_ring_create(dr_ctx* c, dr_srs* s, const dr_ring_params* prm, const uint8_
     ring->vk = make_verifier_key(ctx, N, d.omega, d.seed, d.suite_id, d.suite_id_len, srs->g1_0_be96, srs->g2_be192, ring->commit_be96, ring->vk_lines);
     ring->suite.generator = d.generator;
     ring->suite.blinding_base = d.blinding_base;
+    ring->suite.g_tab = d.g_tab;
+    ring->suite.b_tab = d.b_tab;
     ring->suite.suite_id_len = d.suite_id_len;
     memcpy(ring->suite.suite_id, d.suite_id, 32);
     ring->suite.dst_len = d.dst_len;

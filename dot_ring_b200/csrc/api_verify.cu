@@ -317,6 +317,9 @@ static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_
     ctx->activate();
     if (!n) return;
     SuiteDev su = suite_from_abi(suite);
+    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);
+    su.g_tab = g_table->tab.p;
+    su.b_tab = b_table->tab.p;
     ItemsDev items;
     upload_items(ctx, items, n, blob, in_off, in_len, ad_off, ad_len);
     const size_t len = kind == 0 ? 192 : kind == 1 ? 80 : 96;

@@ -40,6 +40,8 @@ struct RingDev {
     Fr w_last;                         // w^(N-4)
     Fr tail[4];                        // coefficients of (X - w^(N-1))(X - w^(N-2))(X - w^(N-3))
     TEAffine seed, blinding_base, generator;
+    const TEPre* g_tab;  // window tables of generator / blinding_base for te_mul_fixed (TeFixedTableBody)
+    const TEPre* b_tab;
     uint32_t suite_id_len;
     uint8_t suite_id[32];
     uint32_t dst_len;
@@ -238,9 +240,11 @@ template <class S>
 DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint8_t* msg, uint32_t msg_len, const uint8_t* ad, uint32_t ad_len, uint8_t* out192,
                                     TEAffine& pk, TEAffine& blinded, uint32_t* blinding_raw) {
     Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
-    pk = te_mul_fn(rg.generator, x);
+    uint32_t xr[8], kr[8], kbr[8];
+    fn_raw_limbs(xr, x);
     TEAffine input = vrf_encode_to_curve(rg, msg, msg_len);
-    TEAffine output = te_mul_fn(input, x);
+    TEAffine output;
+    te_to_affine2(te_mul_fixed(rg.g_tab, xr), te_mul_raw(input, xr, 8), pk, output);
     // vrf_transcript (primitives.py:102-144) with one I/O pair
     VrfHash tr;
     tr.init(rg.hash_kind);
@@ -257,15 +261,15 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     VrfHash tb = tr;
     tb.update_byte(0x12);
     Fn b = vrf_nonce(tb, x);
-    TEAffine bb = te_mul_fn(rg.blinding_base, b);
-    blinded = te_to_affine(te_add(TEExt::from_affine(pk), TEExt::from_affine(bb)));
+    fn_raw_limbs(blinding_raw, b);
+    blinded = te_to_affine(te_add(te_mul_fixed(rg.b_tab, blinding_raw), TEExt::from_affine(pk)));
     sha_absorb_point(tr, blinded);
     Fn k = vrf_nonce(tr, x);
     Fn kb = vrf_nonce(tr, b);
-    TEAffine kg = te_mul_fn(rg.generator, k);
-    TEAffine kbb = te_mul_fn(rg.blinding_base, kb);
-    TEAffine R = te_to_affine(te_add(TEExt::from_affine(kg), TEExt::from_affine(kbb)));
-    TEAffine ok = te_mul_fn(input, k);
+    fn_raw_limbs(kr, k);
+    fn_raw_limbs(kbr, kb);
+    TEAffine R, ok;
+    te_to_affine2(te_add(te_mul_fixed(rg.g_tab, kr), te_mul_fixed(rg.b_tab, kbr)), te_mul_raw(input, kr, 8), R, ok);
     VrfHash tc = tr;
     tc.update_byte(0x40);
     sha_absorb_point(tc, R);
@@ -281,8 +285,33 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     te_encode(out192 + 96, ok);
     fn_to_le_bytes(out192 + 128, s);
     fn_to_le_bytes(out192 + 160, sb);
-    fn_raw_limbs(blinding_raw, b);
 }
+
+// Window table for te_mul_fixed: thread (w, c) of 32 x 16 writes the 16 entries d = 16c .. 16c + 15 of window w.
+struct TeFixedTableBody {
+    DR_HD void operator()(const BlockCtx& ctx, TEAffine base, TEPre* out) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < (uint32_t)TE_FIXED_WINDOWS * 16) {
+                const uint32_t w = i >> 4, first = (i & 15) * 16;
+                TEExt step = TEExt::from_affine(base);
+#pragma unroll 1
+                for (uint32_t j = 0; j < 8 * w; j++) step = te_dbl(step);
+                TEExt cur = TEExt::identity();
+#pragma unroll 1
+                for (int bit = 7; bit >= 0; bit--) {
+                    cur = te_dbl(cur);
+                    if ((first >> bit) & 1) cur = te_add(cur, step);
+                }
+#pragma unroll 1
+                for (uint32_t d = first; d < first + 16; d++) {
+                    out[256 * w + d] = TEPre::from_affine(d ? te_to_affine(cur) : TEAffine::identity());
+                    cur = te_add(cur, step);
+                }
+            }
+        }
+    }
+};
 
 // one thread per proof
 struct PedersenProveBody {

@@ -122,6 +122,27 @@ DR_HD_COLD TEExt te_mul_raw(const TEAffine& p, const uint32_t* k, int nlimbs) {
     return acc;
 }
 
+// k * P for a point with a precomputed window table (8-bit windows over 256 bits: tab[256 * w + d] = d * 2^(8w) * P in
+// affine form, d >= 1; built once per base point by TeFixedTableBody): at most 32 mixed additions, no doublings.
+constexpr int TE_FIXED_WINDOWS = 32;
+constexpr int TE_FIXED_ENTRIES = TE_FIXED_WINDOWS * 256;
+DR_HD_COLD TEExt te_mul_fixed(const TEPre* tab, const uint32_t* k) {
+    TEExt acc = TEExt::identity();
+#pragma unroll 1
+    for (int w = 0; w < TE_FIXED_WINDOWS; w++) {
+        uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 255;
+        if (d) acc = te_madd(acc, tab[256 * w + d]);
+    }
+    return acc;
+}
+// two conversions around one field inversion
+DR_HD void te_to_affine2(const TEExt& p, const TEExt& q, TEAffine& pa, TEAffine& qa) {
+    Fr zi = (p.Z * q.Z).inv();
+    Fr pzi = zi * q.Z, qzi = zi * p.Z;
+    pa = {p.X * pzi, p.Y * pzi};
+    qa = {q.X * qzi, q.Y * qzi};
+}
+
 // sum_i k_i * P_i with shared doublings (Straus), n <= 3, raw 8-limb scalars (< subgroup order).
 DR_HD_COLD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int n) {
     TEExt tab[3][16];

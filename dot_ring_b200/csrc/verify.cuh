@@ -20,6 +20,8 @@ namespace dr {
 
 struct SuiteDev {  // VRF suite constants (dot_ring/curve/specs/bandersnatch.py:48-107)
     TEAffine generator, blinding_base;
+    const TEPre* g_tab;  // te_mul_fixed tables; set by the provers only (the verifiers' multiplications are joint, te_msm_small)
+    const TEPre* b_tab;
     uint32_t suite_id_len;
     uint8_t suite_id[32];
     uint32_t dst_len;
@@ -218,9 +220,11 @@ struct IetfProveBody {  // thin == 0: O | c | s (80 bytes);  thin != 0: O | R | 
             if (i < count) {
                 const VerifyInput& vi = in[i];
                 Fn x = fp_from_le_bytes_mod<Fn>(sks32 + 32 * (size_t)i, 32);
-                TEAffine pk = te_mul_fn(su.generator, x);
+                uint32_t xr[8];
+                fn_raw_limbs(xr, x);
                 TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
-                TEAffine output = te_mul_fn(input, x);
+                TEAffine pk, output;
+                te_to_affine2(te_mul_fixed(su.g_tab, xr), te_mul_raw(input, xr, 8), pk, output);
                 VrfHash tr;
                 tr.init(su.hash_kind);
                 tr.update(su.suite_id, su.suite_id_len);
