@@ -169,11 +169,23 @@ def run_ours(args) -> None:
         from tests.host.emul import emulation_library
 
         library = emulation_library()
-    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library)
+    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library, wide_windows=args.wide_windows)
     if not dry_run and not eng.ctx.library.is_cuda:
         raise SystemExit("bench.py measures the CUDA build only")
     eng_mod.set_default_engine(eng, local)
-    _ = eng.srs
+    # the requested table first; if the device cannot hold it (a smaller part, memory in use) fall back to the next smaller geometry
+    requested = (args.window_bits, args.wide_windows)
+    size = lambda g: (-(-(256 - g[1]) // g[0]) + g[1]) << (g[0] - 1) if g[0] else 0  # table entries per SRS point  # noqa: E731
+    for c, k in [requested] + [g for g in ((14, 4), (14, 0), (13, 0), (12, 0)) if size(g) < size(requested)]:
+        eng.window_bits, eng.wide_windows = c, k
+        try:
+            _ = eng.srs
+            break
+        except MemoryError as e:
+            print(f"[bench] window table ({c}, {k}) does not fit: {e}", file=sys.stderr, flush=True)
+            eng.ctx.trim()
+    else:
+        raise SystemExit("bench.py: no window table fits on this device")
     eng.ctx.set_commit_mode(args.commit_mode)
     eng.ctx.sync()
     table_s = time.perf_counter() - t0
@@ -242,7 +254,8 @@ def run_ours(args) -> None:
     e2e = proofs_total / mx[1]
     commit_ms = phases[2]
     achieved = CANONICAL_IMAD_PER_PROOF * batch * args.steps / (commit_ms * 1e-3)
-    madds_per_proof = sum(DENSE_MSM_SIZES) * (-(-256 // args.window_bits)) + SPARSE_WITNESS_MADDS
+    window_bits, wide_windows, windows = eng.srs.geometry
+    madds_per_proof = sum(DENSE_MSM_SIZES) * windows + SPARSE_WITNESS_MADDS
     executed = madds_per_proof * 10 * 600 * batch * args.steps / (commit_ms * 1e-3)  # 8M + 2S per mixed addition, 600 IMAD per Fq mul
     table_traffic = madds_per_proof * 96 * batch * args.steps  # algorithmic table bytes read
 
@@ -266,7 +279,9 @@ def run_ours(args) -> None:
         "config": {
             "workload": f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {batch} proofs per GPU per step (BASELINE configs[1])",
             "batch_per_gpu": batch,
-            "window_bits": args.window_bits,
+            "window_bits": window_bits,
+            "wide_windows": wide_windows,
+            "table_additions_per_coefficient": windows,
             "table_gb": round(eng.srs.table_bytes / 1e9, 2),
             "l2": "per-step working set (window table + ~8 GB scratch) is far larger than the 126 MB L2; no flush needed",
             "parity": "ring root sha256 " + hashlib.sha256(root_bytes).hexdigest()[:16],
@@ -411,11 +426,14 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "14")))
+    ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "14")), help="fixed-base table window width; 0 = sized by the library")
+    ap.add_argument("--wide-windows", type=int, default=None, help="how many low windows take one more bit (default 4 with 14-bit windows: 18 additions per coefficient, 106 GB)")
     ap.add_argument("--commit-mode", type=int, default=int(os.environ.get("DOT_RING_B200_COMMIT_MODE", "0")), help="0 XYZZ accumulation, 1 batched-affine rounds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()
+    if args.wide_windows is None:
+        args.wide_windows = int(os.environ.get("DOT_RING_B200_WIDE_WINDOWS", "4" if args.window_bits == 14 else "0"))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -131,7 +131,7 @@ void PhaseTimer::collect(Ctx* ctx) {
 void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table) {
     if (geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
     table.alloc(geom.total_entries());
-    uint32_t chunks = geom.H >= 512 ? geom.H / 256 : 1;  // <= 256 serial additions per thread
+    uint32_t chunks = geom.max_entries() >= 512 ? geom.max_entries() / 256 : 1;  // <= 256 serial additions per thread
     size_t nthreads = (size_t)geom.n_points * chunks;
     const uint32_t tb = 64;
     Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
@@ -369,29 +369,44 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !g1_be96 || !g2_be192 || !out || n_g1 == 0) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
-    uint32_t cbits = (uint32_t)window_bits;
+    uint32_t cbits = (uint32_t)window_bits & 0xff, wide = ((uint32_t)window_bits >> 8) & 0xff;
     if (window_bits <= 0) {
-        // largest window whose table fits in half of the free device memory (14 bits = 92 GB for 6145 points on a 180 GB part)
+        // the cheapest table that leaves max(24 GB, a quarter of its size) of the free device memory for everything else: on a
+        // 180 GB part 14-bit windows with four 15-bit ones (18 additions per coefficient, 106 GB for 6145 points), else uniform
         cbits = 8;
+        wide = 0;
 #if !defined(DR_HOST_EMULATION)
         size_t free_b = 0, total_b = 0;
         DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
         free_b += dev_cache().cached;
-        for (uint32_t c = 14; c >= 8; c--) {
-            if (make_geom(c, (uint32_t)n_g1).total_entries() * sizeof(G1Affine) <= free_b / 2) {
-                cbits = c;
-                break;
+        auto fits = [&](uint32_t c, uint32_t k) {
+            size_t bytes = make_geom(c, (uint32_t)n_g1, k).total_entries() * sizeof(G1Affine);
+            size_t reserve = bytes / 4 > ((size_t)24 << 30) ? bytes / 4 : ((size_t)24 << 30);
+            return bytes + reserve <= free_b;
+        };
+        if (fits(14, 4)) {
+            cbits = 14;
+            wide = 4;
+        } else {
+            for (uint32_t c = 14; c >= 8; c--) {
+                if (fits(c, 0)) {
+                    cbits = c;
+                    break;
+                }
             }
         }
 #endif
+    } else if (window_bits >> 16) {
+        throw Error(DR_EINVAL, "bad window_bits");
     }
     if (cbits < 2 || cbits > 15) throw Error(DR_EINVAL, "window_bits must be in [2, 15]");
+    if (wide && (cbits + 1 > 16 || wide > make_geom(cbits, 1, wide).W)) throw Error(DR_EINVAL, "bad number of wide windows");
     auto srs = std::make_unique<Srs>();
     srs->ctx = ctx;
     srs->n = (uint32_t)n_g1;
     memcpy(srs->g1_0_be96, g1_be96, 96);
     memcpy(srs->g2_be192, g2_be192, 384);
-    srs->geom = make_geom(cbits, srs->n);
+    srs->geom = make_geom(cbits, srs->n, wide);
     DevBuf<uint8_t> raw(n_g1 * 96);
     DevBuf<uint32_t> bad(1);
     dev_zero(ctx->stream, bad.p, 4);
@@ -411,6 +426,12 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
 
 void dr_srs_destroy(dr_srs* s) { delete (Srs*)s; }
 size_t dr_srs_size(const dr_srs* s) { return s ? ((const Srs*)s)->n : 0; }
+void dr_srs_geometry(const dr_srs* s, uint32_t* window_bits, uint32_t* wide_windows, uint32_t* windows) {
+    const TableGeom g = s ? ((const Srs*)s)->geom : TableGeom{};
+    if (window_bits) *window_bits = g.c;
+    if (wide_windows) *wide_windows = g.wide;
+    if (windows) *windows = g.W;
+}
 size_t dr_srs_table_bytes(const dr_srs* s) { return s ? ((const Srs*)s)->geom.total_entries() * sizeof(G1Affine) : 0; }
 
 int dr_kzg_commit(dr_ctx* c, dr_srs* s, const uint8_t* coeffs_le32, size_t n, size_t batch, uint8_t* out_be96) {

@@ -305,7 +305,9 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         ProveScratch& cur = scratch_for(ctx);
         size_t per_proof = (35 + (N > 4096 ? 16 : 0)) * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
         size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
-        size_t fit = have / 2 / per_proof;
+        // keep 3 GB (or half of what is left, if less) for the other buffers of this and later calls
+        const size_t keep = have / 2 < ((size_t)3 << 30) ? have / 2 : ((size_t)3 << 30);
+        size_t fit = (have - keep) / per_proof;
         if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
     }
 #endif

@@ -16,19 +16,26 @@
 namespace dr {
 
 struct TableGeom {
-    uint32_t c;        // window bits
-    uint32_t W;        // windows = ceil(256 / c)
-    uint32_t H;        // entries per (i, w) = 2^(c-1)
+    uint32_t c;        // bits of a (narrow) window
+    uint32_t W;        // windows; W * c + wide >= 256
+    uint32_t H;        // entries per (i, w) of a narrow window = 2^(c-1)
     uint32_t n_points; // SRS points covered
-    DR_HD size_t entry(uint32_t i, uint32_t w, uint32_t d) const { return (((size_t)i * W + w) << (c - 1)) + (d - 1); }
-    size_t total_entries() const { return ((size_t)n_points * W) << (c - 1); }
+    uint32_t wide;     // the `wide` lowest windows take c + 1 bits (2H entries each): one window fewer per scalar for (W + wide) / (W + 1)
+                       // of the memory; 0 = uniform windows
+    DR_HD uint32_t width(uint32_t w) const { return c + (w < wide ? 1u : 0u); }
+    DR_HD uint32_t bit(uint32_t w) const { return w * c + (w < wide ? w : wide); }
+    DR_HD uint32_t max_entries() const { return wide ? 2 * H : H; }
+    // point i owns (W + wide) * H consecutive entries; window w starts at (w + min(w, wide)) * H
+    DR_HD size_t entry(uint32_t i, uint32_t w, uint32_t d) const { return (((size_t)i * (W + wide) + w + (w < wide ? w : wide)) << (c - 1)) + (d - 1); }
+    size_t total_entries() const { return ((size_t)n_points * (W + wide)) << (c - 1); }
 };
-inline TableGeom make_geom(uint32_t c, uint32_t n_points) {
+inline TableGeom make_geom(uint32_t c, uint32_t n_points, uint32_t wide = 0) {
     TableGeom g;
     g.c = c;
-    g.W = (256 + c - 1) / c;
+    g.W = (256 - wide + c - 1) / c;
     g.H = 1u << (c - 1);
     g.n_points = n_points;
+    g.wide = wide;
     return g;
 }
 
@@ -60,8 +67,10 @@ struct TableBuildBody {
             uint32_t i = gid / chunks, q = gid % chunks;
             if (i < g.n_points) {
                 const uint32_t W = g.W;
-                const uint32_t L = g.H / chunks;
+                const uint32_t L = g.max_entries() / chunks;
                 const uint32_t d0 = q * L + 1;
+                // digits above H exist only in the `wide` lowest windows; W0 = windows this chunk starts with
+                const uint32_t W0 = d0 > g.H ? g.wide : W;
                 Fq bx[MAXW], by[MAXW], ex[MAXW], ey[MAXW], den[MAXW], pre[MAXW];
                 // 1. window bases B_w = 2^(c*w) * P_i
                 {
@@ -72,7 +81,7 @@ struct TableBuildBody {
                         proj[w] = cur;
                         if (w + 1 < W)
 #pragma unroll 1
-                            for (uint32_t k = 0; k < g.c; k++) cur = g1_dbl(cur);
+                            for (uint32_t k = 0; k < g.width(w); k++) cur = g1_dbl(cur);
                     }
                     // batch normalise: x = X / ZZ, y = Y / ZZZ
                     Fq acc = Fq::one();
@@ -94,14 +103,14 @@ struct TableBuildBody {
                 // 2. chunk start E_w = d0 * B_w
                 if (d0 == 1) {
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
+                    for (uint32_t w = 0; w < W0; w++) {
                         ex[w] = bx[w];
                         ey[w] = by[w];
                     }
                 } else {
                     G1 proj[MAXW];
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
+                    for (uint32_t w = 0; w < W0; w++) {
                         G1Affine b{bx[w], by[w]};
                         G1 acc = G1::inf();
 #pragma unroll 1
@@ -113,14 +122,14 @@ struct TableBuildBody {
                     }
                     Fq acc = Fq::one();
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
+                    for (uint32_t w = 0; w < W0; w++) {
                         pre[w] = acc;
                         den[w] = proj[w].ZZ * proj[w].ZZZ;
                         acc = acc * den[w];
                     }
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)W - 1; w >= 0; w--) {
+                    for (int w = (int)W0 - 1; w >= 0; w--) {
                         Fq di = inv * pre[w];
                         inv = inv * den[w];
                         ex[w] = proj[w].X * (di * proj[w].ZZZ);
@@ -128,13 +137,14 @@ struct TableBuildBody {
                     }
                 }
 #pragma unroll 1
-                for (uint32_t w = 0; w < W; w++) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
+                for (uint32_t w = 0; w < W0; w++) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
                 // 3. E_w += B_w, one shared inversion per step
 #pragma unroll 1
                 for (uint32_t d = d0 + 1; d < d0 + L; d++) {
+                    const uint32_t Wd = d > g.H ? g.wide : W;
                     Fq acc = Fq::one();
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
+                    for (uint32_t w = 0; w < Wd; w++) {
                         pre[w] = acc;
                         // E == B only for d == 2 (then the chord degenerates to the tangent); E == -B never
                         den[w] = (d == 2) ? ey[w].dbl() : bx[w] - ex[w];
@@ -142,7 +152,7 @@ struct TableBuildBody {
                     }
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)W - 1; w >= 0; w--) {
+                    for (int w = (int)Wd - 1; w >= 0; w--) {
                         Fq di = inv * pre[w];
                         inv = inv * den[w];
                         Fq num;
@@ -246,8 +256,8 @@ struct G1PrefixSumBody {
 
 // ---- signed-digit recoding -------------------------------------------------------------------------
 // k: canonical little-endian limbs (< 2^255).  Returns digit w in [-(H-1), H]; carry is threaded.
-DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) {
-    uint32_t bit = w * c;
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t bit, uint32_t c, uint32_t& carry) {
+    (void)w;
     uint32_t limb = bit >> 5, off = bit & 31;
     uint64_t two = (limb < 8 ? (uint64_t)k[limb] : 0) | ((limb + 1 < 8 ? (uint64_t)k[limb + 1] : 0) << 32);
     uint32_t raw = (uint32_t)(two >> off) & ((1u << c) - 1);
@@ -260,6 +270,9 @@ DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) 
     carry = 0;
     return (int)d;
 }
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, const TableGeom& g, uint32_t& carry) { return msm_digit(k, w, g.bit(w), g.width(w), carry); }
+// uniform windows of c bits
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) { return msm_digit(k, w, w * c, c, carry); }
 
 // ---- batched commit ----------------------------------------------------------------------------------
 // grid = (slices, batch).  MSM `by` uses scalars[by * scalar_stride + i] (Montgomery Fr), i < n, against
@@ -278,7 +291,7 @@ struct CommitBody {
             for (uint32_t i = lo + t; i < hi; i += ctx.nthreads) {
                 Fr kc = sc[i].from_mont();
                 uint32_t carry = 0;
-                int d_next = msm_digit(kc.v, 0, g.c, carry);
+                int d_next = msm_digit(kc.v, 0, g, carry);
                 G1Affine pt_next = G1Affine::inf();
                 if (d_next) pt_next = table[g.entry(i, 0, (uint32_t)(d_next < 0 ? -d_next : d_next))];
 #pragma unroll 1
@@ -286,7 +299,7 @@ struct CommitBody {
                     int d = d_next;
                     G1Affine pt = pt_next;
                     if (w + 1 < g.W) {
-                        d_next = msm_digit(kc.v, w + 1, g.c, carry);
+                        d_next = msm_digit(kc.v, w + 1, g, carry);
                         if (d_next) pt_next = table[g.entry(i, w + 1, (uint32_t)(d_next < 0 ? -d_next : d_next))];
                     }
                     if (d) g1_madd(acc, pt, d < 0);
@@ -421,7 +434,7 @@ struct CommitAffineBody {
                         uint32_t carry = 0;
 #pragma unroll 1
                         for (uint32_t w = 0; w < g.W; w++) {
-                            int d = msm_digit(kc.v, w, g.c, carry);
+                            int d = msm_digit(kc.v, w, g, carry);
                             if (d) {
                                 refs[(size_t)count * 32 + lane] = (uint32_t)g.entry(i, w, (uint32_t)(d < 0 ? -d : d)) | (d < 0 ? 0x80000000u : 0u);
                                 count++;

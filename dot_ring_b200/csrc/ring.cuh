@@ -461,7 +461,7 @@ struct WitnessCommitBody {
                     s[1] = flip ? 1 : 0;
                     uint32_t carry = 0;
 #pragma unroll 1
-                    for (uint32_t w = 0; w < g.W; w++) s[2 + w] = (int16_t)msm_digit(kc.v, w, g.c, carry);
+                    for (uint32_t w = 0; w < g.W; w++) s[2 + w] = (int16_t)msm_digit(kc.v, w, g, carry);
                 }
             }
         }

@@ -20,11 +20,13 @@ _engines: dict[int, "Engine"] = {}
 
 class Engine:
     def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None,
-                 srs: "SrsBytes | None" = None):
+                 srs: "SrsBytes | None" = None, wide_windows: int = 0):
         self.device = device
         self.ctx = _native.Context(device, library)
         env = os.environ.get("DOT_RING_B200_WINDOW_BITS")
-        self.window_bits = int(window_bits) if window_bits is not None else (int(env) if env else None)
+        # None / 0 = let the library size the table from the free HBM (dr_srs_load); wide_windows only with an explicit width
+        self.window_bits = int(window_bits) if window_bits is not None else (int(env) if env else 0)
+        self.wide_windows = int(wide_windows) if self.window_bits else 0
         self._srs: _native.NativeSrs | None = None
         self._srs_points = srs_points
         # `srs` overrides the bundled 6145-point file (needed for domains above 2048, whose quotient has 3N + 1 coefficients)
@@ -32,22 +34,11 @@ class Engine:
 
     @property
     def srs(self) -> _native.NativeSrs:
-        """SRS points + window table in HBM, built on first use (about 0.5 s for the default 26.6 GB table)."""
+        """SRS points + window table in HBM, built on first use (about 3.5 s for the 106 GB table a B200 gets by default)."""
         if self._srs is None:
-            if self.window_bits is None:
-                self.window_bits = self._auto_window_bits()
-            self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits)
+            self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits, self.wide_windows)
+            self.window_bits, self.wide_windows, self.windows = self._srs.geometry
         return self._srs
-
-    def _auto_window_bits(self) -> int:
-        """Largest window whose table (n * ceil(256/c) * 2^(c-1) * 96 B) fits in half of the free HBM: 14 bits = 92 GB for
-        the bundled 6145-point SRS on a 180 GB B200 (19 additions per coefficient; 12 bits = 27 GB, 22 additions)."""
-        free = self.ctx.device_info()["free_bytes"]
-        n = self.srs_bytes.n_g1
-        for c in (14, 13, 12, 11, 10, 9, 8):
-            if n * -(-256 // c) * (1 << (c - 1)) * 96 <= free // 2:
-                return c
-        return 8
 
     def close(self) -> None:
         if self._srs is not None:

@@ -213,3 +213,9 @@ def test_pedersen_blinding_factor_and_unblinding(api):
     assert proof.verify_unblinding(hx(v, "pk"), proof._blinding_factor)
     assert not proof.verify_unblinding(hx(v, "pk"), proof._blinding_factor + 1)
     assert cls.decode(proof.encode())._blinding_factor is None
+
+
+def test_mixed_window_geometries_commit_like_the_oracle(api):
+    from tests import window_cases
+
+    window_cases.check_commit_geometries(engine_mod.default_engine().ctx, [(4, 4), (5, 1), (7, 4)], n=5)

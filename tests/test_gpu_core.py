@@ -63,6 +63,18 @@ def test_kzg_commit_matches_oracle(ctx, small_srs):
             assert g == bls.g1_serialize(rp.kzg_commit(sub, v))
 
 
+def test_mixed_window_geometries_commit_like_the_oracle(ctx):
+    """dr_srs_load geometries with some windows one bit wider (the bench default is 14 bits with four 15-bit windows)."""
+    from tests import window_cases
+
+    window_cases.check_commit_geometries(ctx, [(8, 8), (10, 6), (13, 9), (14, 4)], n=40)
+    ctx.set_commit_mode(1)  # batched-affine rounds read the same table
+    try:
+        window_cases.check_commit_geometries(ctx, [(8, 8)], n=700, seed=6)
+    finally:
+        ctx.set_commit_mode(0)
+
+
 def test_kzg_commit_linearity_full_size(ctx, small_srs):
     """Size-independent property: commit(a) + commit(b) == commit(a + b) at the full table width."""
     rng = random.Random(12)
