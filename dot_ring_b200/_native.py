@@ -9,9 +9,12 @@ explicitly; nothing in this package ever selects it.
 from __future__ import annotations
 
 import ctypes
+import itertools
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 from pathlib import Path
+
+import numpy as np
 
 DR_OK, DR_EINVAL, DR_ECUDA, DR_ENOMEM, DR_ESTATE = 0, -1, -2, -3, -4
 
@@ -203,13 +206,18 @@ def pack_items(inputs: list[bytes], ads: list[bytes]):
     n = len(inputs)
     if len(ads) != n:
         raise ValueError("inputs and additional data must have the same length")
-    blob = bytearray()
-    offs = [[], [], [], []]
-    for a, d in zip(inputs, ads):
-        offs[0].append(len(blob)); offs[1].append(len(a)); blob += a
-        offs[2].append(len(blob)); offs[3].append(len(d)); blob += d
-    U32 = ctypes.c_uint32 * max(n, 1)
-    return (bytes(blob) if blob else None, *[U32(*o) for o in offs])
+    if n == 0:
+        U32 = ctypes.c_uint32 * 1
+        return None, U32(), U32(), U32(), U32()
+    in_len = np.fromiter(map(len, inputs), dtype=np.uint32, count=n)
+    ad_len = np.fromiter(map(len, ads), dtype=np.uint32, count=n)
+    ends = np.cumsum(in_len.astype(np.uint64) + ad_len)
+    if int(ends[-1]) >> 32:
+        raise ValueError("a batch carries at most 4 GiB of input and additional data")
+    in_off = (ends - in_len - ad_len).astype(np.uint32)
+    ad_off = in_off + in_len
+    blob = b"".join(itertools.chain.from_iterable(zip(inputs, ads)))
+    return (blob or None, *[np.ctypeslib.as_ctypes(a) for a in (in_off, in_len, ad_off, ad_len)])
 
 
 class Context:
@@ -612,14 +620,10 @@ class NativeRing:
         n = len(alphas)
         if not (len(ads) == len(secret_keys) == len(producer_index) == n):
             raise ValueError("batch inputs must have equal length")
-        blob = bytearray()
-        a_off, a_len, d_off, d_len = [], [], [], []
-        for a, d in zip(alphas, ads):
-            a_off.append(len(blob)); a_len.append(len(a)); blob += a
-            d_off.append(len(blob)); d_len.append(len(d)); blob += d
-        U32 = ctypes.c_uint32 * max(n, 1)
+        blob, a_off, a_len, d_off, d_len = pack_items(alphas, ads)
         proofs = ctypes.create_string_buffer(784 * max(n, 1))
-        status = U32()
+        status = (ctypes.c_uint32 * max(n, 1))()
+        rows = np.ctypeslib.as_ctypes(np.array(producer_index if n else [0], dtype=np.uint32))
         zk = None
         if isinstance(zk_rows, (bytes, bytearray)):  # already 12 x 32-byte little-endian values per proof
             if len(zk_rows) != 12 * 32 * n:
@@ -632,12 +636,11 @@ class NativeRing:
         lib = self.ctx.library
         lib.check(
             lib.lib.dr_ring_prove_batch(
-                self.ctx.handle, self.handle, n, bytes(blob) if blob else None, U32(*a_off), U32(*a_len), U32(*d_off), U32(*d_len),
-                b"".join(secret_keys), U32(*producer_index), zk, proofs, status,
+                self.ctx.handle, self.handle, n, blob, a_off, a_len, d_off, d_len, b"".join(secret_keys), rows, zk, proofs, status,
             )
         )
         raw = proofs.raw
-        return [raw[784 * i : 784 * i + 784] for i in range(n)], [int(status[i]) for i in range(n)]
+        return [raw[784 * i : 784 * i + 784] for i in range(n)], status[:n]
 
     def verify_batch(self, inputs: list[bytes], ads: list[bytes], proofs: list[bytes], coeffs: list[int], aggregate: bool = False):
         """RingVRF decode + verify for 784-byte proofs -> (per-item verdicts 1 / 0 / 2, all_ok)."""
