@@ -300,10 +300,11 @@ def run_ours(args) -> None:
             "executed_frac": executed / imad_peak,
             "executed_note": f"{madds_per_proof} mixed G1 additions per proof actually issued (fixed-base tables + sparse witness columns) x 6000 IMAD; 'achieved' counts the canonical Pippenger work of all 7 MSMs",
             "peak_source": "measured live: dependent-free mad.lo.u32 on all SMs (dr_microbench); IMAD.WIDE measured " + f"{imad_wide_peak / 1e12:.2f} T/s",
-            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, 14-bit windows;
-            # profiles/r01_ncu_full_CommitBody_c14.csv) against 11.5 GB of table entries it must touch: 96-byte entries straddle sectors
-            "traffic": 23.1e9,
-            "traffic_launch": "CommitBody grid (2, 1024) x 128 threads, 46.8 ms under ncu; algorithmic table bytes of that launch 11.5e9",
+            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, 18 additions per coefficient;
+            # profiles/r01_ncu_full_CommitBody_w18.csv) against 10.9 GB of table entries it must touch: a 96-byte entry at a random
+            # address straddles 64-byte DRAM atoms (2 or 3 of them), and the kernel is bound by the integer pipe, not by these reads
+            "traffic": 23.0e9,
+            "traffic_launch": "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9",
             "algorithmic_table_bytes": table_traffic,
             "hbm_gbs_for_table_reads": table_traffic / (commit_ms * 1e-3) / 1e9,
             "kernel_share_of_step": commit_ms / sum(phases),
@@ -352,13 +353,14 @@ def _oracle_prove_n(args):
 def cpu_baseline_single() -> dict:
     from oracle import backend_name
 
-    dt = _oracle_prove_n((1, 0))
+    count = int(os.environ.get("DOT_RING_B200_CPU_BASELINE_PROOFS", "10"))  # about 11 s of CPU work
+    dt = _oracle_prove_n((count, 0))
     return {
-        "value": 1.0 / dt,
+        "value": count / dt,
         "unit": "proofs/s",
         "cores": 1,
         "kind": "port",
-        "sample": f"1 proof, ring {RING_SIZE} / domain 2048, oracle port ({backend_name()}), ring set-up excluded",
+        "sample": f"{count} proofs, ring {RING_SIZE} / domain 2048, oracle port ({backend_name()}), ring set-up excluded",
     }
 
 
