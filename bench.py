@@ -66,15 +66,43 @@ CANONICAL_IMAD_PER_PROOF = sum(canonical_fq_mul_per_msm(n) for n in MSM_SIZES) *
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock, power and throttle reasons sampled during the timed region: NVML in-process (no child process next to the
+    timed calls); `nvidia-smi` only when the NVML binding is missing."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, device: int):
         super().__init__(daemon=True)
-        self.device = device
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in visible.split(",") if v.strip()]
+        self.device = int(ids[device]) if device < len(ids) and ids[device].isdigit() else device
         self.samples: list[dict] = []
         self._halt = threading.Event()
 
+    def _nvml_loop(self) -> bool:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return False
+        while not self._halt.is_set():
+            try:
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append({
+                    "sm": float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), "max": sm_max, "power": pynvml.nvmlDeviceGetPowerUsage(h) / 1e3,
+                    "reasons": ["Active" if mask & bit else "Not Active" for bit, _ in self.REASONS],
+                })  # fmt: skip
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+        return True
+
     def run(self) -> None:
+        if self._nvml_loop():
+            return
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
             try:
@@ -169,20 +197,20 @@ def run_ours(args) -> None:
         from tests.host.emul import emulation_library
 
         library = emulation_library()
-    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library, wide_windows=args.wide_windows)
+    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library, wide_windows=args.wide_windows, glv=bool(args.glv))
     if not dry_run and not eng.ctx.library.is_cuda:
         raise SystemExit("bench.py measures the CUDA build only")
     eng_mod.set_default_engine(eng, local)
     # the requested table first; if the device cannot hold it (a smaller part, memory in use) fall back to the next smaller geometry
-    requested = (args.window_bits, args.wide_windows)
-    size = lambda g: (-(-(256 - g[1]) // g[0]) + g[1]) << (g[0] - 1) if g[0] else 0  # table entries per SRS point  # noqa: E731
-    for c, k in [requested] + [g for g in ((14, 4), (14, 0), (13, 0), (12, 0)) if size(g) < size(requested)]:
-        eng.window_bits, eng.wide_windows = c, k
+    requested = (args.window_bits, args.wide_windows, bool(args.glv))
+    size = lambda g: (-(-((128 if g[2] else 256) - g[1]) // g[0]) + g[1]) << (g[0] - 1) if g[0] else 0  # ~table entries per SRS point  # noqa: E731
+    for c, k, glv in [requested] + [g for g in ((14, 4, False), (14, 0, False), (13, 0, False), (12, 0, False)) if size(g) < size(requested)]:
+        eng.window_bits, eng.wide_windows, eng.glv = c, k, glv
         try:
             _ = eng.srs
             break
         except MemoryError as e:
-            print(f"[bench] window table ({c}, {k}) does not fit: {e}", file=sys.stderr, flush=True)
+            print(f"[bench] window table ({c}, {k}, glv={glv}) does not fit: {e}", file=sys.stderr, flush=True)
             eng.ctx.trim()
     else:
         raise SystemExit("bench.py: no window table fits on this device")
@@ -254,7 +282,7 @@ def run_ours(args) -> None:
     e2e = proofs_total / mx[1]
     commit_ms = phases[2]
     achieved = CANONICAL_IMAD_PER_PROOF * batch * args.steps / (commit_ms * 1e-3)
-    window_bits, wide_windows, windows = eng.srs.geometry
+    window_bits, wide_windows, glv, windows = eng.srs.geometry
     madds_per_proof = sum(DENSE_MSM_SIZES) * windows + SPARSE_WITNESS_MADDS
     executed = madds_per_proof * 10 * 600 * batch * args.steps / (commit_ms * 1e-3)  # 8M + 2S per mixed addition, 600 IMAD per Fq mul
     table_traffic = madds_per_proof * 96 * batch * args.steps  # algorithmic table bytes read
@@ -281,6 +309,7 @@ def run_ours(args) -> None:
             "batch_per_gpu": batch,
             "window_bits": window_bits,
             "wide_windows": wide_windows,
+            "glv_split": bool(glv),
             "table_additions_per_coefficient": windows,
             "table_gb": round(eng.srs.table_bytes / 1e9, 2),
             "l2": "per-step working set (window table + ~8 GB scratch) is far larger than the 126 MB L2; no flush needed",
@@ -428,14 +457,19 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "14")), help="fixed-base table window width; 0 = sized by the library")
-    ap.add_argument("--wide-windows", type=int, default=None, help="how many low windows take one more bit (default 4 with 14-bit windows: 18 additions per coefficient, 106 GB)")
+    ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "16")),
+                    help="fixed-base table window width; 0 = sized by the library. Default: 16-bit windows over GLV halves (16 additions per coefficient, 161 GB); "
+                    "if that does not fit the run falls back to 14-bit windows with four 15-bit ones (18 additions, 106 GB)")
+    ap.add_argument("--wide-windows", type=int, default=None, help="how many low windows take one more bit (default 4 with 14-bit windows)")
+    ap.add_argument("--glv", type=int, default=None, help="1: table over 128 bits, scalars split with the G1 endomorphism (2 x windows additions per coefficient)")
     ap.add_argument("--commit-mode", type=int, default=int(os.environ.get("DOT_RING_B200_COMMIT_MODE", "0")), help="0 XYZZ accumulation, 1 batched-affine rounds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()
+    if args.glv is None:
+        args.glv = int(os.environ.get("DOT_RING_B200_GLV", "1" if args.window_bits == 16 else "0"))
     if args.wide_windows is None:
-        args.wide_windows = int(os.environ.get("DOT_RING_B200_WIDE_WINDOWS", "4" if args.window_bits == 14 else "0"))
+        args.wide_windows = int(os.environ.get("DOT_RING_B200_WIDE_WINDOWS", "4" if args.window_bits == 14 and not args.glv else "0"))
     if args.impl == "reference":
         run_reference(args)
     else:

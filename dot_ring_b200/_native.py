@@ -72,7 +72,7 @@ class Library:
         L.dr_srs_size.restype = c_size_t
         L.dr_srs_table_bytes.argtypes = [c_void_p]
         L.dr_srs_table_bytes.restype = c_size_t
-        L.dr_srs_geometry.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]
+        L.dr_srs_geometry.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]
         L.dr_srs_geometry.restype = None
         L.dr_kzg_commit.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
         L.dr_kzg_commit_bench.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_uint64, POINTER(c_float), c_void_p]
@@ -473,16 +473,16 @@ class Context:
 class NativeSrs:
     """dr_srs: SRS points + fixed-base window table resident on the device."""
 
-    def __init__(self, ctx: Context, g1_be96: bytes, g2_be192: bytes, window_bits: int = 0, wide_windows: int = 0):
+    def __init__(self, ctx: Context, g1_be96: bytes, g2_be192: bytes, window_bits: int = 0, wide_windows: int = 0, glv: bool = False):
         self.ctx = ctx
         self.handle = c_void_p()
         n = len(g1_be96) // 96
         if len(g2_be192) != 384:
             raise ValueError("expected two 192-byte G2 points")
         lib = ctx.library
-        if not 0 <= window_bits < 256 or not 0 <= wide_windows < 256 or (wide_windows and not window_bits):
+        if not 0 <= window_bits < 256 or not 0 <= wide_windows < 256 or ((wide_windows or glv) and not window_bits):
             raise ValueError("bad window geometry")
-        lib.check(lib.lib.dr_srs_load(ctx.handle, g1_be96, n, g2_be192, window_bits | (wide_windows << 8), ctypes.byref(self.handle)))
+        lib.check(lib.lib.dr_srs_load(ctx.handle, g1_be96, n, g2_be192, window_bits | (wide_windows << 8) | (int(bool(glv)) << 16), ctypes.byref(self.handle)))
         self.size = n
 
     def close(self) -> None:
@@ -497,11 +497,11 @@ class NativeSrs:
             pass
 
     @property
-    def geometry(self) -> tuple[int, int, int]:
-        """(window bits c, number of (c + 1)-bit windows, table additions per coefficient)."""
-        c, k, w = c_uint32(), c_uint32(), c_uint32()
-        self.ctx.library.lib.dr_srs_geometry(self.handle, ctypes.byref(c), ctypes.byref(k), ctypes.byref(w))
-        return c.value, k.value, w.value
+    def geometry(self) -> tuple[int, int, int, int]:
+        """(window bits c, number of (c + 1)-bit windows, GLV split 0 / 1, table additions per coefficient)."""
+        c, k, g, a = c_uint32(), c_uint32(), c_uint32(), c_uint32()
+        self.ctx.library.lib.dr_srs_geometry(self.handle, ctypes.byref(c), ctypes.byref(k), ctypes.byref(g), ctypes.byref(a))
+        return c.value, k.value, g.value, a.value
 
     @property
     def table_bytes(self) -> int:

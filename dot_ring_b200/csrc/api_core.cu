@@ -131,7 +131,7 @@ void PhaseTimer::collect(Ctx* ctx) {
 void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom, DevBuf<G1Affine>& table) {
     if (geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
     table.alloc(geom.total_entries());
-    uint32_t chunks = geom.max_entries() >= 512 ? geom.max_entries() / 256 : 1;  // <= 256 serial additions per thread
+    uint32_t chunks = geom.max_entries() >= 512 ? (geom.max_entries() + 255) / 256 : 1;  // <= 256 serial additions per thread
     size_t nthreads = (size_t)geom.n_points * chunks;
     const uint32_t tb = 64;
     Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
@@ -170,7 +170,7 @@ const LagrangeTable& Srs::lagrange_table(uint32_t N, uint32_t logN, const Fr& om
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
     if (n == 0 || batch == 0) return;
     if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
-    if (ctx->commit_mode == 1 && ((size_t)(n + 31) / 32) * srs->geom.W >= 2 * AFFINE_MIN_PAIRS) {
+    if (ctx->commit_mode == 1 && !srs->geom.glv && ((size_t)(n + 31) / 32) * srs->geom.W >= 2 * AFFINE_MIN_PAIRS) {
         // batched-affine rounds: one warp per (polynomial, slice), persistent CTAs of 4 warps, HBM scratch per resident lane
         const uint32_t warps = COMMIT_THREADS / 32;
         const uint32_t resident = 148 * 4;
@@ -205,7 +205,10 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
     }
     ctx->partials.ensure((size_t)batch * slices);
     const uint32_t threads = COMMIT_THREADS;
-    launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
+    if (srs->geom.glv)
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
+    else
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
     launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
 }
 
@@ -369,7 +372,7 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !g1_be96 || !g2_be192 || !out || n_g1 == 0) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
-    uint32_t cbits = (uint32_t)window_bits & 0xff, wide = ((uint32_t)window_bits >> 8) & 0xff;
+    uint32_t cbits = (uint32_t)window_bits & 0xff, wide = ((uint32_t)window_bits >> 8) & 0xff, glv = ((uint32_t)window_bits >> 16) & 1;
     if (window_bits <= 0) {
         // the cheapest table that leaves max(24 GB, a quarter of its size) of the free device memory for everything else: on a
         // 180 GB part 14-bit windows with four 15-bit ones (18 additions per coefficient, 106 GB for 6145 points), else uniform
@@ -396,17 +399,17 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
             }
         }
 #endif
-    } else if (window_bits >> 16) {
+    } else if (window_bits >> 17) {
         throw Error(DR_EINVAL, "bad window_bits");
     }
-    if (cbits < 2 || cbits > 15) throw Error(DR_EINVAL, "window_bits must be in [2, 15]");
-    if (wide && (cbits + 1 > 16 || wide > make_geom(cbits, 1, wide).W)) throw Error(DR_EINVAL, "bad number of wide windows");
+    if (cbits < 2 || cbits > (glv ? 16u : 15u)) throw Error(DR_EINVAL, "window_bits must be in [2, 15] (16 with the GLV split)");
+    if (wide && (cbits + 1 > 16 || wide > make_geom(cbits, 1, wide, glv).W)) throw Error(DR_EINVAL, "bad number of wide windows");
     auto srs = std::make_unique<Srs>();
     srs->ctx = ctx;
     srs->n = (uint32_t)n_g1;
     memcpy(srs->g1_0_be96, g1_be96, 96);
     memcpy(srs->g2_be192, g2_be192, 384);
-    srs->geom = make_geom(cbits, srs->n, wide);
+    srs->geom = make_geom(cbits, srs->n, wide, glv);
     DevBuf<uint8_t> raw(n_g1 * 96);
     DevBuf<uint32_t> bad(1);
     dev_zero(ctx->stream, bad.p, 4);
@@ -426,11 +429,12 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
 
 void dr_srs_destroy(dr_srs* s) { delete (Srs*)s; }
 size_t dr_srs_size(const dr_srs* s) { return s ? ((const Srs*)s)->n : 0; }
-void dr_srs_geometry(const dr_srs* s, uint32_t* window_bits, uint32_t* wide_windows, uint32_t* windows) {
+void dr_srs_geometry(const dr_srs* s, uint32_t* window_bits, uint32_t* wide_windows, uint32_t* glv, uint32_t* additions) {
     const TableGeom g = s ? ((const Srs*)s)->geom : TableGeom{};
     if (window_bits) *window_bits = g.c;
     if (wide_windows) *wide_windows = g.wide;
-    if (windows) *windows = g.W;
+    if (glv) *glv = g.glv;
+    if (additions) *additions = s ? g.additions() : 0;
 }
 size_t dr_srs_table_bytes(const dr_srs* s) { return s ? ((const Srs*)s)->geom.total_entries() * sizeof(G1Affine) : 0; }
 

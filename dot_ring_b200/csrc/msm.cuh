@@ -15,27 +15,126 @@
 
 namespace dr {
 
+// ---- GLV: k = k1 + k2 * lambda (mod r), lambda = x^2 - 1 (x the BLS12-381 parameter), lambda^2 + lambda + 1 = r, and
+// lambda * (X, Y) = (beta * X, Y) on G1.  k2 = floor(k / lambda), k1 = k mod lambda; both are below 2^128, so a table that
+// covers 128 bits serves both halves: sum_i k_i P_i = A + phi(B) with A, B accumulated from the same entries.
+#define DR_GLV_LAMBDA {0xffffffffu, 0x00000000u, 0x0001a402u, 0xac45a401u}
+#define DR_GLV_MU {0xf6cfee30u, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x1u} /* floor(2^256 / lambda) */
+DR_HD Fq glv_beta() {  // Montgomery form of the cube root of unity matching lambda
+    Fq b;
+    constexpr uint32_t m[12] = {0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu,
+                                0x01bacb9eu, 0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u};
+    for (int i = 0; i < 12; i++) b.v[i] = m[i];
+    return b;
+}
+// k: 8 canonical limbs (< r).  out: the selected half (which == 0: k1, else k2) as 8 limbs, upper four zero.
+DR_HD void glv_half(const uint32_t* k, uint32_t which, uint32_t* out) {
+    constexpr uint32_t GLV_LAMBDA[4] = DR_GLV_LAMBDA;
+    constexpr uint32_t GLV_MU[5] = DR_GLV_MU;
+    // q = (k * mu) >> 256 (Barrett): never above floor(k / lambda) and at most one below it
+    uint32_t prod[13];
+    for (int i = 0; i < 13; i++) prod[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 5; j++) {
+            uint64_t t = (uint64_t)k[i] * GLV_MU[j] + prod[i + j] + carry;
+            prod[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        prod[i + 5] = (uint32_t)carry;
+    }
+    uint32_t q[5] = {prod[8], prod[9], prod[10], prod[11], prod[12]};  // q <= lambda + 1 < 2^128: q[4] == 0
+    // rem = k - q * lambda, at most 2 * lambda: five limbs are enough
+    uint32_t ql[8];
+    for (int i = 0; i < 8; i++) ql[i] = 0;
+    for (int i = 0; i < 4; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; j++) {
+            uint64_t t = (uint64_t)q[i] * GLV_LAMBDA[j] + ql[i + j] + carry;
+            ql[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        ql[i + 4] = (uint32_t)carry;
+    }
+    uint32_t rem[5];
+    uint64_t borrow = 0;
+    for (int i = 0; i < 5; i++) {
+        uint64_t t = (uint64_t)k[i] - ql[i] - borrow;
+        rem[i] = (uint32_t)t;
+        borrow = (t >> 32) & 1;
+    }
+    // rem >= lambda ?  (rem[4] != 0, or the low four limbs compare >=)
+    bool ge = rem[4] != 0;
+    if (!ge) {
+        ge = true;
+        for (int i = 3; i >= 0; i--) {
+            if (rem[i] != GLV_LAMBDA[i]) {
+                ge = rem[i] > GLV_LAMBDA[i];
+                break;
+            }
+        }
+    }
+    if (ge) {
+        borrow = 0;
+        for (int i = 0; i < 5; i++) {
+            uint64_t t = (uint64_t)rem[i] - (i < 4 ? GLV_LAMBDA[i] : 0u) - borrow;
+            rem[i] = (uint32_t)t;
+            borrow = (t >> 32) & 1;
+        }
+        uint64_t carry = 1;
+        for (int i = 0; i < 5; i++) {
+            uint64_t t = (uint64_t)q[i] + carry;
+            q[i] = (uint32_t)t;
+            carry = t >> 32;
+        }
+    }
+    for (int i = 0; i < 4; i++) out[i] = which ? q[i] : rem[i];
+    for (int i = 4; i < 8; i++) out[i] = 0;
+}
+
 struct TableGeom {
     uint32_t c;        // bits of a (narrow) window
-    uint32_t W;        // windows; W * c + wide >= 256
+    uint32_t W;        // windows; W * c + wide >= 256 (128 with glv)
     uint32_t H;        // entries per (i, w) of a narrow window = 2^(c-1)
     uint32_t n_points; // SRS points covered
     uint32_t wide;     // the `wide` lowest windows take c + 1 bits (2H entries each): one window fewer per scalar for (W + wide) / (W + 1)
                        // of the memory; 0 = uniform windows
+    uint32_t glv;      // the table covers 128 bits and every scalar is split in two halves (2W additions per coefficient)
+    uint32_t top;      // entries of the last window when it has to hold more than its signed range (glv: the halves run up to
+                       // lambda + 1, whose top digit can exceed H); 0 = like any other window
     DR_HD uint32_t width(uint32_t w) const { return c + (w < wide ? 1u : 0u); }
     DR_HD uint32_t bit(uint32_t w) const { return w * c + (w < wide ? w : wide); }
-    DR_HD uint32_t max_entries() const { return wide ? 2 * H : H; }
-    // point i owns (W + wide) * H consecutive entries; window w starts at (w + min(w, wide)) * H
-    DR_HD size_t entry(uint32_t i, uint32_t w, uint32_t d) const { return (((size_t)i * (W + wide) + w + (w < wide ? w : wide)) << (c - 1)) + (d - 1); }
-    size_t total_entries() const { return ((size_t)n_points * (W + wide)) << (c - 1); }
+    DR_HD uint32_t entries(uint32_t w) const { return (top && w + 1 == W) ? top : (w < wide ? 2 * H : H); }
+    DR_HD uint32_t max_entries() const {
+        uint32_t m = wide ? 2 * H : H;
+        return top > m ? top : m;
+    }
+    DR_HD uint32_t additions() const { return glv ? 2 * W : W; }
+    // point i owns per_point() consecutive entries; window w starts at (w + min(w, wide)) * H (the last window may be longer)
+    DR_HD size_t per_point() const { return ((size_t)(W + wide) << (c - 1)) + (top ? top - entries_plain(W - 1) : 0); }
+    DR_HD uint32_t entries_plain(uint32_t w) const { return w < wide ? 2 * H : H; }
+    DR_HD size_t entry(uint32_t i, uint32_t w, uint32_t d) const { return (size_t)i * per_point() + ((size_t)(w + (w < wide ? w : wide)) << (c - 1)) + (d - 1); }
+    size_t total_entries() const { return (size_t)n_points * per_point(); }
 };
-inline TableGeom make_geom(uint32_t c, uint32_t n_points, uint32_t wide = 0) {
+inline TableGeom make_geom(uint32_t c, uint32_t n_points, uint32_t wide = 0, uint32_t glv = 0) {
     TableGeom g;
     g.c = c;
-    g.W = (256 - wide + c - 1) / c;
+    const uint32_t bits = glv ? 128 : 256;
+    g.W = (bits - wide + c - 1) / c;
     g.H = 1u << (c - 1);
     g.n_points = n_points;
     g.wide = wide;
+    g.glv = glv;
+    g.top = 0;
+    if (glv) {
+        constexpr uint32_t GLV_LAMBDA[4] = DR_GLV_LAMBDA;
+        // largest top digit: (lambda + 1) >> bit(W - 1), plus the carry of the window below
+        const uint32_t b = g.bit(g.W - 1);
+        uint64_t hi = ((uint64_t)GLV_LAMBDA[3] << 32) | GLV_LAMBDA[2];  // bits 64..127 of lambda
+        uint64_t top_digit = b >= 64 ? hi >> (b - 64) : ~(uint64_t)0;
+        uint64_t need = top_digit + 2;
+        if (need > g.entries_plain(g.W - 1)) g.top = (uint32_t)need;
+    }
     return g;
 }
 
@@ -65,14 +164,15 @@ struct TableBuildBody {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t gid = ctx.bx * ctx.nthreads + t;
             uint32_t i = gid / chunks, q = gid % chunks;
-            if (i < g.n_points) {
+            const uint32_t max_e = g.max_entries();
+            const uint32_t L = (max_e + chunks - 1) / chunks;
+            const uint32_t d0 = q * L + 1;
+            if (i < g.n_points && d0 <= max_e) {
                 const uint32_t W = g.W;
-                const uint32_t L = g.max_entries() / chunks;
-                const uint32_t d0 = q * L + 1;
-                // digits above H exist only in the `wide` lowest windows; W0 = windows this chunk starts with
-                const uint32_t W0 = d0 > g.H ? g.wide : W;
+                const uint32_t d_end = d0 + L - 1 < max_e ? d0 + L - 1 : max_e;
+                // window w holds digits 1..entries(w): wider windows and a long last window go on after the others stop
                 Fq bx[MAXW], by[MAXW], ex[MAXW], ey[MAXW], den[MAXW], pre[MAXW];
-                // 1. window bases B_w = 2^(c*w) * P_i
+                // 1. window bases B_w = 2^bit(w) * P_i
                 {
                     G1 cur = G1::from_affine(srs[i]);
                     G1 proj[MAXW];
@@ -103,14 +203,15 @@ struct TableBuildBody {
                 // 2. chunk start E_w = d0 * B_w
                 if (d0 == 1) {
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W0; w++) {
+                    for (uint32_t w = 0; w < W; w++) {
                         ex[w] = bx[w];
                         ey[w] = by[w];
                     }
                 } else {
                     G1 proj[MAXW];
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W0; w++) {
+                    for (uint32_t w = 0; w < W; w++) {
+                        if (d0 > g.entries(w)) continue;
                         G1Affine b{bx[w], by[w]};
                         G1 acc = G1::inf();
 #pragma unroll 1
@@ -122,14 +223,16 @@ struct TableBuildBody {
                     }
                     Fq acc = Fq::one();
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W0; w++) {
+                    for (uint32_t w = 0; w < W; w++) {
                         pre[w] = acc;
+                        if (d0 > g.entries(w)) continue;
                         den[w] = proj[w].ZZ * proj[w].ZZZ;
                         acc = acc * den[w];
                     }
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)W0 - 1; w >= 0; w--) {
+                    for (int w = (int)W - 1; w >= 0; w--) {
+                        if (d0 > g.entries((uint32_t)w)) continue;
                         Fq di = inv * pre[w];
                         inv = inv * den[w];
                         ex[w] = proj[w].X * (di * proj[w].ZZZ);
@@ -137,22 +240,24 @@ struct TableBuildBody {
                     }
                 }
 #pragma unroll 1
-                for (uint32_t w = 0; w < W0; w++) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
+                for (uint32_t w = 0; w < W; w++)
+                    if (d0 <= g.entries(w)) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
                 // 3. E_w += B_w, one shared inversion per step
 #pragma unroll 1
-                for (uint32_t d = d0 + 1; d < d0 + L; d++) {
-                    const uint32_t Wd = d > g.H ? g.wide : W;
+                for (uint32_t d = d0 + 1; d <= d_end; d++) {
                     Fq acc = Fq::one();
 #pragma unroll 1
-                    for (uint32_t w = 0; w < Wd; w++) {
+                    for (uint32_t w = 0; w < W; w++) {
                         pre[w] = acc;
+                        if (d > g.entries(w)) continue;
                         // E == B only for d == 2 (then the chord degenerates to the tangent); E == -B never
                         den[w] = (d == 2) ? ey[w].dbl() : bx[w] - ex[w];
                         acc = acc * den[w];
                     }
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)Wd - 1; w >= 0; w--) {
+                    for (int w = (int)W - 1; w >= 0; w--) {
+                        if (d > g.entries((uint32_t)w)) continue;
                         Fq di = inv * pre[w];
                         inv = inv * den[w];
                         Fq num;
@@ -256,13 +361,12 @@ struct G1PrefixSumBody {
 
 // ---- signed-digit recoding -------------------------------------------------------------------------
 // k: canonical little-endian limbs (< 2^255).  Returns digit w in [-(H-1), H]; carry is threaded.
-DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t bit, uint32_t c, uint32_t& carry) {
-    (void)w;
+// `H`: largest digit the window stores (2^(c-1) for a signed window)
+DR_HD int msm_digit(const uint32_t* k, uint32_t bit, uint32_t c, uint32_t H, uint32_t& carry) {
     uint32_t limb = bit >> 5, off = bit & 31;
     uint64_t two = (limb < 8 ? (uint64_t)k[limb] : 0) | ((limb + 1 < 8 ? (uint64_t)k[limb + 1] : 0) << 32);
     uint32_t raw = (uint32_t)(two >> off) & ((1u << c) - 1);
     uint32_t d = raw + carry;
-    uint32_t H = 1u << (c - 1);
     if (d > H) {
         carry = 1;
         return (int)d - (int)(1u << c);
@@ -270,14 +374,15 @@ DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t bit, uint32_t c, uin
     carry = 0;
     return (int)d;
 }
-DR_HD int msm_digit(const uint32_t* k, uint32_t w, const TableGeom& g, uint32_t& carry) { return msm_digit(k, w, g.bit(w), g.width(w), carry); }
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, const TableGeom& g, uint32_t& carry) { return msm_digit(k, g.bit(w), g.width(w), g.entries(w), carry); }
 // uniform windows of c bits
-DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) { return msm_digit(k, w, w * c, c, carry); }
+DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) { return msm_digit(k, w * c, c, 1u << (c - 1), carry); }
 
 // ---- batched commit ----------------------------------------------------------------------------------
 // grid = (slices, batch).  MSM `by` uses scalars[by * scalar_stride + i] (Montgomery Fr), i < n, against
 // SRS points 0..n-1.  Each block accumulates its slice of points and tree-reduces to one XYZZ partial.
-struct CommitBody {
+template <bool GLV>
+struct CommitBodyT {
     DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, const Fr* scalars, size_t scalar_stride, uint32_t n, G1* partials) const {
         G1* sm = (G1*)ctx.smem;
         const uint32_t slices = ctx.gx;
@@ -286,26 +391,40 @@ struct CommitBody {
         const uint32_t hi = (lo + per < n) ? lo + per : n;
         const Fr* sc = scalars + (size_t)ctx.by * scalar_stride;
         DR_THREAD_LOOP(t, ctx) {
-            G1 acc = G1::inf();
+            // with a GLV table: pass 0 sums the entries selected by the k1 halves, pass 1 those of the k2 halves; the endomorphism
+            // is applied once to the second sum (phi is a homomorphism), so each pass is the plain loop over a 128-bit scalar
 #pragma unroll 1
-            for (uint32_t i = lo + t; i < hi; i += ctx.nthreads) {
-                Fr kc = sc[i].from_mont();
-                uint32_t carry = 0;
-                int d_next = msm_digit(kc.v, 0, g, carry);
-                G1Affine pt_next = G1Affine::inf();
-                if (d_next) pt_next = table[g.entry(i, 0, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+            for (uint32_t pass = 0; pass < (GLV ? 2u : 1u); pass++) {
+                G1 acc = G1::inf();
 #pragma unroll 1
-                for (uint32_t w = 0; w < g.W; w++) {
-                    int d = d_next;
-                    G1Affine pt = pt_next;
-                    if (w + 1 < g.W) {
-                        d_next = msm_digit(kc.v, w + 1, g, carry);
-                        if (d_next) pt_next = table[g.entry(i, w + 1, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+                for (uint32_t i = lo + t; i < hi; i += ctx.nthreads) {
+                    Fr kc = sc[i].from_mont();
+                    if (GLV) {
+                        uint32_t half[8];
+                        glv_half(kc.v, pass, half);
+                        for (int l = 0; l < 8; l++) kc.v[l] = half[l];
                     }
-                    if (d) g1_madd(acc, pt, d < 0);
+                    uint32_t carry = 0;
+                    int d_next = msm_digit(kc.v, 0, g, carry);
+                    G1Affine pt_next = G1Affine::inf();
+                    if (d_next) pt_next = table[g.entry(i, 0, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+#pragma unroll 1
+                    for (uint32_t w = 0; w < g.W; w++) {
+                        int d = d_next;
+                        G1Affine pt = pt_next;
+                        if (w + 1 < g.W) {
+                            d_next = msm_digit(kc.v, w + 1, g, carry);
+                            if (d_next) pt_next = table[g.entry(i, w + 1, (uint32_t)(d_next < 0 ? -d_next : d_next))];
+                        }
+                        if (d) g1_madd(acc, pt, d < 0);
+                    }
                 }
+                if (GLV && pass) {
+                    acc.X = acc.X * glv_beta();
+                    g1_add(acc, sm[t]);
+                }
+                sm[t] = acc;
             }
-            sm[t] = acc;
         }
         DR_BLOCK_SYNC();
         for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
@@ -321,6 +440,9 @@ struct CommitBody {
         }
     }
 };
+
+using CommitBody = CommitBodyT<false>;
+using CommitGlvBody = CommitBodyT<true>;
 
 // ---- batched-affine commit --------------------------------------------------------------------------------
 // Same sum as CommitBody, cheaper additions.  Adding two affine points costs 2M + 1S once 1/(x2 - x1) is known, and

@@ -20,13 +20,14 @@ _engines: dict[int, "Engine"] = {}
 
 class Engine:
     def __init__(self, device: int = 0, window_bits: int | None = None, library: _native.Library | None = None, srs_points: int | None = None,
-                 srs: "SrsBytes | None" = None, wide_windows: int = 0):
+                 srs: "SrsBytes | None" = None, wide_windows: int = 0, glv: bool = False):
         self.device = device
         self.ctx = _native.Context(device, library)
         env = os.environ.get("DOT_RING_B200_WINDOW_BITS")
         # None / 0 = let the library size the table from the free HBM (dr_srs_load); wide_windows only with an explicit width
         self.window_bits = int(window_bits) if window_bits is not None else (int(env) if env else 0)
         self.wide_windows = int(wide_windows) if self.window_bits else 0
+        self.glv = bool(glv) if self.window_bits else False
         self._srs: _native.NativeSrs | None = None
         self._srs_points = srs_points
         # `srs` overrides the bundled 6145-point file (needed for domains above 2048, whose quotient has 3N + 1 coefficients)
@@ -36,8 +37,9 @@ class Engine:
     def srs(self) -> _native.NativeSrs:
         """SRS points + window table in HBM, built on first use (about 3.5 s for the 106 GB table a B200 gets by default)."""
         if self._srs is None:
-            self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits, self.wide_windows)
-            self.window_bits, self.wide_windows, self.windows = self._srs.geometry
+            self._srs = _native.NativeSrs(self.ctx, self.srs_bytes.g1_be96, self.srs_bytes.g2_be192, self.window_bits, self.wide_windows, self.glv)
+            self.window_bits, self.wide_windows, glv, self.table_additions = self._srs.geometry
+            self.glv = bool(glv)
         return self._srs
 
     def close(self) -> None:

@@ -63,15 +63,17 @@ int dr_ctx_device_info(dr_ctx* ctx, char* name_buf, size_t name_len, int* sm_cou
  * g1_be96: n_g1 uncompressed points [tau^i]_1; g2_be192: [1]_2 and [tau]_2 (srs.py:57-88 layout).
  * window_bits selects the fixed-base table: bits 0..7 = c, the window width (2..15; c + 1 <= 16); bits 8..15 = k, how many of the low windows
  * take c + 1 bits instead (0 = uniform).  W = ceil((256 - k) / c) table additions per coefficient, table bytes =
- * n_g1 * (W + k) * 2^(c-1) * 96.  0 = auto: the cheapest table that leaves max(24 GB, a quarter of its size) of the free device
+ * n_g1 * (W + k) * 2^(c-1) * 96.  Bit 16 = GLV: every scalar is split as k1 + k2 * lambda (128-bit halves, lambda the eigenvalue of
+ * the G1 endomorphism), the table covers 128 bits (W = ceil((128 - k) / c), c up to 16, a slightly longer last window) and a
+ * coefficient costs 2W additions: c = 16 gives 16 additions in 161 GB for 6145 points.  0 = auto: the cheapest table that leaves max(24 GB, a quarter of its size) of the free device
  * memory: on a 180 GB B200 c = 14, k = 4 (18 additions, 106 GB for the bundled 6145-point SRS; uniform 14 bits = 19 additions, 92 GB).
  */
 int dr_srs_load(dr_ctx* ctx, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g2_be192, int window_bits, dr_srs** out);
 void dr_srs_destroy(dr_srs* srs);
 size_t dr_srs_size(const dr_srs* srs);
 size_t dr_srs_table_bytes(const dr_srs* srs);
-/* The table geometry in use: window width c, number of (c + 1)-bit windows, windows (= table additions) per coefficient. */
-void dr_srs_geometry(const dr_srs* srs, uint32_t* window_bits, uint32_t* wide_windows, uint32_t* windows);
+/* The table geometry in use: window width c, number of (c + 1)-bit windows, GLV split (0 / 1), table additions per coefficient. */
+void dr_srs_geometry(const dr_srs* srs, uint32_t* window_bits, uint32_t* wide_windows, uint32_t* glv, uint32_t* additions);
 /* `batch` polynomials of n coefficients each (coefficient j of polynomial b at coeffs_le32 + 32*(b*n+j));
  * values >= r are reduced (kzg.py passes unreduced quotient coefficients, ops.py:215-220); all-zero ->
  * infinity (kzg.py:167-168).  Output: batch x 96-byte uncompressed commitments. */

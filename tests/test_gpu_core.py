@@ -67,7 +67,7 @@ def test_mixed_window_geometries_commit_like_the_oracle(ctx):
     """dr_srs_load geometries with some windows one bit wider (the bench default is 14 bits with four 15-bit windows)."""
     from tests import window_cases
 
-    window_cases.check_commit_geometries(ctx, [(8, 8), (10, 6), (13, 9), (14, 4)], n=40)
+    window_cases.check_commit_geometries(ctx, [(8, 8), (10, 6), (13, 9), (14, 4), (8, 0, True), (13, 2, True), (16, 0, True)], n=40)
     ctx.set_commit_mode(1)  # batched-affine rounds read the same table
     try:
         window_cases.check_commit_geometries(ctx, [(8, 8)], n=700, seed=6)

@@ -59,6 +59,33 @@ def test_ring8_blinded_rows_match_reference(srs):
     ring.close()
 
 
+def test_glv_table_gives_the_reference_root_and_proofs(ctx):
+    """Same vectors through a table that covers 128 bits with the scalars split by the G1 endomorphism (the bench default)."""
+    from dot_ring_b200 import _native
+    from dot_ring_b200.srs import read_srs_file
+
+    raw = read_srs_file(None, None)
+    glv_srs = _native.NativeSrs(ctx, raw.g1_be96, raw.g2_be192, 12, 0, True)
+    try:
+        assert glv_srs.geometry == (12, 0, 1, 22)
+        g = load("ring8_reference.json")
+        for i, v in enumerate(load("bandersnatch_sha-512_ell2_ring.json")):
+            keys = split_keys(hx(v, "ring_pks"))
+            ring = native_ring(glv_srs, keys, rp.Params(test_vectors=True))
+            assert ring.root().hex() == v["ring_pks_com"]
+            k = rp.Ring(keys, rp.Params(test_vectors=True)).index_of(hx(v, "pk"))
+            proofs, status = ring.prove_batch([hx(v, "alpha")], [hx(v, "ad")], [hx(v, "sk")], [k])
+            assert status == [0] and proofs[0] == ring_proof_bytes(v)
+            ring.close()
+            if i == 0:
+                ring = native_ring(glv_srs, keys, rp.Params())
+                proofs, status = ring.prove_batch([hx(v, "alpha")], [hx(v, "ad")], [hx(v, "sk")], [k], zk_rows=g["zk_rows"])
+                assert status == [0] and proofs[0].hex() == g["proof"]
+                ring.close()
+    finally:
+        glv_srs.close()
+
+
 def test_ring1023_root_and_proofs_match_reference(srs):
     g = load("ring1023_reference.json")
     pk, sk, keys = bench_ring_keys(1023)

@@ -13,8 +13,8 @@ from oracle import fr
 from oracle import ring_proof as rp
 
 
-def expected_windows(c: int, wide: int) -> int:
-    return -(-(256 - wide) // c)
+def expected_windows(c: int, wide: int, glv: bool = False) -> int:
+    return -(-((128 if glv else 256) - wide) // c)
 
 
 def check_commit_geometries(ctx, geometries, n: int, seed: int = 5) -> None:
@@ -24,14 +24,19 @@ def check_commit_geometries(ctx, geometries, n: int, seed: int = 5) -> None:
     rng = random.Random(seed)
     vecs = [[rng.randrange(fr.R) for _ in range(n)] for _ in range(2)]
     # all-ones digits (carry chains through every window), the largest scalar, single high bits, small values
+    lam = 0xAC45A4010001A40200000000FFFFFFFF  # GLV eigenvalue: halves at the edges of their range
+    vecs += [[(lam * lam + lam - i) % fr.R for i in range(n)], [lam - 1 + i for i in range(n)], [(lam + 1) * lam - 1 + i for i in range(n)]]
     vecs += [[fr.R - 1] * n, [(1 << 254) + i for i in range(n)], [(1 << 255) - 1 - i for i in range(n)], [1 << (7 * i % 255) for i in range(n)],
              [rng.randrange(3) for _ in range(n)], [0] * n]  # fmt: skip
     want = [bls.g1_serialize(rp.kzg_commit(sub, [x % fr.R for x in v])) for v in vecs]
-    for c, wide in geometries:
-        native = _native.NativeSrs(ctx, raw.g1_be96, raw.g2_be192, c, wide)
+    for geom in geometries:
+        c, wide, glv = geom if len(geom) == 3 else (*geom, False)
+        native = _native.NativeSrs(ctx, raw.g1_be96, raw.g2_be192, c, wide, glv)
         try:
-            assert native.geometry == (c, wide, expected_windows(c, wide))
-            assert native.table_bytes == n * (expected_windows(c, wide) + wide) * (1 << (c - 1)) * 96
-            assert native.commit(vecs) == want, (c, wide)
+            windows = expected_windows(c, wide, glv)
+            assert native.geometry == (c, wide, int(glv), windows * (2 if glv else 1))
+            if not glv:
+                assert native.table_bytes == n * (windows + wide) * (1 << (c - 1)) * 96
+            assert native.commit(vecs) == want, geom
         finally:
             native.close()
