@@ -164,7 +164,10 @@ inline void* dev_alloc(size_t bytes) {
         dev_cache_trim();
         e = cudaMalloc(&p, size);
     }
-    if (e != cudaSuccess) throw Error(DR_ENOMEM, std::string("cudaMalloc(") + std::to_string(size) + "): " + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // the failed allocation must not surface again at the next launch check
+        throw Error(DR_ENOMEM, std::string("cudaMalloc(") + std::to_string(size) + "): " + cudaGetErrorString(e));
+    }
     std::lock_guard<std::mutex> lock(c.m);
     c.live[p] = {dev, size};
     return p;
