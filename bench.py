@@ -319,7 +319,7 @@ def run_ours(args) -> None:
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {
-            "kernel": "kernel_entry_lb<CommitBody> (fixed-base KZG commit) + WitnessCommitBody (sparse witness commitments)",
+            "kernel": "kernel_entry_lb<CommitBodyT> (fixed-base KZG commit) + WitnessCommitBody (sparse witness commitments)",
             "bound": "imad (int32 multiply-add pipe; neither hbm nor tensor: the path is 381-bit modular arithmetic)",
             "achieved": achieved / 1e12,
             "peak": imad_peak / 1e12,
@@ -329,11 +329,13 @@ def run_ours(args) -> None:
             "executed_frac": executed / imad_peak,
             "executed_note": f"{madds_per_proof} mixed G1 additions per proof actually issued (fixed-base tables + sparse witness columns) x 6000 IMAD; 'achieved' counts the canonical Pippenger work of all 7 MSMs",
             "peak_source": "measured live: dependent-free mad.lo.u32 on all SMs (dr_microbench); IMAD.WIDE measured " + f"{imad_wide_peak / 1e12:.2f} T/s",
-            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, 18 additions per coefficient;
-            # profiles/r01_ncu_full_CommitBody_w18.csv) against 10.9 GB of table entries it must touch: a 96-byte entry at a random
-            # address straddles 64-byte DRAM atoms (2 or 3 of them), and the kernel is bound by the integer pipe, not by these reads
-            "traffic": 23.0e9,
-            "traffic_launch": "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9",
+            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, GLV table, 16 additions per
+            # coefficient; profiles/r01_ncu_full_CommitBody_glv16.csv) against 9.7 GB of table entries it must touch: a 96-byte entry at
+            # a random address straddles 64-byte DRAM atoms (2 or 3 of them), and the kernel is bound by the integer pipe, not by these
+            # reads.  (106 GB table: 23.0e9 for 10.9e9 algorithmic, r01_ncu_full_CommitBody_w18.csv.)
+            "traffic": 22.0e9 if glv else 23.0e9,
+            "traffic_launch": ("CommitBodyT<true> grid (2, 1024) x 128 threads, 40.3 ms under ncu; algorithmic table bytes of that launch 9.7e9" if glv else
+                               "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9"),
             "algorithmic_table_bytes": table_traffic,
             "hbm_gbs_for_table_reads": table_traffic / (commit_ms * 1e-3) / 1e9,
             "kernel_share_of_step": commit_ms / sum(phases),
