@@ -35,9 +35,11 @@ RING_SIZE = 1023
 SIGNER_INDEX = 3
 MSM_SIZES = (2048, 2048, 2048, 2048, 6145, 6144, 2047)  # per proof at N = 2048
 DENSE_MSM_SIZES = (6145, 6144, 2047)  # quotient + two openings: dense coefficient vectors
-# witness columns are committed from their evaluation form: ~131.5 non-zero steps for acc_x / acc_y (26 table additions each,
-# 10-bit windows), ~135 unit steps for b, 1 for acc_ip, plus 3 blinding rows per column
-SPARSE_WITNESS_MADDS = int(2 * 131.5 * 26 + 135 + 3 * 26 + 1 + 4 * 26)
+def sparse_witness_madds(table_bits: int) -> int:
+    """Witness columns are committed from their evaluation form: ~131.5 non-zero steps for acc_x / acc_y (one table addition per
+    window each), ~135 unit steps for b, 1 for acc_ip, plus 3 blinding rows per column."""
+    w = -(-256 // max(table_bits, 1))
+    return int(2 * 131.5 * w + 135 + 3 * w + 1 + 4 * w)
 
 
 def seed_bytes(*parts) -> bytes:
@@ -283,7 +285,7 @@ def run_ours(args) -> None:
     commit_ms = phases[2]
     achieved = CANONICAL_IMAD_PER_PROOF * batch * args.steps / (commit_ms * 1e-3)
     window_bits, wide_windows, glv, windows = eng.srs.geometry
-    madds_per_proof = sum(DENSE_MSM_SIZES) * windows + SPARSE_WITNESS_MADDS
+    madds_per_proof = sum(DENSE_MSM_SIZES) * windows + sparse_witness_madds(ring.native.witness_table_bits() or 10)
     executed = madds_per_proof * 10 * 600 * batch * args.steps / (commit_ms * 1e-3)  # 8M + 2S per mixed addition, 600 IMAD per Fq mul
     table_traffic = madds_per_proof * 96 * batch * args.steps  # algorithmic table bytes read
 

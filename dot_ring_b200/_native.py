@@ -94,6 +94,8 @@ class Library:
         L.dr_ring_points.argtypes = [c_void_p, c_void_p, c_size_t]
         L.dr_ring_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 10
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
+        L.dr_ring_witness_table_bits.argtypes = [c_void_p]
+        L.dr_ring_witness_table_bits.restype = c_uint32
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
         L.dr_ctx_set_dense_witness_commit.argtypes = [c_void_p, c_int]
         L.dr_ctx_set_commit_mode.argtypes = [c_void_p, c_int]
@@ -660,6 +662,9 @@ class NativeRing:
             )
         )
         return list(out.raw[:n]), bool(all_ok.value)
+
+    def witness_table_bits(self) -> int:
+        return int(self.ctx.library.lib.dr_ring_witness_table_bits(self.handle))
 
     def prove_phase_ms(self) -> list[float]:
         arr = (c_float * 6)()

@@ -421,6 +421,11 @@ int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
     DR_API_END
 }
 
+uint32_t dr_ring_witness_table_bits(const dr_ring* r) {
+    const Ring* ring = (const Ring*)r;
+    return ring && ring->lag ? ring->lag->geom.c : 0;
+}
+
 int dr_ctx_set_generic_ntt_path(dr_ctx* c, int enabled) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
