@@ -132,7 +132,8 @@ void build_window_table(Ctx* ctx, const G1Affine* points, const TableGeom& geom,
     if (geom.W > 64) throw Error(DR_EINVAL, "window_bits too small");
     table.alloc(geom.total_entries());
     uint32_t chunks = geom.max_entries() >= 512 ? (geom.max_entries() + 255) / 256 : 1;  // <= 256 serial additions per thread
-    size_t nthreads = (size_t)geom.n_points * chunks;
+    const uint32_t maxw = geom.W <= 32 ? 32 : 64, runs = maxw / geom.W;  // TableBuildBody: runs of 256 digits per thread
+    size_t nthreads = (size_t)geom.n_points * ((chunks + runs - 1) / runs);
     const uint32_t tb = 64;
     Dim3 grid((uint32_t)((nthreads + tb - 1) / tb));
     if (geom.W <= 32)

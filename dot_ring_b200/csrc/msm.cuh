@@ -156,21 +156,22 @@ struct SrsLoadBody {
 };
 
 // ---- table construction -------------------------------------------------------------------------
-// Thread (i, q): SRS point i, digit range d in [q*L + 1, (q+1)*L], all W windows in lockstep so that
-// each step's W affine additions share one field inversion (Montgomery's trick).
+// A thread builds, for one SRS point, R = MAXW / W runs of L consecutive digits in every window: R * W chains E <- E + B_w that
+// advance in lockstep, so that each step's affine additions share one field inversion (Montgomery's trick).  Window w holds the
+// digits 1..entries(w); chains whose digit has passed that bound simply drop out of the batch.
 template <int MAXW>
 struct TableBuildBody {
     DR_HD void operator()(const BlockCtx& ctx, const G1Affine* srs, G1Affine* table, TableGeom g, uint32_t chunks) const {
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t gid = ctx.bx * ctx.nthreads + t;
-            uint32_t i = gid / chunks, q = gid % chunks;
+            const uint32_t W = g.W;
+            const uint32_t R = (uint32_t)MAXW / W ? (uint32_t)MAXW / W : 1;  // runs per thread
+            const uint32_t groups = (chunks + R - 1) / R;
+            const uint32_t gid = ctx.bx * ctx.nthreads + t;
+            const uint32_t i = gid / groups, q0 = (gid % groups) * R;
             const uint32_t max_e = g.max_entries();
             const uint32_t L = (max_e + chunks - 1) / chunks;
-            const uint32_t d0 = q * L + 1;
-            if (i < g.n_points && d0 <= max_e) {
-                const uint32_t W = g.W;
-                const uint32_t d_end = d0 + L - 1 < max_e ? d0 + L - 1 : max_e;
-                // window w holds digits 1..entries(w): wider windows and a long last window go on after the others stop
+            if (i < g.n_points && q0 * L + 1 <= max_e) {
+                const uint32_t lanes = R * W;  // lane l = r * W + w: run r of window w, first digit (q0 + r) * L + 1
                 Fq bx[MAXW], by[MAXW], ex[MAXW], ey[MAXW], den[MAXW], pre[MAXW];
                 // 1. window bases B_w = 2^bit(w) * P_i
                 {
@@ -200,17 +201,12 @@ struct TableBuildBody {
                         by[w] = proj[w].Y * (di * proj[w].ZZ);
                     }
                 }
-                // 2. chunk start E_w = d0 * B_w
-                if (d0 == 1) {
-#pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
-                        ex[w] = bx[w];
-                        ey[w] = by[w];
-                    }
-                } else {
+                // 2. run starts E_l = d0(l) * B_w
+                {
                     G1 proj[MAXW];
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
+                    for (uint32_t l = 0; l < lanes; l++) {
+                        const uint32_t w = l % W, d0 = (q0 + l / W) * L + 1;
                         if (d0 > g.entries(w)) continue;
                         G1Affine b{bx[w], by[w]};
                         G1 acc = G1::inf();
@@ -219,59 +215,63 @@ struct TableBuildBody {
                             acc = g1_dbl(acc);
                             if ((d0 >> bit) & 1) g1_madd(acc, b);
                         }
-                        proj[w] = acc;
+                        proj[l] = acc;
                     }
                     Fq acc = Fq::one();
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
-                        pre[w] = acc;
-                        if (d0 > g.entries(w)) continue;
-                        den[w] = proj[w].ZZ * proj[w].ZZZ;
-                        acc = acc * den[w];
+                    for (uint32_t l = 0; l < lanes; l++) {
+                        pre[l] = acc;
+                        if ((q0 + l / W) * L + 1 > g.entries(l % W)) continue;
+                        den[l] = proj[l].ZZ * proj[l].ZZZ;
+                        acc = acc * den[l];
                     }
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)W - 1; w >= 0; w--) {
-                        if (d0 > g.entries((uint32_t)w)) continue;
-                        Fq di = inv * pre[w];
-                        inv = inv * den[w];
-                        ex[w] = proj[w].X * (di * proj[w].ZZZ);
-                        ey[w] = proj[w].Y * (di * proj[w].ZZ);
+                    for (int l = (int)lanes - 1; l >= 0; l--) {
+                        const uint32_t w = (uint32_t)l % W, d0 = (q0 + (uint32_t)l / W) * L + 1;
+                        if (d0 > g.entries(w)) continue;
+                        Fq di = inv * pre[l];
+                        inv = inv * den[l];
+                        ex[l] = proj[l].X * (di * proj[l].ZZZ);
+                        ey[l] = proj[l].Y * (di * proj[l].ZZ);
+                        table[g.entry(i, w, d0)] = G1Affine{ex[l], ey[l]};
                     }
                 }
+                // 3. E_l += B_w, one shared inversion per step
 #pragma unroll 1
-                for (uint32_t w = 0; w < W; w++)
-                    if (d0 <= g.entries(w)) table[g.entry(i, w, d0)] = G1Affine{ex[w], ey[w]};
-                // 3. E_w += B_w, one shared inversion per step
-#pragma unroll 1
-                for (uint32_t d = d0 + 1; d <= d_end; d++) {
+                for (uint32_t o = 1; o < L; o++) {
                     Fq acc = Fq::one();
+                    uint32_t active = 0;
 #pragma unroll 1
-                    for (uint32_t w = 0; w < W; w++) {
-                        pre[w] = acc;
+                    for (uint32_t l = 0; l < lanes; l++) {
+                        pre[l] = acc;
+                        const uint32_t w = l % W, d = (q0 + l / W) * L + 1 + o;
                         if (d > g.entries(w)) continue;
                         // E == B only for d == 2 (then the chord degenerates to the tangent); E == -B never
-                        den[w] = (d == 2) ? ey[w].dbl() : bx[w] - ex[w];
-                        acc = acc * den[w];
+                        den[l] = (d == 2) ? ey[l].dbl() : bx[w] - ex[l];
+                        acc = acc * den[l];
+                        active++;
                     }
+                    if (!active) break;
                     Fq inv = acc.inv();
 #pragma unroll 1
-                    for (int w = (int)W - 1; w >= 0; w--) {
-                        if (d > g.entries((uint32_t)w)) continue;
-                        Fq di = inv * pre[w];
-                        inv = inv * den[w];
+                    for (int l = (int)lanes - 1; l >= 0; l--) {
+                        const uint32_t w = (uint32_t)l % W, d = (q0 + (uint32_t)l / W) * L + 1 + o;
+                        if (d > g.entries(w)) continue;
+                        Fq di = inv * pre[l];
+                        inv = inv * den[l];
                         Fq num;
                         if (d == 2) {
-                            Fq xx = ex[w].sqr();
+                            Fq xx = ex[l].sqr();
                             num = xx.dbl() + xx;
                         } else {
-                            num = by[w] - ey[w];
+                            num = by[w] - ey[l];
                         }
                         Fq lam = num * di;
-                        Fq x3 = lam.sqr() - ex[w] - bx[w];
-                        Fq y3 = lam * (ex[w] - x3) - ey[w];
-                        ex[w] = x3;
-                        ey[w] = y3;
+                        Fq x3 = lam.sqr() - ex[l] - bx[w];
+                        Fq y3 = lam * (ex[l] - x3) - ey[l];
+                        ex[l] = x3;
+                        ey[l] = y3;
                         table[g.entry(i, w, d)] = G1Affine{x3, y3};
                     }
                 }

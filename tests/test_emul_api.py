@@ -218,4 +218,4 @@ def test_pedersen_blinding_factor_and_unblinding(api):
 def test_mixed_window_geometries_commit_like_the_oracle(api):
     from tests import window_cases
 
-    window_cases.check_commit_geometries(engine_mod.default_engine().ctx, [(4, 4), (5, 1), (7, 4), (4, 0, True), (6, 2, True), (7, 0, True)], n=5)
+    window_cases.check_commit_geometries(engine_mod.default_engine().ctx, [(4, 4), (5, 1), (7, 4), (4, 0, True), (6, 2, True), (7, 0, True), (11, 0, True)], n=5)
