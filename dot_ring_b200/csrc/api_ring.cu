@@ -359,7 +359,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         } else {
             if (!ring->lag) ring->lag = &ring->srs->lagrange_table(N, rg.logN, rg.omega, rg.tw_inv, rg.n_inv);
             ctx->partials.ensure((size_t)4 * m);
-            launch(ctx->stream, Dim3(4, m), 64, witness_commit_smem(ring->lag->geom.W, 64), WitnessCommitBody(), (const G1Affine*)ring->lag->table.p, ring->lag->geom, rg, (const ProofState*)sc.st.p,
+            launch_lb<64, 8>(ctx->stream, Dim3(4, m), 64, witness_commit_smem(ring->lag->geom.W, 64), WitnessCommitBody(), (const G1Affine*)ring->lag->table.p, ring->lag->geom, rg, (const ProofState*)sc.st.p,
                    ctx->partials.p);
             launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, 1u, 4 * m, sc.res.p);
         }

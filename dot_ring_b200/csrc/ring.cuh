@@ -469,12 +469,34 @@ struct WitnessCommitBody {
         const uint32_t total = (*nsteps < WC_MAX_STEPS ? *nsteps : WC_MAX_STEPS) * g.W;
         DR_THREAD_LOOP(t, ctx) {
             G1 acc = G1::inf();
+            // the entry of the next (step, window) pair is fetched before the current addition is issued
+            int dg = 0;
+            bool neg = false;
+            G1Affine pt = G1Affine::inf();
+            if (t < total) {
+                const int16_t* s = steps + (size_t)(t / g.W) * stride;
+                const uint32_t w = t % g.W;
+                dg = s[2 + w];
+                neg = (dg < 0) != (s[1] != 0);
+                if (dg) pt = table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg < 0 ? -dg : dg))];
+            }
 #pragma unroll 1
             for (uint32_t it = t; it < total; it += ctx.nthreads) {
-                const int16_t* s = steps + (size_t)(it / g.W) * stride;
-                uint32_t w = it % g.W;
-                int dg = s[2 + w];
-                if (dg) g1_madd(acc, table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg < 0 ? -dg : dg))], (dg < 0) != (s[1] != 0));
+                const uint32_t nx = it + ctx.nthreads;
+                int dg_next = 0;
+                bool neg_next = false;
+                G1Affine pt_next = pt;
+                if (nx < total) {
+                    const int16_t* s = steps + (size_t)(nx / g.W) * stride;
+                    const uint32_t w = nx % g.W;
+                    dg_next = s[2 + w];
+                    neg_next = (dg_next < 0) != (s[1] != 0);
+                    if (dg_next) pt_next = table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg_next < 0 ? -dg_next : dg_next))];
+                }
+                if (dg) g1_madd(acc, pt, neg);
+                dg = dg_next;
+                neg = neg_next;
+                pt = pt_next;
             }
             sm[t] = acc;
         }
