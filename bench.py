@@ -217,6 +217,8 @@ def run_ours(args) -> None:
     else:
         raise SystemExit("bench.py: no window table fits on this device")
     eng.ctx.set_commit_mode(args.commit_mode)
+    if args.prove_chunk:
+        eng.ctx.set_prove_chunk(args.prove_chunk)
     eng.ctx.sync()
     table_s = time.perf_counter() - t0
     info = eng.ctx.device_info()
@@ -314,7 +316,7 @@ def run_ours(args) -> None:
             "glv_split": bool(glv),
             "table_additions_per_coefficient": windows,
             "table_gb": round(eng.srs.table_bytes / 1e9, 2),
-            "l2": "per-step working set (window table + ~8 GB scratch) is far larger than the 126 MB L2; no flush needed",
+            "l2": "per-step working set (window table + 2.3 MB of scratch per proof) is far larger than the 126 MB L2; no flush needed",
             "parity": "ring root sha256 " + hashlib.sha256(root_bytes).hexdigest()[:16],
         },
         "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": batch * (12 * 32 + 32 + 4 * 5 + 25 + 22), "d2h_bytes_per_step": batch * (784 + 4), "ms_per_step": mx[1] * 1e3 / args.steps},
@@ -460,12 +462,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=8192, help="proofs per GPU per step (one device pass: 19 GB of scratch at ring 1023)")
     ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "16")),
                     help="fixed-base table window width; 0 = sized by the library. Default: 16-bit windows over GLV halves (16 additions per coefficient, 161 GB); "
                     "if that does not fit the run falls back to 14-bit windows with four 15-bit ones (18 additions, 106 GB)")
     ap.add_argument("--wide-windows", type=int, default=None, help="how many low windows take one more bit (default 4 with 14-bit windows)")
     ap.add_argument("--glv", type=int, default=None, help="1: table over 128 bits, scalars split with the G1 endomorphism (2 x windows additions per coefficient)")
+    ap.add_argument("--prove-chunk", type=int, default=int(os.environ.get("DOT_RING_B200_PROVE_CHUNK", "0")), help="proofs per device pass (0: the library's choice, at most 4096)")
     ap.add_argument("--commit-mode", type=int, default=int(os.environ.get("DOT_RING_B200_COMMIT_MODE", "0")), help="0 XYZZ accumulation, 1 batched-affine rounds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-workers", type=int, default=0)

@@ -296,7 +296,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
 
     // proofs per pass: the one-thread-per-proof kernels (Pedersen part, witness chain, transcripts) are latency-bound, so
     // a pass should be as wide as the scratch (35 N field elements + state per proof) allows
-    size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 4096;
+    size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 8192;
 #if !defined(DR_HOST_EMULATION)
     if (!ctx->prove_chunk) {
         size_t free_b = 0, total_b = 0;
@@ -311,8 +311,12 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
     }
 #endif
+    // equal passes: n proofs in ceil(n / cap) passes of the same width (a short last pass would pay the latency-bound kernels again
+    // for little work)
+    const size_t passes = (n + chunk_cap - 1) / chunk_cap;
+    const size_t pass_width = (n + passes - 1) / passes;
     ProveScratch& sc = scratch_for(ctx);
-    sc.ensure(n < chunk_cap ? n : chunk_cap, N);
+    sc.ensure(pass_width, N);
     PhaseTimer& pt = ctx->phases;
     pt.reset();
     const uint32_t nthr = ntt_threads(N);
@@ -321,8 +325,8 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     const NttPlan* big_plan = large ? &ctx->plan(N, rg.omega) : nullptr;
     std::vector<ProveInput> hin;
 
-    for (size_t base = 0; base < n; base += sc.cap) {
-        const uint32_t m = (uint32_t)((n - base < sc.cap) ? n - base : sc.cap);
+    for (size_t base = 0; base < n; base += pass_width) {
+        const uint32_t m = (uint32_t)((n - base < pass_width) ? n - base : pass_width);
         hin.assign(m, ProveInput{});
         for (uint32_t i = 0; i < m; i++) {
             ProveInput& pi = hin[i];
