@@ -1,4 +1,7 @@
 // C ABI, part 3: ring set-up (key ingestion, fixed columns, ring root) and batched Ring VRF proving.
+#include <cstdio>
+#include <cstdlib>
+
 #include "api_internal.cuh"
 #include "ring.cuh"
 
@@ -305,9 +308,12 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         ProveScratch& cur = scratch_for(ctx);
         size_t per_proof = (35 + (N > 4096 ? 16 : 0)) * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
         size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
-        // keep 3 GB (or half of what is left, if less) for the other buffers of this and later calls
-        const size_t keep = have / 2 < ((size_t)3 << 30) ? have / 2 : ((size_t)3 << 30);
+        // keep 1 GB (or half of what is left, if less) for the other buffers of this and later calls
+        const size_t keep = have / 2 < ((size_t)1 << 30) ? have / 2 : ((size_t)1 << 30);
         size_t fit = (have - keep) / per_proof;
+        if (getenv("DOT_RING_B200_DEBUG"))
+            fprintf(stderr, "[dot_ring_b200] prove: free %.2f GB (+%.2f GB held), %.2f MB per proof -> up to %zu proofs per pass\n", free_b / 1e9,
+                    (double)(have - free_b) / 1e9, per_proof / 1e6, fit);
         if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
     }
 #endif
