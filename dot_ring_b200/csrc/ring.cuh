@@ -429,70 +429,93 @@ struct WitnessInttBody {
 // window digits, into shared memory; (2) the (step, window) pairs are dealt round-robin to the threads, so every lane
 // issues the same number of table additions however the steps are distributed over the rows.
 constexpr uint32_t WC_MAX_STEPS = 272;  // <= 1 (row k) + 253 (bit rows) + 3 blinding rows + slack, per column
-// shared memory: [steps: WC_MAX_STEPS x (row, flip, W digits) as int16] [counter] [per-thread partial sums]
-DR_HD size_t witness_commit_steps_bytes(uint32_t W) { return (((size_t)WC_MAX_STEPS * (2 + W) * sizeof(int16_t) + 16 + 15) / 16) * 16; }
+// shared memory: [steps: WC_MAX_STEPS x (row, flip, W digits) as int16] [rows found: WC_MAX_STEPS x int16]
+// [unit steps: WC_MAX_STEPS x (row, negate) as int16] [3 counters] [per-thread partial sums]
+DR_HD size_t witness_commit_steps_bytes(uint32_t W) { return (((size_t)WC_MAX_STEPS * (2 + W + 1 + 2) * sizeof(int16_t) + 16 + 15) / 16) * 16; }
 DR_HD size_t witness_commit_smem(uint32_t W, uint32_t threads) { return witness_commit_steps_bytes(W) + threads * sizeof(G1); }
 struct WitnessCommitBody {
     DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, RingDev rg, const ProofState* st, G1* out) const {
         int16_t* steps = (int16_t*)ctx.smem;
         const uint32_t stride = 2 + g.W;
-        uint32_t* nsteps = (uint32_t*)(ctx.smem + (size_t)WC_MAX_STEPS * stride * sizeof(int16_t));
+        int16_t* rows = steps + (size_t)WC_MAX_STEPS * stride;
+        int16_t* units = rows + WC_MAX_STEPS;
+        uint32_t* counters = (uint32_t*)(units + 2 * WC_MAX_STEPS);  // rows found, full steps, unit steps
         G1* sm = (G1*)(ctx.smem + witness_commit_steps_bytes(g.W));
         const ProofState& ps = st[ctx.by];
         const uint32_t col = ctx.bx, N = rg.N;
         DR_THREAD_LOOP(t, ctx) {
-            if (t == 0) *nsteps = 0;
+            if (t < 3) counters[t] = 0;
         }
         DR_BLOCK_SYNC();
+        // 1a. find the rows where the column steps (cheap, every lane busy)
         DR_THREAD_LOOP(t, ctx) {
 #pragma unroll 1
             for (uint32_t j = 1 + t; j <= N; j += ctx.nthreads) {
                 Fr d = witness_eval(rg, ps, col, j - 1);
                 if (j < N) d = d - witness_eval(rg, ps, col, j);
                 if (d.is_zero()) continue;
-                // steps of +-1 (b, acc_ip) cost one table entry: use whichever of d, -d is the shorter integer
-                Fr kc = d.from_mont(), nk = d.neg().from_mont();
-                bool flip = (nk.v[1] | nk.v[2] | nk.v[3] | nk.v[4] | nk.v[5] | nk.v[6] | nk.v[7]) == 0;
-                if (flip) kc = nk;
-                uint32_t slot = atomic_add_u32(nsteps, 1u);
-                if (slot < WC_MAX_STEPS) {
-                    int16_t* s = steps + (size_t)slot * stride;
-                    s[0] = (int16_t)j;  // base S_j is table point j - 1 (N <= 4096)
-                    s[1] = flip ? 1 : 0;
-                    uint32_t carry = 0;
-#pragma unroll 1
-                    for (uint32_t w = 0; w < g.W; w++) s[2 + w] = (int16_t)msm_digit(kc.v, w, g, carry);
-                }
+                uint32_t slot = atomic_add_u32(&counters[0], 1u);
+                if (slot < WC_MAX_STEPS) rows[slot] = (int16_t)j;  // base S_j is table point j - 1 (N <= 4096)
             }
         }
         DR_BLOCK_SYNC();
-        const uint32_t total = (*nsteps < WC_MAX_STEPS ? *nsteps : WC_MAX_STEPS) * g.W;
+        // 1b. one step per lane.  Steps of +-1 (the b column, acc_ip) are one table entry each and go to their own list, so
+        // that phase 2 does not walk W windows of zero digits for them; the others get their W signed digits.
+        const uint32_t found = counters[0] < WC_MAX_STEPS ? counters[0] : WC_MAX_STEPS;
+        DR_THREAD_LOOP(t, ctx) {
+#pragma unroll 1
+            for (uint32_t slot = t; slot < found; slot += ctx.nthreads) {
+                const uint32_t j = (uint32_t)(uint16_t)rows[slot];
+                Fr d = witness_eval(rg, ps, col, j - 1);
+                if (j < N) d = d - witness_eval(rg, ps, col, j);
+                Fr kc = d.from_mont(), nk = d.neg().from_mont();
+                bool flip = (nk.v[1] | nk.v[2] | nk.v[3] | nk.v[4] | nk.v[5] | nk.v[6] | nk.v[7]) == 0;  // use the shorter of d, -d
+                if (flip) kc = nk;
+                if (kc.v[0] == 1 && (kc.v[1] | kc.v[2] | kc.v[3] | kc.v[4] | kc.v[5] | kc.v[6] | kc.v[7]) == 0) {
+                    uint32_t u = atomic_add_u32(&counters[2], 1u);
+                    units[2 * u] = (int16_t)j;
+                    units[2 * u + 1] = flip ? 1 : 0;
+                    continue;
+                }
+                int16_t* s = steps + (size_t)atomic_add_u32(&counters[1], 1u) * stride;
+                s[0] = (int16_t)j;
+                s[1] = flip ? 1 : 0;
+                uint32_t carry = 0;
+#pragma unroll 1
+                for (uint32_t w = 0; w < g.W; w++) s[2 + w] = (int16_t)msm_digit(kc.v, w, g, carry);
+            }
+        }
+        DR_BLOCK_SYNC();
+        // 2. (step, window) pairs and unit steps dealt round-robin to the lanes
+        const uint32_t full = counters[1] * g.W, total = full + counters[2];
         DR_THREAD_LOOP(t, ctx) {
             G1 acc = G1::inf();
-            // the entry of the next (step, window) pair is fetched before the current addition is issued
+            // the entry of the next pair is fetched before the current addition is issued
             int dg = 0;
             bool neg = false;
             G1Affine pt = G1Affine::inf();
-            if (t < total) {
-                const int16_t* s = steps + (size_t)(t / g.W) * stride;
-                const uint32_t w = t % g.W;
-                dg = s[2 + w];
-                neg = (dg < 0) != (s[1] != 0);
-                if (dg) pt = table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg < 0 ? -dg : dg))];
-            }
+            auto fetch = [&](uint32_t it, int& dg_o, bool& neg_o, G1Affine& pt_o) {
+                if (it < full) {
+                    const int16_t* s = steps + (size_t)(it / g.W) * stride;
+                    const uint32_t w = it % g.W;
+                    dg_o = s[2 + w];
+                    neg_o = (dg_o < 0) != (s[1] != 0);
+                    if (dg_o) pt_o = table[g.entry((uint32_t)(uint16_t)s[0] - 1u, w, (uint32_t)(dg_o < 0 ? -dg_o : dg_o))];
+                } else {
+                    const int16_t* u = units + 2 * (size_t)(it - full);
+                    dg_o = 1;
+                    neg_o = u[1] != 0;
+                    pt_o = table[g.entry((uint32_t)(uint16_t)u[0] - 1u, 0, 1u)];
+                }
+            };
+            if (t < total) fetch(t, dg, neg, pt);
 #pragma unroll 1
             for (uint32_t it = t; it < total; it += ctx.nthreads) {
                 const uint32_t nx = it + ctx.nthreads;
                 int dg_next = 0;
                 bool neg_next = false;
                 G1Affine pt_next = pt;
-                if (nx < total) {
-                    const int16_t* s = steps + (size_t)(nx / g.W) * stride;
-                    const uint32_t w = nx % g.W;
-                    dg_next = s[2 + w];
-                    neg_next = (dg_next < 0) != (s[1] != 0);
-                    if (dg_next) pt_next = table[g.entry((uint32_t)s[0] - 1u, w, (uint32_t)(dg_next < 0 ? -dg_next : dg_next))];
-                }
+                if (nx < total) fetch(nx, dg_next, neg_next, pt_next);
                 if (dg) g1_madd(acc, pt, neg);
                 dg = dg_next;
                 neg = neg_next;
@@ -501,10 +524,10 @@ struct WitnessCommitBody {
             sm[t] = acc;
         }
         DR_BLOCK_SYNC();
-        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
-            DR_STRIDE_LOOP(t, stride, ctx) {
+        for (uint32_t stride2 = ctx.nthreads >> 1; stride2 > 0; stride2 >>= 1) {
+            DR_STRIDE_LOOP(t, stride2, ctx) {
                 G1 a = sm[t];
-                g1_add(a, sm[t + stride]);
+                g1_add(a, sm[t + stride2]);
                 sm[t] = a;
             }
             DR_BLOCK_SYNC();
