@@ -206,10 +206,19 @@ def run_ours(args) -> None:
     # the requested table first; if the device cannot hold it (a smaller part, memory in use) fall back to the next smaller geometry
     requested = (args.window_bits, args.wide_windows, bool(args.glv))
     size = lambda g: (-(-((128 if g[2] else 256) - g[1]) // g[0]) + g[1]) << (g[0] - 1) if g[0] else 0  # ~table entries per SRS point  # noqa: E731
-    for c, k, glv in [requested] + [g for g in ((14, 4, False), (14, 0, False), (13, 0, False), (12, 0, False)) if size(g) < size(requested)]:
+    candidates = [requested] + [g for g in ((14, 4, False), (14, 0, False), (13, 0, False), (12, 0, False)) if size(g) < size(requested)]
+    for idx, (c, k, glv) in enumerate(candidates):
         eng.window_bits, eng.wide_windows, eng.glv = c, k, glv
         try:
             _ = eng.srs
+            # the ring tables (2.6 GB) and a 4096-proof pass (9.5 GB) must still fit next to the table
+            left = eng.ctx.device_info()["free_bytes"]
+            if not dry_run and left < 14e9 and idx + 1 < len(candidates):
+                print(f"[bench] window table ({c}, {k}, glv={glv}) leaves only {left / 1e9:.1f} GB: falling back", file=sys.stderr, flush=True)
+                eng._srs.close()
+                eng._srs = None
+                eng.ctx.trim()
+                continue
             break
         except MemoryError as e:
             print(f"[bench] window table ({c}, {k}, glv={glv}) does not fit: {e}", file=sys.stderr, flush=True)
