@@ -402,8 +402,12 @@ DR_HD Fr witness_eval(const RingDev& rg, const ProofState& ps, uint32_t col, uin
         pt = &rg.seed;
     else if (row <= rg.max_ring)
         pt = &ps.a0;
-    else
-        pt = &ps.s[row - rg.max_ring - 1];
+    else {
+        // max_ring_size below the domain's capacity leaves more than 253 blinding-base rows (members.py:46-51); the b column
+        // is zero there (columns.py:111-124), so the accumulator keeps its final value
+        uint32_t j = row - rg.max_ring - 1;
+        pt = &ps.s[j < SCALAR_BITS ? j : SCALAR_BITS - 1];
+    }
     return col == COL_ACCX ? pt->x : pt->y;
 }
 

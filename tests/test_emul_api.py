@@ -219,3 +219,10 @@ def test_mixed_window_geometries_commit_like_the_oracle(api):
     from tests import window_cases
 
     window_cases.check_commit_geometries(engine_mod.default_engine().ctx, [(4, 4), (5, 1), (7, 4), (4, 0, True), (6, 2, True), (7, 0, True), (11, 0, True)], n=5)
+
+
+def test_max_ring_size_below_domain_capacity(api):
+    """max_ring_size=100 / 1 at domain 512 must prove like the oracle (and the reference, whose tests use such sizes)."""
+    from tests import small_ring_cases
+
+    small_ring_cases.check_small_max_ring(api, cases=((512, 100), (512, 1)))
