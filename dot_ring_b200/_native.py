@@ -75,6 +75,8 @@ class Library:
         L.dr_srs_geometry.argtypes = [c_void_p, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]
         L.dr_srs_geometry.restype = None
         L.dr_kzg_commit.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
+        L.dr_kzg_open.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]
+        L.dr_kzg_pairing_check.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, POINTER(c_int)]
         L.dr_kzg_commit_bench.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_uint64, POINTER(c_float), c_void_p]
         L.dr_g1_msm.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_g1_synthetic_srs.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
@@ -133,6 +135,9 @@ class Library:
     def launch_count(self) -> int:
         return int(self.lib.dr_launch_count())
 
+    def device_count(self) -> int:
+        return int(self.lib.dr_device_count())
+
 
 _default: Library | None = None
 
@@ -182,6 +187,8 @@ class VerifierKeyStruct(ctypes.Structure):
 
 
 def _put(arr, data: bytes) -> None:
+    if len(data) > ctypes.sizeof(arr):
+        raise ValueError(f"value of {len(data)} bytes does not fit a {ctypes.sizeof(arr)}-byte field")
     ctypes.memmove(arr, data, len(data))
 
 
@@ -524,6 +531,33 @@ class NativeSrs:
         raw = out.raw
         return [raw[96 * i : 96 * i + 96] for i in range(batch)]
 
+    def open(self, coeff_vectors: list[list[int]], points: list[int]) -> list[tuple[bytes, int]]:
+        """KZG.open for a batch of equal-length coefficient vectors: [(proof 96 bytes, value)]."""
+        if not coeff_vectors:
+            return []
+        n, batch = len(coeff_vectors[0]), len(coeff_vectors)
+        if any(len(v) != n for v in coeff_vectors) or len(points) != batch:
+            raise ValueError("all coefficient vectors in a batch must have the same length, one point per vector")
+        proofs, values = ctypes.create_string_buffer(96 * batch), ctypes.create_string_buffer(32 * batch)
+        data = b"".join((int(c) % FR_MODULUS).to_bytes(32, "little") for v in coeff_vectors for c in v)
+        xs = b"".join((int(x) % FR_MODULUS).to_bytes(32, "little") for x in points)
+        lib = self.ctx.library
+        lib.check(lib.lib.dr_kzg_open(self.ctx.handle, self.handle, data, n, batch, xs, proofs, values))
+        return [(proofs.raw[96 * i : 96 * i + 96], int.from_bytes(values.raw[32 * i : 32 * i + 32], "little")) for i in range(batch)]
+
+    def pairing_check(self, lhs_points: list[bytes], lhs_scalars: list[int], rhs_points: list[bytes], rhs_scalars: list[int]) -> bool:
+        """e(sum lhs_scalars[i] * lhs_points[i], [1]_2) == e(sum rhs_scalars[j] * rhs_points[j], [tau]_2)  (pcs/kzg.py:194-338)."""
+        if len(lhs_points) != len(lhs_scalars) or len(rhs_points) != len(rhs_scalars):
+            raise ValueError("points and scalars must have the same length")
+        if any(len(p) != 96 for p in lhs_points) or any(len(p) != 96 for p in rhs_points):
+            raise ValueError("expected 96-byte uncompressed G1 points")
+        le = lambda ks: b"".join((int(k) % FR_MODULUS).to_bytes(32, "little") for k in ks)  # noqa: E731
+        ok = c_int(0)
+        lib = self.ctx.library
+        lib.check(lib.lib.dr_kzg_pairing_check(self.ctx.handle, self.handle, b"".join(lhs_points) or None, le(lhs_scalars) or None, len(lhs_points),
+                                               b"".join(rhs_points) or None, le(rhs_scalars) or None, len(rhs_points), ctypes.byref(ok)))
+        return bool(ok.value)
+
     def commit_bench(self, n: int, batch: int, iters: int, seed: int = 1) -> tuple[float, bytes]:
         ms = c_float()
         first = ctypes.create_string_buffer(96)
@@ -554,8 +588,7 @@ class RingParamsStruct(ctypes.Structure):
 
 
 def _fill(arr, data: bytes) -> None:
-    for i, b in enumerate(data):
-        arr[i] = b
+    _put(arr, bytes(data))
 
 
 def _xy(pt) -> bytes:

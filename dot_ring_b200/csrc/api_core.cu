@@ -243,6 +243,18 @@ int dr_is_cuda_build(void) {
 #endif
 }
 uint64_t dr_launch_count(void) { return launch_counter(); }
+int dr_device_count(void) {
+#if defined(DR_HOST_EMULATION)
+    return 1;
+#else
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+#endif
+}
 
 int dr_ctx_create(int device, dr_ctx** out) {
     DR_API_BEGIN

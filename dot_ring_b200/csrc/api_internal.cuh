@@ -127,6 +127,8 @@ struct Srs {
     uint8_t g1_0_be96[96];
     uint8_t g2_be192[384];
     std::vector<std::unique_ptr<LagrangeTable>> lagrange;
+    DevBuf<LineCoeffs> lines;  // Miller-loop lines of the two G2 points (pairing_warp.cuh), built on first use
+    const LineCoeffs* pairing_lines();
     // built on first use for (N, omega); tw_inv_half = [omega^-k], k < N/2, on the device
     const LagrangeTable& lagrange_table(uint32_t N, uint32_t logN, const Fr& omega, const Fr* tw_inv_half, const Fr& n_inv);
 };

@@ -128,7 +128,7 @@ static void status_to_verdict(const std::vector<uint32_t>& st, uint8_t* verdict)
 
 // aggregated batches of at least this many proofs fold their sides with two bucket-method MSMs (the MSM pipeline has a
 // latency floor of a few ms, below this size the per-proof scalar multiplications are faster); tests lower it
-static size_t RING_VERIFY_MSM_THRESHOLD = 8192;
+static std::atomic<size_t> RING_VERIFY_MSM_THRESHOLD{8192};  // process-wide test knob; read once per call
 
 // shared tail of the two ring-verification entry points; relations / payloads already on the device
 static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t n, const uint8_t* payloads, uint32_t stride, const TEAffine* relations, uint32_t rel_stride,
@@ -148,7 +148,7 @@ static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t 
     launch(ctx->stream, Dim3((7 * m + 63) / 64), 64, 0, PayloadG1DecodeBody(), payloads, stride, m, vs.p);
     launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, RingVerifyAlgebraBody(), vk, payloads, stride, relations, rel_stride, (const uint8_t*)dco.p, m, vs.p);
     uint32_t all = 0;
-    const bool by_msm = aggregate && n >= RING_VERIFY_MSM_THRESHOLD;
+    const bool by_msm = aggregate && n >= RING_VERIFY_MSM_THRESHOLD.load();
     if (!by_msm) launch(ctx->stream, Dim3((VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
     if (by_msm) {
         // two variable-base MSMs instead of 13 scalar multiplications per proof

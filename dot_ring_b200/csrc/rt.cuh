@@ -8,10 +8,12 @@
 // run block after block, thread after thread, on the CPU, which lets the CPU test-suite exercise
 // the exact kernel logic (indexing, phase structure, transcripts) without a GPU.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -89,8 +91,8 @@ __global__ void __launch_bounds__(THREADS, BLOCKS) kernel_entry_lb(Body body, Ar
 }
 
 // launch counter (bench.py reports it as gpu_launches)
-inline uint64_t& launch_counter() {
-    static uint64_t c = 0;
+inline std::atomic<uint64_t>& launch_counter() {  // several contexts (one per GPU, one thread each) launch concurrently
+    static std::atomic<uint64_t> c{0};
     return c;
 }
 
@@ -174,6 +176,9 @@ inline void* dev_alloc(size_t bytes) {
 }
 inline void dev_free(void* p) {
     if (!p) return;
+    // A buffer released while an exception unwinds the call may still be read by kernels already queued on the stream; the
+    // normal path only frees after the call synchronised its stream.  Drain the device before the block can be handed out again.
+    if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
     DevCache& c = dev_cache();
     std::unique_lock<std::mutex> lock(c.m);
     auto it = c.live.find(p);
@@ -217,8 +222,8 @@ inline void host_free_pinned(void* p) {
 #else
 // ------------------------------------------------------------------ host emulation (tests only)
 typedef int Stream;
-inline uint64_t& launch_counter() {
-    static uint64_t c = 0;
+inline std::atomic<uint64_t>& launch_counter() {  // several contexts (one per GPU, one thread each) launch concurrently
+    static std::atomic<uint64_t> c{0};
     return c;
 }
 template <class Body, class... Args>

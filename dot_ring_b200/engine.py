@@ -50,6 +50,8 @@ class Engine:
 
 
 def default_engine() -> Engine:
+    """The engine behind the module-level API (``KZG``, ``TinyVRF`` ...): what `set_default_engine` installed (an
+    :class:`Engine` or an :class:`EnginePool`), else a lazily created single-device engine."""
     device = int(os.environ.get("DOT_RING_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     with _lock:
         eng = _engines.get(device)
@@ -66,3 +68,169 @@ def set_default_engine(engine: Engine | None, device: int = 0) -> None:
             _engines.pop(device, None)
         else:
             _engines[device] = engine
+
+
+class EnginePool:
+    """One :class:`Engine` (``dr_ctx`` + SRS window table + ring replicas) per GPU of the node, behind one Python process.
+
+    The path shards naturally: proofs and verifications are independent units, so a caller's batch is split
+    into contiguous shards, one per device, and the results are concatenated in order; nothing is exchanged between GPUs.
+    Every device has its own worker thread; ctypes releases the GIL for the duration of a C-ABI call, so the shards run
+    concurrently.  This is what the reference does with a process pool over one work list
+    (tests/benchmark/bench_ring_proof.py:168-182).
+
+    ``Ring(keys, params, engine=pool)`` builds one ring replica per device (in parallel) and
+    ``RingVRF.prove_batch`` / ``verify_batch`` / ``batch_verify`` then use every GPU of the pool.
+    """
+
+    def __init__(self, devices=None, **engine_kwargs):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if devices is None:
+            devices = range(_native.default_library().device_count())
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError("EnginePool needs at least one device")
+        self._workers = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"dr-gpu{d}") for d in self.devices]
+        self.engines = self.map(lambda i: Engine(self.devices[i], **engine_kwargs))
+        self.ctx = PooledContext(self)
+        self.srs_bytes = self.engines[0].srs_bytes
+
+    def __len__(self) -> int:
+        return len(self.engines)
+
+    @property
+    def srs(self):
+        """First device's SRS (all replicas are built on demand by ``warm``)."""
+        return self.engines[0].srs
+
+    def map(self, fn, indices=None) -> list:
+        """Run ``fn(i)`` on worker i for every i in `indices` (default: all) concurrently; results in index order."""
+        idx = list(range(len(self._workers))) if indices is None else list(indices)
+        futures = [self._workers[i].submit(fn, i) for i in idx]
+        return [f.result() for f in futures]
+
+    def warm(self) -> None:
+        """Build every device's window table now (concurrently) instead of at the first commitment."""
+        self.map(lambda i: self.engines[i].srs)
+
+    @staticmethod
+    def shard_bounds(n: int, parts: int) -> list[tuple[int, int]]:
+        """Contiguous, balanced shards: the first n % parts shards take one extra item; empty shards are dropped."""
+        base, extra = divmod(n, parts)
+        out, lo = [], 0
+        for i in range(parts):
+            hi = lo + base + (1 if i < extra else 0)
+            if hi > lo:
+                out.append((lo, hi))
+            lo = hi
+        return out
+
+    def close(self) -> None:
+        self.map(lambda i: self.engines[i].close())
+        for w in self._workers:
+            w.shutdown(wait=True)
+
+
+class PooledContext:
+    """``_native.Context`` interface over a pool: the batched Tiny / Thin / Pedersen calls (independent items, lists in the
+    same order as the reference's per-item API) are sharded contiguously over the devices; everything else (single-item
+    helpers, codecs, settings) goes to the first device."""
+
+    _SHARDED = {"pedersen_verify": 1, "thin_verify": 1, "tiny_verify": 1, "vrf_prove": 2, "pedersen_prove_with_blinding": 1}  # index of the first list argument
+    _MIN_ITEMS_PER_DEVICE = 256
+
+    def __init__(self, pool: "EnginePool"):
+        self._pool = pool
+
+    def __getattr__(self, name):
+        first = self._pool.engines[0].ctx
+        attr = getattr(first, name)
+        if name not in self._SHARDED:
+            return attr
+        lead = self._SHARDED[name]
+        pool = self._pool
+
+        def sharded(*args, **kwargs):
+            n = len(args[lead])
+            parts = max(1, min(len(pool), n // self._MIN_ITEMS_PER_DEVICE))
+            bounds = pool.shard_bounds(n, parts)
+            if len(bounds) <= 1:
+                return attr(*args, **kwargs)
+
+            def run(i):
+                lo, hi = bounds[i]
+                sliced = [a[lo:hi] if j >= lead and isinstance(a, (list, tuple)) and len(a) == n else a for j, a in enumerate(args)]
+                return getattr(pool.engines[i].ctx, name)(*sliced, **kwargs)
+
+            out = pool.map(run, range(len(bounds)))
+            if isinstance(out[0], tuple):  # (proofs, blinding factors)
+                return tuple([x for part in out for x in part[k]] for k in range(len(out[0])))
+            return [x for part in out for x in part]
+
+        return sharded
+
+
+class PooledRingNative:
+    """The ``NativeRing`` interface over one replica per device of an :class:`EnginePool` (same results, sharded batches)."""
+
+    def __init__(self, pool: EnginePool, make_replica):
+        self.pool = pool
+        self.replicas = pool.map(lambda i: make_replica(pool.engines[i]))
+        self.ctx = self.replicas[0].ctx
+        self.domain_size = self.replicas[0].domain_size
+
+    def close(self) -> None:
+        self.pool.map(lambda i: self.replicas[i].close())
+
+    def root(self) -> bytes:
+        return self.replicas[0].root()
+
+    def fixed_commitments(self) -> bytes:
+        return self.replicas[0].fixed_commitments()
+
+    def points(self):
+        return self.replicas[0].points()
+
+    def witness_table_bits(self) -> int:
+        return self.replicas[0].witness_table_bits()
+
+    def prove_phase_ms(self) -> list[float]:
+        """Per-phase device time of the slowest replica's last call."""
+        per = self.pool.map(lambda i: self.replicas[i].prove_phase_ms())
+        return max(per, key=sum)
+
+    def prove_batch(self, alphas, ads, secret_keys, producer_index, zk_rows=None):
+        n = len(alphas)
+        bounds = self.pool.shard_bounds(n, len(self.replicas))
+        if len(bounds) <= 1:
+            return self.replicas[0].prove_batch(alphas, ads, secret_keys, producer_index, zk_rows)
+
+        def zk_slice(lo, hi):
+            if zk_rows is None:
+                return None
+            if isinstance(zk_rows, (bytes, bytearray)):
+                return zk_rows[384 * lo : 384 * hi]
+            return zk_rows[12 * lo : 12 * hi]
+
+        parts = self.pool.map(
+            lambda i: self.replicas[i].prove_batch(alphas[bounds[i][0] : bounds[i][1]], ads[bounds[i][0] : bounds[i][1]], secret_keys[bounds[i][0] : bounds[i][1]],
+                                                   producer_index[bounds[i][0] : bounds[i][1]], zk_slice(*bounds[i])),
+            range(len(bounds)),
+        )
+        return [p for proofs, _ in parts for p in proofs], [s for _, status in parts for s in status]
+
+    def verify_batch(self, inputs, ads, proofs, coeffs, aggregate: bool = False):
+        """Per-item mode: shards are independent.  Aggregated mode (`RingVRF.batch_verify`): every device folds its shard into
+        its own random-linear-combination check (its slice of the caller's coefficients) and the batch is accepted iff every
+        shard is -- the conjunction of independent batch checks, run concurrently, instead of shipping partial sums to one GPU."""
+        n = len(proofs)
+        bounds = self.pool.shard_bounds(n, len(self.replicas))
+        if len(bounds) <= 1:
+            return self.replicas[0].verify_batch(inputs, ads, proofs, coeffs, aggregate)
+        parts = self.pool.map(
+            lambda i: self.replicas[i].verify_batch(inputs[bounds[i][0] : bounds[i][1]], ads[bounds[i][0] : bounds[i][1]], proofs[bounds[i][0] : bounds[i][1]],
+                                                    coeffs[2 * bounds[i][0] : 2 * bounds[i][1]], aggregate),
+            range(len(bounds)),
+        )
+        return [v for verdicts, _ in parts for v in verdicts], all(ok for _, ok in parts)

@@ -16,7 +16,7 @@ from typing import Any
 
 from . import _native
 from .curve import point_to_string
-from .engine import Engine, default_engine
+from .engine import Engine, EnginePool, PooledRingNative, default_engine
 from .params import RingProofParams
 
 
@@ -45,7 +45,7 @@ class Ring:
     nm_points: tuple[tuple[int, int], ...]
     params: RingProofParams
 
-    def __init__(self, keys: Sequence[bytes], params: RingProofParams | None = None, engine: Engine | None = None) -> None:
+    def __init__(self, keys: Sequence[bytes], params: RingProofParams | None = None, engine: "Engine | EnginePool | None" = None) -> None:
         if params is None:
             params = RingProofParams.from_ring_size(len(keys))
         self.params = params
@@ -58,7 +58,10 @@ class Ring:
         self.keys = tuple(bytes(k) for k in keys)
         # keys of the wrong length can never decode; the reference maps them to the padding point as well
         normalised = [k if len(k) == 32 else b"\xff" * 32 for k in self.keys]
-        self.native = _native_ring(self.engine, normalised, params)
+        if isinstance(self.engine, EnginePool):  # one replica per GPU; batches are sharded over them (engine.py)
+            self.native = PooledRingNative(self.engine, lambda eng: _native_ring(eng, normalised, params))
+        else:
+            self.native = _native_ring(self.engine, normalised, params)
         self.nm_points = tuple(self.native.points())
         self._index: dict[tuple[int, int], int] | None = None
 
@@ -141,6 +144,19 @@ class RingRoot:
 
     def fixed_commitments(self) -> list[Any]:
         return [self.px.commitment, self.py.commitment, self.s.commitment]
+
+    def verifier_transcript_prefix(self, transcript_challenge: bytes | None = None):
+        """root.py:54-71: transcript state after absorbing the verifier key = [1]_1 | [1]_2 | [tau]_2 | C_px | C_py | C_s (uncompressed)."""
+        if self.params is None:
+            raise ValueError("Ring root verifier transcript requires ring proof parameters")
+        from .transcript import FiatShamirTranscript
+
+        srs = default_engine().srs_bytes
+        if transcript_challenge is None:
+            transcript_challenge = self.params.cv.curve.params.suite_id
+        transcript = FiatShamirTranscript(self.params.prime, transcript_challenge)
+        transcript.absorb_labeled(b"vk", srs.g1_be96[:96] + srs.g2_be192 + b"".join(self.fixed_commitments()))
+        return transcript
 
     @staticmethod
     def encoded_len(params: RingProofParams | None = None) -> int:

@@ -44,28 +44,7 @@ def _dec_scalar(cv: CurveVariant, value: bytes) -> int:
     return scalar
 
 
-def _random_nonzero_coefficients(count: int, order: int) -> list[int]:
-    """pcs/kzg.py:84-108: first coefficient 1, the rest rejection-sampled from SHAKE256(32 random bytes | ctr)."""
-    if count <= 0:
-        return []
-    coeffs = [1]
-    byte_len = (order.bit_length() + 7) // 8
-    limit = (1 << (8 * byte_len)) - ((1 << (8 * byte_len)) % order)
-    seed = secrets.token_bytes(32)
-    counter = 0
-    while len(coeffs) < count:
-        raw = hashlib.shake_256(seed + counter.to_bytes(8, "little")).digest(byte_len * (count - len(coeffs)) * 2)
-        counter += 1
-        for offset in range(0, len(raw), byte_len):
-            candidate = int.from_bytes(raw[offset : offset + byte_len], "big")
-            if candidate >= limit:
-                continue
-            coeff = candidate % order
-            if coeff:
-                coeffs.append(coeff)
-                if len(coeffs) == count:
-                    break
-    return coeffs
+from .kzg import _random_nonzero_coefficients  # noqa: E402  (pcs/kzg.py:84-108)
 
 
 def _suite_struct(cv: CurveVariant):
@@ -439,18 +418,20 @@ class RingVRF(VRF):
         if len(sks) != n or len(pks) != n:
             raise ValueError("secret_key / producer_key must be single values or one per item")
         # vrf.py:196-197: producer_key must be pk(sk) -- one device scalar multiplication per distinct key pair, remembered per ring
+        # under a digest of the pair (no secret key outlives the call in the cache)
         cache = ring.__dict__.setdefault("_signer_rows", {})
+        tag = lambda sk, pk: hashlib.blake2b(sk + pk, digest_size=16).digest()  # noqa: E731
         pairs = set(zip(sks, pks))
-        distinct = sorted(pairs - cache.keys())
+        distinct = sorted(p for p in pairs if tag(*p) not in cache)
         if distinct:
             derived = cls.cv.public_keys_from_secrets([sk for sk, _ in distinct])
             for (sk, pk), got in zip(distinct, derived):
                 if pk != got:
                     raise ValueError("producer_key does not match secret_key")
-                cache[(sk, pk)] = ring.index_of(pk)
+                cache[tag(sk, pk)] = ring.index_of(pk)
         if ring_root is not None and ring_root.encode() != RingRoot.from_ring(ring).encode():
             raise ValueError("ring_root does not match ring")
-        index = {pk: cache[(sk, pk)] for sk, pk in pairs}
+        index = {pk: cache[tag(sk, pk)] for sk, pk in pairs}
         if zk_rows is None and not ring.params.test_vectors:
             prime = ring.params.prime
             zk_rows = [secrets.randbelow(prime) for _ in range(12 * n)]

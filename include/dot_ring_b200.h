@@ -43,6 +43,9 @@ const char* dr_version(void);
 /* 1 when built for the GPU (nvcc, sm_100a); 0 for the CPU emulation build used only by tests/host. */
 int dr_is_cuda_build(void);
 
+/* CUDA devices visible to this process (one dr_ctx per device; dot_ring_b200.engine.EnginePool shards batches over them). */
+int dr_device_count(void);
+
 /* ---- context ------------------------------------------------------------------------------- */
 int dr_ctx_create(int device, dr_ctx** out);
 void dr_ctx_destroy(dr_ctx* ctx);
@@ -78,6 +81,16 @@ void dr_srs_geometry(const dr_srs* srs, uint32_t* window_bits, uint32_t* wide_wi
  * values >= r are reduced (kzg.py passes unreduced quotient coefficients, ops.py:215-220); all-zero ->
  * infinity (kzg.py:167-168).  Output: batch x 96-byte uncompressed commitments. */
 int dr_kzg_commit(dr_ctx* ctx, dr_srs* srs, const uint8_t* coeffs_le32, size_t n, size_t batch, uint8_t* out_be96);
+/* `KZG.open` (dot_ring/ring_proof/pcs/kzg.py:178-191 over `synthetic_div_with_eval`, pcs/utils.py:27-35) for `batch` polynomials of n >= 1
+ * coefficients: values_le32[b] = f_b(x_b) and proofs_be96[b] = commit((f_b - f_b(x_b)) / (X - x_b)), the quotient committed like dr_kzg_commit. */
+int dr_kzg_open(dr_ctx* ctx, dr_srs* srs, const uint8_t* coeffs_le32, size_t n, size_t batch, const uint8_t* points_le32, uint8_t* proofs_be96, uint8_t* values_le32);
+/* The pairing equation every KZG verifier of the reference ends in (pcs/kzg.py:194-338: `verify`, `batch_verify`,
+ * `batch_verify_linear_preconverted` after their random linear combination):
+ *   *ok = ( e(sum_i lhs_scalars[i] * lhs_points[i], [1]_2) == e(sum_j rhs_scalars[j] * rhs_points[j], [tau]_2) )
+ * with [1]_2, [tau]_2 the G2 points of `srs`.  Points 96-byte uncompressed, scalars 32-byte little-endian (reduced mod r here).
+ * Replaces the two `mult_pippenger` calls + `blst_miller_loop` x 2 + `blst_final_verify` (pcs/pairing.py:24-31). */
+int dr_kzg_pairing_check(dr_ctx* ctx, dr_srs* srs, const uint8_t* lhs_points_be96, const uint8_t* lhs_scalars_le32, size_t n_lhs, const uint8_t* rhs_points_be96,
+                         const uint8_t* rhs_scalars_le32, size_t n_rhs, int* ok);
 /* How the table entries of a commitment are summed: 0 = XYZZ mixed additions (10 multiplications each), 1 = batched-affine
  * pairing rounds (one inversion per round of independent additions, ~6.3 multiplications each) for polynomials long enough to
  * fill a round.  Same group element either way; tests cross-check the two. */
