@@ -5,11 +5,20 @@
     python bench.py --impl reference --gpus N --steps K ...   # reference algorithm on the host CPU cores
 
 Workload (BASELINE.json configs[1]; seeding of the reference's own tests/benchmark/bench_ring_proof.py:
-47-77,140-152): one 1023-key ring, signer at index 3, per step a batch of `--batch` proofs with
+47-77,140-152): one 1023-key ring, signer at index 3, per step ONE batch of `--total` (4096) proofs with
 alpha = "bench-batch-input" | le64(j), ad = "bench-batch-ad" | le64(j) and 12 blinding rows per proof from
-random.Random(0).  Every rank proves its own batch per step (weak scaling, no data-path collective);
-`value` = proofs of all ranks / max-over-ranks device time; `e2e` = the same through the public Python API
-with host buffers (H2D of the inputs and D2H of the 784-byte proofs inside the timed region).
+random.Random(step), sharded contiguously over the GPUs (strong scaling, no data-path collective): under torchrun
+every rank proves its slice of the batch; `python bench.py --gpus N` without torchrun drives N GPUs from one process
+through dot_ring_b200.engine.EnginePool.  `--batch B` selects weak scaling instead (B proofs per GPU per step); the
+strong line also carries that operating point as `saturated` (8192 proofs per GPU per step).
+`value` = proofs of all GPUs / max-over-ranks device time (one CUDA event pair around each step's call);
+`e2e` = the same through the public Python API with host buffers (H2D of the inputs and D2H of the 784-byte
+proofs inside the timed region).
+
+Before anything is timed the six ring-1023 proofs of the unmodified reference (tests/golden/ring1023_reference.json)
+are proved through the same engine, window table and batch width and compared byte for byte; after the timed region a
+sample of the last step's proofs is verified on the device (and, at N=1, three of them by the CPU oracle inside the
+cpu_baseline leg).  No value is printed if any of that fails.
 
 A number printed by this script under a profiler is not a bench value.
 """
@@ -186,51 +195,99 @@ def reduce_sum(dist, local, values: list[float]) -> list[float]:
 
 
 # -------------------------------------------------------------------------------------------------- ours
-def run_ours(args) -> None:
-    rank, local, world, dist = dist_setup(args.gpus)
-    os.environ["DOT_RING_B200_DEVICE"] = str(local)
-    from dot_ring_b200 import Bandersnatch, Ring, RingProofParams, RingRoot, RingVRF
+GOLDEN_RING1023 = ROOT / "tests" / "golden" / "ring1023_reference.json"  # written by the unmodified reference (tests/golden/generate_golden.py)
+
+
+def build_engine(args, local: int, n_local_devices: int, dry_run: bool):
+    """Engine (one device) or EnginePool (one process, several devices) with the requested window table; falls back to the next
+    smaller geometry when the device cannot hold it.  Returns (engine, seconds)."""
     from dot_ring_b200 import engine as eng_mod
 
     t0 = time.perf_counter()
-    dry_run = DRY_RUN
     library = None
     if dry_run:
         from tests.host.emul import emulation_library
 
         library = emulation_library()
-    eng = eng_mod.Engine(local, window_bits=args.window_bits, library=library, wide_windows=args.wide_windows, glv=bool(args.glv))
-    if not dry_run and not eng.ctx.library.is_cuda:
-        raise SystemExit("bench.py measures the CUDA build only")
-    eng_mod.set_default_engine(eng, local)
-    # the requested table first; if the device cannot hold it (a smaller part, memory in use) fall back to the next smaller geometry
     requested = (args.window_bits, args.wide_windows, bool(args.glv))
     size = lambda g: (-(-((128 if g[2] else 256) - g[1]) // g[0]) + g[1]) << (g[0] - 1) if g[0] else 0  # ~table entries per SRS point  # noqa: E731
     candidates = [requested] + [g for g in ((14, 4, False), (14, 0, False), (13, 0, False), (12, 0, False)) if size(g) < size(requested)]
-    for idx, (c, k, glv) in enumerate(candidates):
-        eng.window_bits, eng.wide_windows, eng.glv = c, k, glv
-        try:
-            _ = eng.srs
-            # the ring tables (2.6 GB) and a 4096-proof pass (9.5 GB) must still fit next to the table
-            left = eng.ctx.device_info()["free_bytes"]
-            if not dry_run and left < 14e9 and idx + 1 < len(candidates):
-                print(f"[bench] window table ({c}, {k}, glv={glv}) leaves only {left / 1e9:.1f} GB: falling back", file=sys.stderr, flush=True)
-                eng._srs.close()
-                eng._srs = None
+
+    def one(device: int):
+        eng = eng_mod.Engine(device, window_bits=args.window_bits, library=library, wide_windows=args.wide_windows, glv=bool(args.glv))
+        if not dry_run and not eng.ctx.library.is_cuda:
+            raise SystemExit("bench.py measures the CUDA build only")
+        for idx, (c, k, glv) in enumerate(candidates):
+            eng.window_bits, eng.wide_windows, eng.glv = c, k, glv
+            try:
+                _ = eng.srs
+                # the ring tables (2.6 GB) and a 4096-proof pass (9.5 GB) must still fit next to the table
+                left = eng.ctx.device_info()["free_bytes"]
+                if not dry_run and left < 14e9 and idx + 1 < len(candidates):
+                    print(f"[bench] window table ({c}, {k}, glv={glv}) leaves only {left / 1e9:.1f} GB: falling back", file=sys.stderr, flush=True)
+                    eng._srs.close()
+                    eng._srs = None
+                    eng.ctx.trim()
+                    continue
+                break
+            except MemoryError as e:
+                print(f"[bench] window table ({c}, {k}, glv={glv}) does not fit: {e}", file=sys.stderr, flush=True)
                 eng.ctx.trim()
-                continue
-            break
-        except MemoryError as e:
-            print(f"[bench] window table ({c}, {k}, glv={glv}) does not fit: {e}", file=sys.stderr, flush=True)
-            eng.ctx.trim()
-    else:
-        raise SystemExit("bench.py: no window table fits on this device")
-    eng.ctx.set_commit_mode(args.commit_mode)
-    if args.prove_chunk:
-        eng.ctx.set_prove_chunk(args.prove_chunk)
-    eng.ctx.sync()
-    table_s = time.perf_counter() - t0
-    info = eng.ctx.device_info()
+        else:
+            raise SystemExit("bench.py: no window table fits on this device")
+        eng.ctx.set_commit_mode(args.commit_mode)
+        if args.prove_chunk:
+            eng.ctx.set_prove_chunk(args.prove_chunk)
+        eng.ctx.sync()
+        return eng
+
+    if n_local_devices <= 1:
+        eng = one(local)
+        eng_mod.set_default_engine(eng, local)
+        return eng, time.perf_counter() - t0
+    pool = eng_mod.EnginePool.__new__(eng_mod.EnginePool)  # engines built by `one` (table fallback per device), then adopted by the pool
+    from concurrent.futures import ThreadPoolExecutor
+
+    pool.devices = [0] * n_local_devices if dry_run else list(range(n_local_devices))
+    pool._workers = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"dr-gpu{d}") for d in pool.devices]
+    pool.engines = pool.map(lambda i: one(pool.devices[i]))
+    pool.ctx = eng_mod.PooledContext(pool)
+    pool.srs_bytes = pool.engines[0].srs_bytes
+    eng_mod.set_default_engine(pool, local)
+    return pool, time.perf_counter() - t0
+
+
+def golden_parity(RingVRF, Bandersnatch, ring, sk, pk, width: int, keys: list[bytes], rng, limit: int | None = None) -> dict:
+    """Prove, in ONE batch of the bench's own per-device width through the bench's engine / table / ring, the six ring-1023 proofs
+    the unmodified reference produced (4 with zeroed blinding rows, 2 with given rows) and compare the 784 bytes of each."""
+    g = json.loads(GOLDEN_RING1023.read_text())
+    if hashlib.sha256(b"".join(keys)).hexdigest() != g["keys_sha256"] or pk.hex() != g["signer_pk"]:
+        raise SystemExit("bench.py: the synthetic ring differs from the reference's benchmark ring (tests/golden/ring1023_reference.json)")
+    items = [(bytes.fromhex(v["alpha"]), bytes.fromhex(v["ad"]), [0] * 12, v["proof"]) for v in g["proofs_test_vectors"][:limit]]
+    items += [(bytes.fromhex(v["alpha"]), bytes.fromhex(v["ad"]), [int(z, 16) for z in v["zk_rows"]], v["proof"]) for v in g["proofs_blinded"][:limit]]
+    n = max(width, len(items))
+    alphas = [it[0] for it in items] + [b"bench-parity-filler" + le64(j) for j in range(n - len(items))]
+    ads = [it[1] for it in items] + [b"" for _ in range(n - len(items))]
+    zk = b"".join(z.to_bytes(32, "little") for it in items for z in it[2]) + b"".join(rng.randrange(FR).to_bytes(32, "little") for _ in range(12 * (n - len(items))))
+    proofs = RingVRF[Bandersnatch].prove_batch(alphas, ads, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
+    equal = [proofs[i].hex() == it[3] for i, it in enumerate(items)]
+    if not all(equal):
+        raise SystemExit(f"bench.py: golden proofs differ from the reference at items {[i for i, e in enumerate(equal) if not e]}; refusing to report a number")
+    return {"golden_proofs": len(items), "equal": True, "batch_width": n}
+
+
+def run_ours(args) -> None:
+    rank, local, world, dist = dist_setup(args.gpus)
+    pool_devices = args.gpus if world == 1 and args.gpus > 1 else 1  # one process driving several GPUs through EnginePool
+    n_dev = world * pool_devices
+    os.environ["DOT_RING_B200_DEVICE"] = str(local)
+    from dot_ring_b200 import Bandersnatch, Ring, RingProofParams, RingRoot, RingVRF
+
+    dry_run = DRY_RUN
+    eng, table_s = build_engine(args, local, pool_devices, dry_run)
+    engines = eng.engines if pool_devices > 1 else [eng]
+    info = engines[0].ctx.device_info()
+    lib = engines[0].ctx.library
 
     # synthetic ring: keys derived with the product's own key derivation (no oracle on this path)
     t0 = time.perf_counter()
@@ -245,124 +302,204 @@ def run_ours(args) -> None:
     root = RingRoot.from_ring(ring, params)
     root_bytes = root.encode()
     ring_s = time.perf_counter() - t0
+    ring.native.time_calls = True
+    prove = lambda a, d, zk: RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)  # noqa: E731
 
-    batch = args.batch
-    rng = random.Random(rank)
+    # ---- workload ---------------------------------------------------------------------------------------------
+    strong = args.scaling == "strong"
+    if strong:  # BASELINE configs[1]: ONE batch of `total` proofs per step, sharded contiguously over the GPUs
+        total = args.total
+        lo, hi = _shard(total, world, rank)
+    else:  # every GPU proves its own `batch` proofs per step
+        total = args.batch * n_dev
+        lo, hi = rank * args.batch * pool_devices, (rank + 1) * args.batch * pool_devices
+    mine = hi - lo
+    per_device = -(-mine // pool_devices)
 
-    def inputs(step: int):
-        base = (rank * 1_000_000 + step) * batch
+    def inputs(step: int, lo: int, hi: int, total: int, stream_seed):
+        """alpha / ad = the reference's benchmark strings over the global proof index j = step * total + g; blinding rows from
+        random.Random(stream_seed): in strong mode ONE stream over the whole batch, sliced per rank."""
+        rng = random.Random(stream_seed)
+        if lo:
+            for _ in range(12 * lo):
+                rng.randrange(FR)
+        base = step * total
         return (
-            [b"bench-batch-input" + le64(base + j) for j in range(batch)],
-            [b"bench-batch-ad" + le64(base + j) for j in range(batch)],
-            b"".join(rng.randrange(FR).to_bytes(32, "little") for _ in range(12 * batch)),  # blinding rows as wire bytes
+            [b"bench-batch-input" + le64(base + g) for g in range(lo, hi)],
+            [b"bench-batch-ad" + le64(base + g) for g in range(lo, hi)],
+            b"".join(rng.randrange(FR).to_bytes(32, "little") for _ in range(12 * (hi - lo))),  # blinding rows as wire bytes
         )
 
-    launches0 = eng.ctx.library.launch_count()
-    for w in range(args.warmup):
-        a, d, zk = inputs(500_000 + w)
-        RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
-    launches_warm = eng.ctx.library.launch_count()
+    # ---- parity gate: the reference's own proofs through this engine, table and batch width -------------------
+    parity = golden_parity(RingVRF, Bandersnatch, ring, sk, pk, mine, keys, random.Random(1234 + rank), limit=1 if dry_run else None)
+    parity["ring_root_sha256"] = hashlib.sha256(root_bytes).hexdigest()[:16]
 
-    prepared = [inputs(s) for s in range(args.steps)]
+    launches0 = lib.launch_count()
+    for w in range(args.warmup):
+        a, d, zk = inputs(500_000 + w, lo, hi, total, (w + 1) * 7919 if strong else 1_000_003 * (rank + 1) + w)
+        prove(a, d, zk)
+    launches_warm = lib.launch_count()
+
+    prepared = [inputs(s, lo, hi, total, s if strong else 1_000_003 * (rank + 1) + 1000 + s) for s in range(args.steps)]
     sampler = ClockSampler(local)
     sampler.start()
     barrier(dist, local)
-    eng.ctx.sync()
-    dev_ms, phases = 0.0, [0.0] * 6
+    for e in engines:
+        e.ctx.sync()
+    dev_ms, phases, kernel_ms, kernel_launches = 0.0, [0.0] * 6, 0.0, 0
     t_start = time.perf_counter()
     last = None
     for a, d, zk in prepared:
-        last = RingVRF[Bandersnatch].prove_batch(a, d, sk, pk, ring, None, zk_rows=zk, as_bytes=True)
+        last = prove(a, d, zk)
+        dev_ms += ring.native.last_call_ms  # one CUDA event pair around the whole call (slowest device of a pool)
         ph = ring.native.prove_phase_ms()
-        dev_ms += sum(ph)
         phases = [x + y for x, y in zip(phases, ph)]
-    eng.ctx.sync()
+        km, kl = ring.native.commit_kernel_ms()
+        kernel_ms += km
+        kernel_launches += kl
+    for e in engines:
+        e.ctx.sync()
     barrier(dist, local)
     wall_s = time.perf_counter() - t_start
     clocks = sampler.stop()
-    launches = eng.ctx.library.launch_count() - launches_warm
+    launches = lib.launch_count() - launches_warm
+
+    # ---- every timed step's output is checked: a sample of the last step with the device verifier -------------
+    la, ld, _ = prepared[-1]
+    k = min(len(last), 64)
+    picks = sorted(random.Random(99).sample(range(len(last)), k))
+    verdicts = RingVRF[Bandersnatch].verify_batch([last[i] for i in picks], [la[i] for i in picks], [ld[i] for i in picks], ring, root)
+    if verdicts != [1] * k or len(set(last)) != len(last):
+        raise SystemExit("bench.py: proofs of the timed region do not verify; refusing to report a number")
+    parity["verified_sample"] = k
+    oracle_sample = [(last[i], la[i], ld[i]) for i in picks[:3]]
 
     # integer-pipe ceiling measured live on this GPU (dependent-free mad.lo.u32, all SMs)
     if dry_run:
         imad_peak = imad_wide_peak = 148 * 64 * 1.965e9  # nominal; a dry run is not a measurement
     else:
-        imad_peak, _ = eng.ctx.microbench("imad", 20000)
-        imad_wide_peak, _ = eng.ctx.microbench("imad_wide", 20000)
+        imad_peak, _ = engines[0].ctx.microbench("imad", 20000)
+        imad_wide_peak, _ = engines[0].ctx.microbench("imad_wide", 20000)
+
+    # ---- the other operating point, reported beside the headline: every GPU saturated with its own 8192-proof passes ----
+    saturated = None
+    if strong and args.saturated_batch and not dry_run:
+        sb = args.saturated_batch * pool_devices
+        slo = rank * sb
+        for w in range(2):
+            prove(*inputs(700_000 + w, slo, slo + sb, sb * world, 1_000_003 * (rank + 1) + 2000 + w))
+        sat_in = [inputs(710_000 + s, slo, slo + sb, sb * world, 1_000_003 * (rank + 1) + 3000 + s) for s in range(args.saturated_steps)]
+        barrier(dist, local)
+        sat_ms, t1 = 0.0, time.perf_counter()
+        for a, d, zk in sat_in:
+            prove(a, d, zk)
+            sat_ms += ring.native.last_call_ms
+        barrier(dist, local)
+        sat_wall = time.perf_counter() - t1
+        smx = reduce_max(dist, local, [sat_ms, sat_wall])
+        n_sat = sb * world * args.saturated_steps
+        saturated = {"proofs_per_gpu_per_step": args.saturated_batch, "steps": args.saturated_steps, "value": n_sat / (smx[0] * 1e-3), "e2e": n_sat / smx[1], "unit": "proofs/s",
+                     "scaling": "weak", "note": "every GPU proves its own full-width passes (the throughput operating point of round 1's headline)"}
 
     mx = reduce_max(dist, local, [dev_ms, wall_s])
-    proofs_total = batch * args.steps * world
+    proofs_total = total * args.steps
     value = proofs_total / (mx[0] * 1e-3)
     e2e = proofs_total / mx[1]
-    commit_ms = phases[2]
-    achieved = CANONICAL_IMAD_PER_PROOF * batch * args.steps / (commit_ms * 1e-3)
-    window_bits, wide_windows, glv, windows = eng.srs.geometry
-    madds_per_proof = sum(DENSE_MSM_SIZES) * windows + sparse_witness_madds(ring.native.witness_table_bits() or 10)
-    executed = madds_per_proof * 10 * 600 * batch * args.steps / (commit_ms * 1e-3)  # 8M + 2S per mixed addition, 600 IMAD per Fq mul
-    table_traffic = madds_per_proof * 96 * batch * args.steps  # algorithmic table bytes read
+    window_bits, wide_windows, glv, windows = engines[0].srs.geometry
+    wbits = ring.native.witness_table_bits() or 10
+    # dominant kernel = the dense fixed-base commit (quotient + two openings); event-timed around its launches only
+    dense_madds = sum(DENSE_MSM_SIZES) * windows
+    kernel_imad = dense_madds * 10 * 600 * mine * args.steps / pool_devices  # per device: 8M + 2S per mixed addition, 600 IMAD per Fq mul
+    kernel_rate = kernel_imad / (kernel_ms * 1e-3) if kernel_ms else 0.0
+    canonical_dense = sum(canonical_fq_mul_per_msm(n) for n in DENSE_MSM_SIZES) * 600
+    madds_per_proof = dense_madds + sparse_witness_madds(wbits)
+    step_imad = madds_per_proof * 10 * 600 * mine * args.steps / pool_devices
+    table_bytes_per_launch = dense_madds * 96 * per_device / 3  # average over the 3 launches of a pass
 
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
         return
+    per_gpu = total // n_dev if strong else args.batch
     line = {
         "metric": "ring_vrf_proofs_per_s",
         "value": value,
         "unit": "proofs/s",
-        "n_gpus": world,
+        "n_gpus": n_dev,
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": mx[0] / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None,
         "dtype": "u32 limbs (381-bit Fq / 255-bit Fr Montgomery)",
         "data": "synthetic",
         "config": {
-            "workload": f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {batch} proofs per GPU per step (BASELINE configs[1])",
-            "batch_per_gpu": batch,
+            "workload": (f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, one batch of {total} proofs per step sharded over {n_dev} GPU(s) "
+                         f"({per_gpu} per GPU) -- BASELINE configs[1]" if strong else
+                         f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {args.batch} proofs per GPU per step (BASELINE configs[1] shape, weak scaling)"),
+            "total_proofs_per_step": total,
+            "proofs_per_gpu_per_step": per_gpu,
+            "launch": "one process, EnginePool over %d devices" % pool_devices if pool_devices > 1 else ("torchrun, one rank per GPU" if world > 1 else "one process, one GPU"),
             "window_bits": window_bits,
             "wide_windows": wide_windows,
             "glv_split": bool(glv),
             "table_additions_per_coefficient": windows,
-            "table_gb": round(eng.srs.table_bytes / 1e9, 2),
-            "l2": "per-step working set (window table + 2.3 MB of scratch per proof) is far larger than the 126 MB L2; no flush needed",
-            "parity": "ring root sha256 " + hashlib.sha256(root_bytes).hexdigest()[:16],
+            "table_gb": round(engines[0].srs.table_bytes / 1e9, 2),
+            "l2": "per-step working set (window table + ~2 MB of scratch per proof) is far larger than the 126 MB L2; no flush needed",
+            "parity": parity,
         },
-        "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": batch * (12 * 32 + 32 + 4 * 5 + 25 + 22), "d2h_bytes_per_step": batch * (784 + 4), "ms_per_step": mx[1] * 1e3 / args.steps},
+        "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": total * (12 * 32 + 32 + 4 * 5 + 25 + 22), "d2h_bytes_per_step": total * (784 + 4), "ms_per_step": mx[1] * 1e3 / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {
-            "kernel": "kernel_entry_lb<CommitBodyT> (fixed-base KZG commit) + WitnessCommitBody (sparse witness commitments)",
+            "kernel": "kernel_entry_lb<CommitBodyT<GLV>> (dense fixed-base KZG commit: quotient + two openings)",
             "bound": "imad (int32 multiply-add pipe; neither hbm nor tensor: the path is 381-bit modular arithmetic)",
-            "achieved": achieved / 1e12,
+            "achieved": kernel_rate / 1e12,
             "peak": imad_peak / 1e12,
-            "unit": "T IMAD/s (canonical Pippenger count, SURVEY.md 8d: 4.674 G IMAD per proof)",
-            "frac": achieved / imad_peak,
-            "executed": executed / 1e12,
-            "executed_frac": executed / imad_peak,
-            "executed_note": f"{madds_per_proof} mixed G1 additions per proof actually issued (fixed-base tables + sparse witness columns) x 6000 IMAD; 'achieved' counts the canonical Pippenger work of all 7 MSMs",
+            "unit": "T IMAD/s executed by the kernel (mixed G1 additions issued x 10 Fq mul x 600 IMAD), CUDA events around its launches only",
+            "frac": kernel_rate / imad_peak,
+            "kernel_ms_per_step": kernel_ms / args.steps,
+            "kernel_launches_per_step": kernel_launches / args.steps,
+            "kernel_share_of_step": kernel_ms / dev_ms if dev_ms else None,
+            "algorithmic_reduction": canonical_dense / (dense_madds * 6000),
+            "algorithmic_reduction_note": "canonical Pippenger IMAD of the same three MSMs (SURVEY.md 8d) / IMAD executed: the fixed-base table removes buckets and doublings",
+            "whole_step_executed_frac": step_imad / (dev_ms * 1e-3) / imad_peak if dev_ms else None,
+            "whole_step_canonical_frac": CANONICAL_IMAD_PER_PROOF * mine * args.steps / pool_devices / (dev_ms * 1e-3) / imad_peak if dev_ms else None,
             "peak_source": "measured live: dependent-free mad.lo.u32 on all SMs (dr_microbench); IMAD.WIDE measured " + f"{imad_wide_peak / 1e12:.2f} T/s",
-            # ncu dram__bytes_read + write of the largest commit launch (1024 x 6145 coefficients, GLV table, 16 additions per
-            # coefficient; profiles/r01_ncu_full_CommitBody_glv16.csv) against 9.7 GB of table entries it must touch: a 96-byte entry at
-            # a random address straddles 64-byte DRAM atoms (2 or 3 of them), and the kernel is bound by the integer pipe, not by these
-            # reads.  (106 GB table: 23.0e9 for 10.9e9 algorithmic, r01_ncu_full_CommitBody_w18.csv.)
-            "traffic": 22.0e9 if glv else 23.0e9,
-            "traffic_launch": ("CommitBodyT<true> grid (2, 1024) x 128 threads, 40.3 ms under ncu; algorithmic table bytes of that launch 9.7e9" if glv else
-                               "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9"),
-            "algorithmic_table_bytes": table_traffic,
-            "hbm_gbs_for_table_reads": table_traffic / (commit_ms * 1e-3) / 1e9,
-            "kernel_share_of_step": commit_ms / sum(phases),
+            "traffic": NCU_TRAFFIC["glv" if glv else "plain"]["bytes"],
+            "traffic_launch": NCU_TRAFFIC["glv" if glv else "plain"]["launch"],
+            "algorithmic_table_bytes_per_launch": table_bytes_per_launch,
+            "hbm_gbs_for_table_reads": dense_madds * 96 * mine * args.steps / pool_devices / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None,
         },
         "phase_ms_per_step": {k: v / args.steps for k, v in zip(["pedersen+witness", "interpolate", "commit(msm)", "lde+constraints+quotient", "evals+openings", "transcripts+assembly"], phases)},
         "setup": {"srs_table_s": table_s, "ring_s": ring_s, "device": info["name"], "sm_count": info["sm_count"]},
     }
+    if saturated:
+        line["saturated"] = saturated
     if dry_run:
         line["dry_run"] = "CPU emulation of the kernels (tests only); not a measurement"
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single()
+    if n_dev == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(oracle_sample)
+        line["config"]["parity"]["oracle_verified"] = line["cpu_baseline"].pop("oracle_verified")
     emit(line)
     if last:
         sys.stderr.write(f"[bench] last proof sha256 {hashlib.sha256(last[-1]).hexdigest()[:16]}\n")
+
+
+def _shard(total: int, parts: int, index: int) -> tuple[int, int]:
+    base, extra = divmod(total, parts)
+    lo = index * base + min(index, extra)
+    return lo, lo + base + (1 if index < extra else 0)
+
+
+# ncu --set full captures of the dominant kernel (profiles/): dram__bytes_read.sum + dram__bytes_write.sum of ONE launch.  A 96-byte
+# table entry at a random address straddles 64-byte DRAM atoms (2 or 3 of them), so the traffic exceeds the algorithmic table bytes;
+# the kernel is bound by the integer pipe, not by these reads.
+NCU_TRAFFIC = {
+    "glv": {"bytes": 22.0e9, "launch": "CommitBodyT<true> grid (2, 1024) x 128 threads (1024 x 6145 coefficients), 40.3 ms under ncu; algorithmic table bytes of that launch 9.7e9 (profiles/r01_ncu_full_CommitBody_glv16.csv)"},
+    "plain": {"bytes": 23.0e9, "launch": "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9 (profiles/r01_ncu_full_CommitBody_w18.csv)"},
+}
 
 
 # ------------------------------------------------------------------------------------ CPU baseline (oracle)
@@ -394,12 +531,24 @@ def _oracle_prove_n(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline_single() -> dict:
+def cpu_baseline_single(gpu_sample=()) -> dict:
+    """The oracle port timed on one host core (reported baseline), and -- the checker role of the same leg -- the oracle's verifier
+    run over a few proofs the GPU produced inside the timed region."""
     from oracle import backend_name
 
     count = int(os.environ.get("DOT_RING_B200_CPU_BASELINE_PROOFS", "10"))  # about 11 s of CPU work
     dt = _oracle_prove_n((count, 0))
+    verified = 0
+    if gpu_sample:
+        from oracle import vrf as ovrf
+
+        _, _, oring, oroot = _oracle_ring()
+        for proof, alpha, ad in gpu_sample:
+            if not ovrf.ring_verify(ovrf.RingVrfProof.decode(proof), alpha, ad, oring, oroot, ring_matches=True):
+                raise SystemExit("bench.py: the CPU oracle rejects a proof of the timed region; refusing to report a number")
+            verified += 1
     return {
+        "oracle_verified": verified,
         "value": count / dt,
         "unit": "proofs/s",
         "cores": 1,
@@ -471,7 +620,12 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="proofs per GPU per step (one device pass: 19 GB of scratch at ring 1023)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE configs[1]): one batch of --total proofs per step sharded over the GPUs; weak: --batch proofs per GPU per step")
+    ap.add_argument("--total", type=int, default=4096, help="proofs per step over all GPUs (strong scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="proofs per GPU per step; giving it selects --scaling weak (8192 = one full-width device pass)")
+    ap.add_argument("--saturated-batch", type=int, default=8192, help="also report the saturated operating point: this many proofs per GPU per step (0 = skip)")
+    ap.add_argument("--saturated-steps", type=int, default=3)
     ap.add_argument("--window-bits", type=int, default=int(os.environ.get("DOT_RING_B200_WINDOW_BITS", "16")),
                     help="fixed-base table window width; 0 = sized by the library. Default: 16-bit windows over GLV halves (16 additions per coefficient, 161 GB); "
                     "if that does not fit the run falls back to 14-bit windows with four 15-bit ones (18 additions, 106 GB)")
@@ -482,6 +636,10 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()
+    if args.batch is not None:
+        args.scaling = "weak"
+    elif args.scaling == "weak":
+        args.batch = 8192
     if args.glv is None:
         args.glv = int(os.environ.get("DOT_RING_B200_GLV", "1" if args.window_bits == 16 else "0"))
     if args.wide_windows is None:

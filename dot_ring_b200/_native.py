@@ -96,6 +96,7 @@ class Library:
         L.dr_ring_points.argtypes = [c_void_p, c_void_p, c_size_t]
         L.dr_ring_prove_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 10
         L.dr_ring_prove_phase_ms.argtypes = [c_void_p, POINTER(c_float * 6)]
+        L.dr_ring_prove_commit_kernel_ms.argtypes = [c_void_p, POINTER(c_float), POINTER(c_uint32)]
         L.dr_ring_witness_table_bits.argtypes = [c_void_p]
         L.dr_ring_witness_table_bits.restype = c_uint32
         L.dr_ctx_set_prove_chunk.argtypes = [c_void_p, c_size_t]
@@ -619,6 +620,8 @@ class NativeRing:
                 raise ValueError("ring keys must be 32 bytes")
         self.handle = c_void_p()
         self.domain_size = domain_size
+        self.time_calls = False
+        self.last_call_ms = 0.0
         lib = self.ctx.library
         lib.check(lib.lib.dr_ring_create(self.ctx.handle, srs.handle, ctypes.byref(p), b"".join(keys), len(keys), ctypes.byref(self.handle)))
 
@@ -669,11 +672,15 @@ class NativeRing:
                 raise ValueError("zk_rows must hold 12 field elements per proof")
             zk = b"".join(int(v).to_bytes(32, "little") for v in zk_rows)
         lib = self.ctx.library
+        if self.time_calls:  # one CUDA event pair on the ctx stream around the whole call (bench.py)
+            self.ctx.timer_start()
         lib.check(
             lib.lib.dr_ring_prove_batch(
                 self.ctx.handle, self.handle, n, blob, a_off, a_len, d_off, d_len, b"".join(secret_keys), rows, zk, proofs, status,
             )
         )
+        if self.time_calls:
+            self.last_call_ms = self.ctx.timer_stop()
         raw = proofs.raw
         return [raw[784 * i : 784 * i + 784] for i in range(n)], status[:n]
 
@@ -698,6 +705,12 @@ class NativeRing:
 
     def witness_table_bits(self) -> int:
         return int(self.ctx.library.lib.dr_ring_witness_table_bits(self.handle))
+
+    def commit_kernel_ms(self) -> tuple[float, int]:
+        """(device ms, launches) of the dense commit kernel `CommitBodyT` within the last prove call (CUDA events around the launches)."""
+        ms, n = c_float(), c_uint32()
+        self.ctx.library.check(self.ctx.library.lib.dr_ring_prove_commit_kernel_ms(self.ctx.handle, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
 
     def prove_phase_ms(self) -> list[float]:
         arr = (c_float * 6)()

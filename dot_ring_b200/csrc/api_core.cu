@@ -98,6 +98,7 @@ void ntt_device(Ctx* ctx, const NttPlan& plan, const Fr* in, Fr* out, size_t bat
 void PhaseTimer::mark(Ctx* ctx, int phase) {
     size_t i = phase_of.size();
     phase_of.push_back(phase);
+    if (phase != 6) current = phase;
 #if !defined(DR_HOST_EMULATION)
     if (events.size() <= i) {
         cudaEvent_t e;
@@ -112,6 +113,14 @@ void PhaseTimer::mark(Ctx* ctx, int phase) {
 #endif
 }
 
+int PhaseTimer::current_of(size_t i) const {
+    while (i > 0) {
+        i--;
+        if (phase_of[i] != 6) return phase_of[i] >= 0 && phase_of[i] < 6 ? phase_of[i] : 5;
+    }
+    return 5;
+}
+
 void PhaseTimer::collect(Ctx* ctx) {
     (void)ctx;
     for (size_t i = 0; i + 1 < phase_of.size(); i++) {
@@ -124,6 +133,7 @@ void PhaseTimer::collect(Ctx* ctx) {
         ms = std::chrono::duration<float, std::milli>(stamps[i + 1] - stamps[i]).count();
 #endif
         total[ph] += ms;
+        if (ph == 6) total[current_of(i)] += ms;  // the kernel-only span is part of its enclosing phase
     }
     phase_of.clear();
 }
@@ -209,10 +219,17 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
     }
     ctx->partials.ensure((size_t)batch * slices);
     const uint32_t threads = COMMIT_THREADS;
+    PhaseTimer& pt = ctx->phases;
+    const int enclosing = pt.current;
+    if (pt.active) {
+        pt.mark(ctx, 6);
+        pt.kernel_launches++;
+    }
     if (srs->geom.glv)
         launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
     else
         launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
+    if (pt.active) pt.mark(ctx, enclosing);
     launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
 }
 

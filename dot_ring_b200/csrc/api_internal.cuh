@@ -37,8 +37,11 @@ struct Ctx;
 
 // Accumulates device time per pipeline phase with events recorded between the launches.
 struct PhaseTimer {
-    static constexpr int NPH = 6;
-    float total[NPH] = {0, 0, 0, 0, 0, 0};
+    static constexpr int NPH = 7;  // 0..5: pipeline phases (dr_ring_prove_phase_ms); 6: the dense commit kernel alone (CommitBodyT launches)
+    float total[NPH] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t kernel_launches = 0;  // CommitBodyT launches counted into total[6]
+    bool active = false;           // between reset() and the last collect() of a prove call
+    int current = -1;
     std::vector<int> phase_of;  // phase that starts at mark i (-1 = end marker)
 #if !defined(DR_HOST_EMULATION)
     std::vector<cudaEvent_t> events;
@@ -48,9 +51,12 @@ struct PhaseTimer {
     void reset() {
         for (float& t : total) t = 0;
         phase_of.clear();
+        kernel_launches = 0;
+        current = -1;
     }
     void mark(Ctx* ctx, int phase);
     void collect(Ctx* ctx);
+    int current_of(size_t i) const;
 };
 
 struct Ctx {

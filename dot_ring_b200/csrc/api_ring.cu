@@ -325,6 +325,11 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     sc.ensure(pass_width, N);
     PhaseTimer& pt = ctx->phases;
     pt.reset();
+    pt.active = true;
+    struct Deactivate {
+        PhaseTimer& p;
+        ~Deactivate() { p.active = false; }
+    } deactivate{pt};
     const uint32_t nthr = ntt_threads(N);
     const size_t ntt_smem = ntt_smem_bytes(N);
     const bool large = N > 4096 || ctx->generic_ntt_path;  // two-pass transforms + element-wise twists instead of the fused single-CTA kernels
@@ -428,6 +433,15 @@ int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !out) throw Error(DR_EINVAL, "bad argument");
     for (int i = 0; i < 6; i++) out[i] = ctx->phases.total[i];
+    DR_API_END
+}
+
+int dr_ring_prove_commit_kernel_ms(dr_ctx* c, float* ms, uint32_t* launches) {
+    DR_API_BEGIN
+    Ctx* ctx = (Ctx*)c;
+    if (!ctx || !ms || !launches) throw Error(DR_EINVAL, "bad argument");
+    *ms = ctx->phases.total[6];
+    *launches = ctx->phases.kernel_launches;
     DR_API_END
 }
 

@@ -183,6 +183,20 @@ class PooledRingNative:
     def close(self) -> None:
         self.pool.map(lambda i: self.replicas[i].close())
 
+    @property
+    def time_calls(self) -> bool:
+        return self.replicas[0].time_calls
+
+    @time_calls.setter
+    def time_calls(self, on: bool) -> None:
+        for r in self.replicas:
+            r.time_calls = bool(on)
+
+    @property
+    def last_call_ms(self) -> float:
+        """Device time of the slowest replica's last prove call."""
+        return max(r.last_call_ms for r in self.replicas)
+
     def root(self) -> bytes:
         return self.replicas[0].root()
 
@@ -194,6 +208,10 @@ class PooledRingNative:
 
     def witness_table_bits(self) -> int:
         return self.replicas[0].witness_table_bits()
+
+    def commit_kernel_ms(self) -> tuple[float, int]:
+        per = self.pool.map(lambda i: self.replicas[i].commit_kernel_ms())
+        return max(per)
 
     def prove_phase_ms(self) -> list[float]:
         """Per-phase device time of the slowest replica's last call."""

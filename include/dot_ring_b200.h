@@ -177,6 +177,9 @@ int dr_ring_prove_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* blo
 /* Per-phase device time of the last dr_ring_prove_batch on this ctx (ms): [0] pedersen+witness, [1] interpolate,
  * [2] commits (all MSMs), [3] LDE+constraints+quotient, [4] evaluations+openings polys, [5] transcripts+assembly. */
 int dr_ring_prove_phase_ms(dr_ctx* ctx, float out[6]);
+/* Device time (CUDA events on the ctx stream, around the launches only) and launch count of the dominant kernel, the dense fixed-base
+ * commit `CommitBodyT`, within the last dr_ring_prove_batch on this ctx: 3 launches per pass (quotient + two openings). */
+int dr_ring_prove_commit_kernel_ms(dr_ctx* ctx, float* ms, uint32_t* launches);
 /* Window width of the table the sparse witness commitments of this ring read (built at the first proof; 0 before that). */
 uint32_t dr_ring_witness_table_bits(const dr_ring* ring);
 /* Proofs processed per internal pass (bounds device scratch: about 1 KiB * domain_size per proof). 0 = default 1024. */

@@ -25,30 +25,41 @@ def _run(cmd, timeout=900):
     return json.loads(lines[0])
 
 
-def _check_line(line, n_gpus, batch, steps):
+def _check_line(line, n_gpus, total, steps, scaling):
     for key in REQUIRED:
         assert key in line, key
     assert line["metric"] == "ring_vrf_proofs_per_s" and line["unit"] == "proofs/s"
-    assert line["n_gpus"] == n_gpus and line["steps"] == steps and line["scaling"] == "weak"
-    assert line["config"]["parity"].endswith(KA1_ROOT_SHA256_PREFIX)
-    assert abs(line["value"] * line["ms_per_step"] * 1e-3 - batch * n_gpus) < 1e-6 * batch * n_gpus
+    assert line["n_gpus"] == n_gpus and line["steps"] == steps and line["scaling"] == scaling
+    parity = line["config"]["parity"]
+    assert parity["ring_root_sha256"] == KA1_ROOT_SHA256_PREFIX and parity["equal"] is True and parity["golden_proofs"] == 2 and parity["verified_sample"] >= 1
+    assert line["config"]["total_proofs_per_step"] == total
+    assert abs(line["value"] * line["ms_per_step"] * 1e-3 - total) < 1e-6 * total
     assert line["gpu_launches"] > 0
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "algorithmic_reduction"} <= set(line["roofline"])
+    assert 0 < line["roofline"]["frac"] < 1.2 and line["roofline"]["kernel_launches_per_step"] == 3
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["e2e"]["value"] <= line["value"] * 1.001
 
 
 def test_bench_single_process_line():
     line = _run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4", "--no-cpu-baseline"])
-    _check_line(line, 1, 1, 1)
+    _check_line(line, 1, 1, 1, "weak")
 
 
 def test_bench_two_ranks_gloo():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29617",
-           "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4"]  # fmt: skip
+           "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "3", "--window-bits", "4"]  # fmt: skip
     line = _run(cmd)
-    _check_line(line, 2, 1, 1)
+    _check_line(line, 2, 3, 1, "strong")  # one batch of 3 proofs sharded 2 + 1 over the ranks
+    assert line["config"]["launch"].startswith("torchrun")
     assert "cpu_baseline" not in line  # rank 0 at N=1 only
+
+
+def test_bench_one_process_two_devices_pool():
+    """`python bench.py --gpus 2` without torchrun: one process, EnginePool over two (emulated) devices, strong scaling."""
+    line = _run([sys.executable, "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "2", "--window-bits", "4"])
+    _check_line(line, 2, 2, 1, "strong")
+    assert "EnginePool" in line["config"]["launch"]
 
 
 def test_bench_refuses_cpu_library_without_dryrun():
