@@ -205,7 +205,7 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
         ctx->partials.ensure(items);
         launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(ctas), COMMIT_THREADS, COMMIT_THREADS * sizeof(G1), CommitAffineBody(), (const G1Affine*)srs->table.p,
                                                   srs->geom, scalars, stride, n, batch, slices, sc, ctx->partials.p);
-        launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
+        launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
         return;
     }
     // enough CTAs to fill the machine: batch * slices >= ~2 waves of 148 SMs x 4 resident CTAs
@@ -230,7 +230,7 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
     else
         launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
     if (pt.active) pt.mark(ctx, enclosing);
-    launch(ctx->stream, Dim3((batch + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, slices, batch, out_affine);
+    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
 }
 
 }  // namespace dr
@@ -284,6 +284,9 @@ int dr_ctx_create(int device, dr_ctx** out) {
     if (device < 0 || device >= count) throw Error(DR_EINVAL, "no such CUDA device");
     DR_CUDA(cudaSetDevice(device));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DR_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     // Fix the per-thread stack once: kernels here need between 0 and ~16 KB of local memory, and letting the runtime grow the
     // backing store lazily costs a device-wide reallocation (hundreds of ms) whenever a larger kernel follows a smaller one.
     if (const char* e = getenv("DOT_RING_B200_STACK_BYTES")) {
@@ -295,6 +298,7 @@ int dr_ctx_create(int device, dr_ctx** out) {
     DR_CUDA(cudaEventCreate(&ctx->ev_stop));
 #else
     ctx->stream = 0;
+    ctx->side = 0;
 #endif
     *out = (dr_ctx*)ctx.release();
     DR_API_END
@@ -306,12 +310,16 @@ void dr_ctx_destroy(dr_ctx* c) {
 #if !defined(DR_HOST_EMULATION)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side);
 #endif
     ctx->plans.clear();
     ctx->release_scratch();
 #if !defined(DR_HOST_EMULATION)
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
 #endif
     delete ctx;

@@ -62,7 +62,10 @@ struct PhaseTimer {
 struct Ctx {
     int device = 0;
     Stream stream{};
+    // work that nothing on the main stream waits for until the end of a pass (second half of the Pedersen prover) runs here
+    Stream side{};
 #if !defined(DR_HOST_EMULATION)
+    cudaEvent_t ev_fork{}, ev_join{};
     cudaEvent_t ev_start{}, ev_stop{};
 #else
     std::chrono::steady_clock::time_point t_start;
@@ -100,6 +103,19 @@ struct Ctx {
     void activate() {
 #if !defined(DR_HOST_EMULATION)
         DR_CUDA(cudaSetDevice(device));
+#endif
+    }
+    // side stream: starts after everything queued on the main stream so far / main stream waits for everything queued on it
+    void fork_side() {
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaEventRecord(ev_fork, stream));
+        DR_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+#endif
+    }
+    void join_side() {
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaEventRecord(ev_join, side));
+        DR_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
 #endif
     }
     const NttPlan& plan(uint32_t n, const Fr& omega_mont);

@@ -359,8 +359,15 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         } else {
             launch(ctx->stream, Dim3((m * 12 + 127) / 128), 128, 0, ZkRowsBody(), (const uint8_t*)nullptr, sc.st.p, m);
         }
-        launch(ctx->stream, Dim3(pb), tb, 0, PedersenProveBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
-        launch(ctx->stream, Dim3(pb), tb, 0, WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
+        // Pedersen part: the half the ring proof needs (blinding factor, blinded key) on the main stream, two lanes per proof; the
+        // rest (nonces, R, Ok, responses) on the side stream, joined before the proofs are assembled
+        launch(ctx->stream, Dim3((2 * m + tb - 1) / tb), tb, tb * sizeof(TEAffine), PedersenStartBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
+        ctx->fork_side();
+        launch(ctx->side, Dim3((m + 31) / 32), 32, 0, PedersenFinishBody(), rg, (const ProveInput*)sc.in.p, sc.st.p, m);
+        {
+            const uint32_t wt = 4 * WIT_LANES;  // four proofs per block, a warp each
+            launch(ctx->stream, Dim3((m + 3) / 4), wt, witness_coop_smem(wt), WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
+        }
         pt.mark(ctx, 1);
         if (!large) {
             launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
@@ -376,7 +383,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
             ctx->partials.ensure((size_t)4 * m);
             launch_lb<64, 8>(ctx->stream, Dim3(4, m), 64, witness_commit_smem(ring->lag->geom.W, 64), WitnessCommitBody(), (const G1Affine*)ring->lag->table.p, ring->lag->geom, rg, (const ProofState*)sc.st.p,
                    ctx->partials.p);
-            launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, CommitFinishBody(), (const G1*)ctx->partials.p, 1u, 4 * m, sc.res.p);
+            launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, 1u, 4 * m, sc.res.p);
         }
         // column order (b, accx, accy, accip) -> payload slots (0, 2, 3, 1)
         launch(ctx->stream, Dim3((4 * m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 4u, 0x01030200u, sc.st.p, m);
@@ -418,12 +425,18 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         commit_device(ctx, ring->srs, sc.lin.p, N, N - 1, m, sc.res.p);
         launch(ctx->stream, Dim3((m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 1u, 0x06u, sc.st.p, m);
         pt.mark(ctx, 5);
+        ctx->join_side();
         launch(ctx->stream, Dim3(pb), tb, 0, FinalizeBody(), (const ProofState*)sc.st.p, m, sc.out.p, sc.status.p);
         pt.mark(ctx, -1);
+        dev_zero(ctx->stream, sc.in.p, m * sizeof(ProveInput));  // secret keys do not outlive the pass on the device
         d2h(ctx->stream, proofs784 + 784 * base, sc.out.p, (size_t)m * 784);
         d2h(ctx->stream, status + base, sc.status.p, (size_t)m * sizeof(uint32_t));
         stream_sync(ctx->stream);
         pt.collect(ctx);
+    }
+    {  // ... nor in the host staging buffer (volatile: the stores must not be optimised away)
+        volatile uint8_t* w = (volatile uint8_t*)hin.data();
+        for (size_t i = 0; i < hin.size() * sizeof(ProveInput); i++) w[i] = 0;
     }
     DR_API_END
 }

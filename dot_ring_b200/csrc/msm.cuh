@@ -616,19 +616,50 @@ struct CommitAffineBody {
     }
 };
 
-// Sum `slices` partials per MSM and normalise to affine.  One thread per MSM.
+// Sum `slices` partials per MSM and normalise to affine.  `lanes` (a power of two dividing the block size, <= 32) threads per
+// MSM: each folds a strided share of the slices, a shared-memory tree folds the lanes.  Small batches are cut into many slices
+// to fill the machine, and a serial fold of those was most of a single proof's latency.
+DR_HD uint32_t commit_finish_lanes(uint32_t slices) {
+    uint32_t l = 1;
+    while (l < slices && l < 32) l <<= 1;
+    return l;
+}
 struct CommitFinishBody {
-    DR_HD void operator()(const BlockCtx& ctx, const G1* partials, uint32_t slices, uint32_t batch, G1Affine* out) const {
+    DR_HD void operator()(const BlockCtx& ctx, const G1* partials, uint32_t slices, uint32_t batch, G1Affine* out, uint32_t lanes) const {
+        G1* sm = (G1*)ctx.smem;  // nthreads entries when lanes > 1
+        const uint32_t per_block = ctx.nthreads / lanes;
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t m = ctx.bx * ctx.nthreads + t;
+            const uint32_t m = ctx.bx * per_block + t / lanes, lane = t % lanes;
+            G1 acc = G1::inf();
             if (m < batch) {
-                G1 acc = partials[(size_t)m * slices];
-                for (uint32_t s = 1; s < slices; s++) g1_add(acc, partials[(size_t)m * slices + s]);
-                out[m] = g1_to_affine(acc);
+#pragma unroll 1
+                for (uint32_t s = lane; s < slices; s += lanes) g1_add(acc, partials[(size_t)m * slices + s]);
+                if (lanes == 1) out[m] = g1_to_affine(acc);
             }
+            if (lanes > 1) sm[t] = acc;
+        }
+        if (lanes == 1) return;
+        DR_BLOCK_SYNC();
+        for (uint32_t stride = lanes >> 1; stride > 0; stride >>= 1) {
+            DR_THREAD_LOOP(t, ctx) {
+                if ((t % lanes) < stride) {
+                    G1 a = sm[t];
+                    g1_add(a, sm[t + stride]);
+                    sm[t] = a;
+                }
+            }
+            DR_BLOCK_SYNC();
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t m = ctx.bx * per_block + t / lanes;
+            if ((t % lanes) == 0 && m < batch) out[m] = g1_to_affine(sm[t]);
         }
     }
 };
+inline void launch_commit_finish(Stream st, const G1* partials, uint32_t slices, uint32_t batch, G1Affine* out) {
+    const uint32_t lanes = commit_finish_lanes(slices), threads = 64, per_block = threads / lanes;
+    launch(st, Dim3((batch + per_block - 1) / per_block), threads, lanes > 1 ? threads * sizeof(G1) : 0, CommitFinishBody(), partials, slices, batch, out, lanes);
+}
 
 // affine (Montgomery) -> 96-byte uncompressed and/or 48-byte compressed zcash bytes
 struct G1EncodeBody {

@@ -49,6 +49,47 @@ struct RingDev {
     uint32_t hash_kind;  // 0: SHA-512 suite (XMD h2c, counter-mode squeeze), 1: SHAKE128 suite (XOF h2c, direct squeeze)
 };
 
+// The suite's transcript hash (primitives.py:26-55).  Absorb-only until squeezed; squeezing never disturbs the state, so a
+// copy can keep absorbing.  SHA-512 suites squeeze in counter mode (primitives.py:165-174: seed = H(absorbed),
+// block c = H(seed | le64(c))); the SHAKE128 suite squeezes the XOF directly.
+struct VrfHash {
+    uint32_t kind;
+    union {
+        Sha512 sha;
+        Shake128 shake;
+    };
+    DR_HD void init(uint32_t k) {
+        kind = k;
+        if (kind == 0) sha.init();
+        else shake.init();
+    }
+    DR_HD void update(const uint8_t* data, uint32_t len) {
+        if (kind == 0) sha.update(data, len);
+        else shake.absorb(data, len);
+    }
+    DR_HD void update_byte(uint8_t b) { update(&b, 1); }
+    DR_HD_COLD void squeeze(uint8_t* out, uint32_t size) const {
+        if (kind != 0) {
+            shake.squeeze_snapshot(out, size);
+            return;
+        }
+        Sha512 h = sha;
+        uint8_t seed[64];
+        h.final(seed);
+        uint32_t done = 0;
+        for (uint64_t c = 0; done < size; c++) {
+            Sha512 b;
+            b.init();
+            b.update(seed, 64);
+            uint8_t ctr[8];
+            for (int i = 0; i < 8; i++) ctr[i] = (uint8_t)(c >> (8 * i));
+            b.update(ctr, 8);
+            uint8_t blk[64];
+            b.final(blk);
+            for (uint32_t i = 0; i < 64 && done < size; i++) out[done++] = blk[i];
+        }
+    }
+};
 // Per-proof state (one element of an array in HBM).
 struct ProofState {
     uint32_t k;         // producer index
@@ -64,6 +105,10 @@ struct ProofState {
     Fr lzw;             // L(zeta * w)
     G1Affine commits[7];  // C_b, C_accip, C_accx, C_accy, C_q, Phi_zeta, Phi_zeta_w
     uint8_t pedersen[192];
+    // hand-over from the first half of the Pedersen prover (everything the ring proof needs) to the second half, which runs on a
+    // side stream next to the ring-proof pipeline
+    TEAffine vrf_input;  // hash-to-curve point
+    VrfHash vrf_tr;      // VRF transcript after the blinded key
 };
 
 struct ProveInput {  // host-packed per proof
@@ -108,47 +153,6 @@ DR_HD void shake_absorb_g1(Shake128& s, const G1Affine& p) {
     s.absorb(b, 96);
 }
 
-// The suite's transcript hash (primitives.py:26-55).  Absorb-only until squeezed; squeezing never disturbs the state, so a
-// copy can keep absorbing.  SHA-512 suites squeeze in counter mode (primitives.py:165-174: seed = H(absorbed),
-// block c = H(seed | le64(c))); the SHAKE128 suite squeezes the XOF directly.
-struct VrfHash {
-    uint32_t kind;
-    union {
-        Sha512 sha;
-        Shake128 shake;
-    };
-    DR_HD void init(uint32_t k) {
-        kind = k;
-        if (kind == 0) sha.init();
-        else shake.init();
-    }
-    DR_HD void update(const uint8_t* data, uint32_t len) {
-        if (kind == 0) sha.update(data, len);
-        else shake.absorb(data, len);
-    }
-    DR_HD void update_byte(uint8_t b) { update(&b, 1); }
-    DR_HD_COLD void squeeze(uint8_t* out, uint32_t size) const {
-        if (kind != 0) {
-            shake.squeeze_snapshot(out, size);
-            return;
-        }
-        Sha512 h = sha;
-        uint8_t seed[64];
-        h.final(seed);
-        uint32_t done = 0;
-        for (uint64_t c = 0; done < size; c++) {
-            Sha512 b;
-            b.init();
-            b.update(seed, 64);
-            uint8_t ctr[8];
-            for (int i = 0; i < 8; i++) ctr[i] = (uint8_t)(c >> (8 * i));
-            b.update(ctr, 8);
-            uint8_t blk[64];
-            b.final(blk);
-            for (uint32_t i = 0; i < 64 && done < size; i++) out[done++] = blk[i];
-        }
-    }
-};
 DR_HD void vrf_squeeze(const VrfHash& st, uint8_t* out, uint32_t size) { st.squeeze(out, size); }
 DR_HD void fn_to_le_bytes(uint8_t* out, const Fn& x_mont) {
     Fn x = x_mont.from_mont();
@@ -235,18 +239,17 @@ DR_HD TEAffine vrf_encode_to_curve(const S& rg, const uint8_t* msg, uint32_t msg
 }
 
 // ---- A. Pedersen VRF prove (pedersen/vrf.py:86-126) -------------------------------------------------------
-// Writes O | Ybar | R | Ok | s | sb; returns the public key, the blinded key and the blinding factor.
+// First half: everything up to the blinded key.  Writes O | Ybar into out192; returns the public key, the blinded key, the
+// blinding factor and the transcript state the second half continues from.  `input` is the hash-to-curve point.
 template <class S>
-DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint8_t* msg, uint32_t msg_len, const uint8_t* ad, uint32_t ad_len, uint8_t* out192,
-                                    TEAffine& pk, TEAffine& blinded, uint32_t* blinding_raw) {
+DR_HD_COLD void pedersen_prove_begin(const S& rg, const uint8_t* sk32, const TEAffine& input, const uint8_t* ad, uint32_t ad_len, uint8_t* out192, TEAffine& pk,
+                                     TEAffine& blinded, uint32_t* blinding_raw, VrfHash& tr) {
     Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
-    uint32_t xr[8], kr[8], kbr[8];
+    uint32_t xr[8];
     fn_raw_limbs(xr, x);
-    TEAffine input = vrf_encode_to_curve(rg, msg, msg_len);
     TEAffine output;
     te_to_affine2(te_mul_fixed(rg.g_tab, xr), te_mul_raw(input, xr, 8), pk, output);
     // vrf_transcript (primitives.py:102-144) with one I/O pair
-    VrfHash tr;
     tr.init(rg.hash_kind);
     tr.update(rg.suite_id, rg.suite_id_len);
     tr.update_byte(0x02);
@@ -264,6 +267,17 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     fn_raw_limbs(blinding_raw, b);
     blinded = te_to_affine(te_add(te_mul_fixed(rg.b_tab, blinding_raw), TEExt::from_affine(pk)));
     sha_absorb_point(tr, blinded);
+    te_encode(out192, output);
+    te_encode(out192 + 32, blinded);
+}
+// Second half: nonces, R, Ok, challenge, responses.  Writes R | Ok | s | sb into out192 + 64.
+template <class S>
+DR_HD_COLD void pedersen_prove_finish(const S& rg, const uint8_t* sk32, const TEAffine& input, const uint32_t* blinding_raw, const VrfHash& tr, uint8_t* out192) {
+    Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
+    Fn b = Fn::zero();
+    for (int i = 0; i < 8; i++) b.v[i] = blinding_raw[i];
+    b = b.to_mont();
+    uint32_t kr[8], kbr[8];
     Fn k = vrf_nonce(tr, x);
     Fn kb = vrf_nonce(tr, b);
     fn_raw_limbs(kr, k);
@@ -279,12 +293,19 @@ DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint
     Fn c = fp_from_le_bytes_mod<Fn>(cb, 16);
     Fn s = k + c * x;
     Fn sb = kb + c * b;
-    te_encode(out192, output);
-    te_encode(out192 + 32, blinded);
     te_encode(out192 + 64, R);
     te_encode(out192 + 96, ok);
     fn_to_le_bytes(out192 + 128, s);
     fn_to_le_bytes(out192 + 160, sb);
+}
+// Writes O | Ybar | R | Ok | s | sb; returns the public key, the blinded key and the blinding factor.
+template <class S>
+DR_HD_COLD void pedersen_prove_core(const S& rg, const uint8_t* sk32, const uint8_t* msg, uint32_t msg_len, const uint8_t* ad, uint32_t ad_len, uint8_t* out192,
+                                    TEAffine& pk, TEAffine& blinded, uint32_t* blinding_raw) {
+    TEAffine input = vrf_encode_to_curve(rg, msg, msg_len);
+    VrfHash tr;
+    pedersen_prove_begin(rg, sk32, input, ad, ad_len, out192, pk, blinded, blinding_raw, tr);
+    pedersen_prove_finish(rg, sk32, input, blinding_raw, tr, out192);
 }
 
 // Window table for te_mul_fixed: thread (w, c) of 32 x 16 writes the 16 entries d = 16c .. 16c + 15 of window w.
@@ -313,16 +334,31 @@ struct TeFixedTableBody {
     }
 };
 
-// one thread per proof
-struct PedersenProveBody {
+// First half of the Pedersen prover, two threads per proof: the two Elligator 2 maps of hash-to-curve (the longest serial chains of
+// the prover: a field inversion and a square root each) run side by side, then the even lane carries on alone.
+struct PedersenStartBody {
     DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProveInput* in, const uint8_t* blob, ProofState* st, uint32_t count) const {
+        TEAffine* maps = (TEAffine*)ctx.smem;  // [nthreads]
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t p = ctx.bx * ctx.nthreads + t;
+            uint32_t p = (ctx.bx * ctx.nthreads + t) >> 1;
             if (p < count) {
                 const ProveInput& pi = in[p];
+                uint8_t u[96];
+                h2c_uniform_bytes(rg, blob + pi.alpha_off, pi.alpha_len, u);
+                maps[t] = te_map_to_curve_ell2(fr_from_be48_mod(u + 48 * (t & 1)));
+            }
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t p = (ctx.bx * ctx.nthreads + t) >> 1;
+            if (p < count && !(t & 1)) {
+                const ProveInput& pi = in[p];
                 ProofState& ps = st[p];
+                // te_affine_point.py:213-222: 4 * (map(u0) + map(u1))
+                TEExt sum = te_add(TEExt::from_affine(maps[t]), TEExt::from_affine(maps[t + 1]));
+                ps.vrf_input = te_to_affine(te_dbl(te_dbl(sum)));
                 TEAffine pk, blinded;
-                pedersen_prove_core(rg, pi.sk, blob + pi.alpha_off, pi.alpha_len, blob + pi.ad_off, pi.ad_len, ps.pedersen, pk, blinded, ps.t);
+                pedersen_prove_begin(rg, pi.sk, ps.vrf_input, blob + pi.ad_off, pi.ad_len, ps.pedersen, pk, blinded, ps.t, ps.vrf_tr);
                 ps.k = pi.k;
                 ps.relation = blinded;
                 // producer_key must be pk(sk) and sit at row k of the ring (vrf/ring/vrf.py:196-197, members.py:71-81)
@@ -331,47 +367,94 @@ struct PedersenProveBody {
         }
     }
 };
-
-// ---- B. witness accumulators (columns.py:127-146), one thread per proof -----------------------------------
-// acc_0 = seed; the only rows that change it are row k (adds PK_k) and the 253 bit rows (add 2^j * B when
-// bit j of the blinding factor is set).  The chain is walked in extended coordinates twice around ONE
-// field inversion (Montgomery's trick over the 254 Z coordinates) to obtain the affine values the
-// reference computes with one inversion per addition.
-struct WitnessBody {
-    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, ProofState* st, uint32_t count, const Shake128* prefix) const {
+// Second half, one thread per proof; nothing of the ring proof depends on it, so it runs on the side stream.
+struct PedersenFinishBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProveInput* in, ProofState* st, uint32_t count) const {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t p = ctx.bx * ctx.nthreads + t;
             if (p < count) {
                 ProofState& ps = st[p];
-                uint32_t k = ps.k < rg.max_ring ? ps.k : 0;
-                const TEExt a0 = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(rg.nm[k]));
-                // walk 1: stash Z_j in s[j].x and the prefix product Z_a0 * prod_{i<j} Z_i in s[j].y
-                TEExt acc = a0;
-                Fr prefix_prod = a0.Z;
+                pedersen_prove_finish(rg, in[p].sk, ps.vrf_input, ps.t, ps.vrf_tr, ps.pedersen);
+            }
+        }
+    }
+};
+
+// ---- B. witness accumulators (columns.py:127-146), 32 threads per proof ------------------------------------
+// acc_0 = seed; the only rows that change it are row k (adds PK_k) and the 253 bit rows (add 2^j * B when bit j of the blinding
+// factor is set).  The 253 running sums are a prefix scan over group elements: lane l owns bit rows 8l .. 8l+7, sums them,
+// the lane totals are scanned in five rounds through shared memory, and each lane then walks its rows from its offset.  The affine
+// values the reference computes with one inversion per addition come from one inversion per lane (Montgomery's trick over the
+// lane's rows; the 32 inversions of a proof run side by side).
+constexpr uint32_t WIT_LANES = 32, WIT_ROWS = 8;
+static_assert(WIT_LANES * WIT_ROWS >= SCALAR_BITS, "every bit row needs a lane");
+DR_HD size_t witness_coop_smem(uint32_t threads) { return (size_t)2 * threads * sizeof(TEExt); }
+struct WitnessBody {
+    DR_HD void operator()(const BlockCtx& ctx, RingDev rg, ProofState* st, uint32_t count, const Shake128* prefix) const {
+        TEExt* sm = (TEExt*)ctx.smem;  // two scan buffers of nthreads entries
+        const uint32_t T = ctx.nthreads, ppb = T / WIT_LANES;
+        auto bit_of = [](const ProofState& ps, uint32_t j) { return (ps.t[j >> 5] >> (j & 31)) & 1u; };
+        // 1. lane totals (lane 0 starts from a0 = seed + PK_k)
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t lane = t % WIT_LANES, p = ctx.bx * ppb + t / WIT_LANES;
+            TEExt acc = TEExt::identity();
+            if (p < count) {
+                const ProofState& ps = st[p];
+                if (lane == 0) acc = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(rg.nm[ps.k < rg.max_ring ? ps.k : 0]));
 #pragma unroll 1
-                for (uint32_t j = 0; j < SCALAR_BITS; j++) {
-                    if ((ps.t[j >> 5] >> (j & 31)) & 1) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
-                    ps.s[j].x = acc.Z;
-                    ps.s[j].y = prefix_prod;
-                    prefix_prod = prefix_prod * acc.Z;
-                }
-                Fr inv_run = prefix_prod.inv();
-                // backward sweep: s[j].y <- 1 / Z_j
+                for (uint32_t j = lane * WIT_ROWS; j < (lane + 1) * WIT_ROWS && j < SCALAR_BITS; j++)
+                    if (bit_of(ps, j)) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
+            }
+            sm[t] = acc;
+        }
+        DR_BLOCK_SYNC();
+        // 2. inclusive scan over the lanes of every proof (ping-pong between the two buffers)
+        uint32_t cur = 0;
+        for (uint32_t d = 1; d < WIT_LANES; d <<= 1) {
+            DR_THREAD_LOOP(t, ctx) {
+                const uint32_t lane = t % WIT_LANES;
+                TEExt a = sm[cur * T + t];
+                if (lane >= d) a = te_add(a, sm[cur * T + t - d]);
+                sm[(cur ^ 1) * T + t] = a;
+            }
+            DR_BLOCK_SYNC();
+            cur ^= 1;
+        }
+        // 3. walk the lane's rows from the sum of everything before them; affine through one inversion per lane
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t lane = t % WIT_LANES, p = ctx.bx * ppb + t / WIT_LANES;
+            if (p < count) {
+                ProofState& ps = st[p];
+                const TEExt a0 = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(rg.nm[ps.k < rg.max_ring ? ps.k : 0]));
+                TEExt acc = lane ? sm[cur * T + t - 1] : a0;
+                Fr zs[WIT_ROWS], pre[WIT_ROWS];
+                Fr run = lane ? Fr::one() : a0.Z;
+                uint32_t rows = 0;
 #pragma unroll 1
-                for (int j = (int)SCALAR_BITS - 1; j >= 0; j--) {
-                    Fr zj = ps.s[j].x;
-                    ps.s[j].y = inv_run * ps.s[j].y;
-                    inv_run = inv_run * zj;
+                for (uint32_t j = lane * WIT_ROWS; j < (lane + 1) * WIT_ROWS && j < SCALAR_BITS; j++, rows++) {
+                    if (bit_of(ps, j)) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
+                    ps.s[j] = {acc.X, acc.Y};  // projective for now
+                    zs[rows] = acc.Z;
+                    pre[rows] = run;
+                    run = run * acc.Z;
                 }
-                ps.a0 = {a0.X * inv_run, a0.Y * inv_run};  // inv_run == 1 / Z_a0
-                // walk 2: affine accumulator values
-                acc = a0;
+                Fr inv_run = run.inv();
 #pragma unroll 1
-                for (uint32_t j = 0; j < SCALAR_BITS; j++) {
-                    if ((ps.t[j >> 5] >> (j & 31)) & 1) acc = te_add(acc, TEExt::from_affine(rg.nm[rg.max_ring + j]));
-                    Fr zi = ps.s[j].y;
-                    ps.s[j] = {acc.X * zi, acc.Y * zi};
+                for (uint32_t i = rows; i-- > 0;) {
+                    const uint32_t j = lane * WIT_ROWS + i;
+                    Fr zi = inv_run * pre[i];
+                    inv_run = inv_run * zs[i];
+                    ps.s[j] = {ps.s[j].x * zi, ps.s[j].y * zi};
                 }
+                if (lane == 0) ps.a0 = {a0.X * inv_run, a0.Y * inv_run};  // inv_run == 1 / Z_a0
+            }
+        }
+        DR_BLOCK_SYNC();
+        // 4. consistency check and transcript start, one lane per proof
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t lane = t % WIT_LANES, p = ctx.bx * ppb + t / WIT_LANES;
+            if (p < count && lane == 0) {
+                ProofState& ps = st[p];
                 // the accumulator must end at seed + relation (proof_builder.py:66-69)
                 TEExt chk = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(ps.relation));
                 if (!te_ext_eq_affine(chk, ps.s[SCALAR_BITS - 1])) ps.status |= 2u;

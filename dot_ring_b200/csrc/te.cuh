@@ -183,23 +183,27 @@ DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
 // ---- square roots in Fr (2-adicity 32) ---------------------------------------------------------
 // Returns false when `a` is a non-residue.  Which of the two roots comes back is unspecified; every
 // caller normalises the sign (x-recover orders the candidates, Elligator fixes the parity).
-DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
-    if (a.is_zero()) {
-        out = a;
-        return true;
-    }
+// Split in two so that Elligator 2 can try a and 5a with ONE exponentiation: begin() raises to the odd part of the group
+// order, finish() is the Tonelli-Shanks descent over the 2^32 roots of unity.
+struct FrSqrtState {
+    Fr x, t;  // a^((q+1)/2), a^q   (p - 1 = q * 2^32)
+};
+DR_HD_COLD FrSqrtState fr_sqrt_begin(const Fr& a) {
     constexpr uint32_t e_c[8] = DR_FR_TS_QM1_HALF;
-    constexpr uint32_t c_c[8] = DR_FR_TS_C;
     uint32_t e[8];
-    Fr c;
 #pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        e[i] = e_c[i];
-        c.v[i] = c_c[i];
-    }
+    for (int i = 0; i < 8; i++) e[i] = e_c[i];
     Fr w = a.pow(e, 8);  // a^((q-1)/2)
     Fr x = a * w;        // a^((q+1)/2)
-    Fr t = x * w;        // a^q
+    return {x, x * w};   // a^q
+}
+// false: the operand (non-zero) is a non-residue
+DR_HD_COLD bool fr_sqrt_finish(Fr& out, const FrSqrtState& st) {
+    constexpr uint32_t c_c[8] = DR_FR_TS_C;
+    Fr c;
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) c.v[i] = c_c[i];
+    Fr x = st.x, t = st.t;
     int m = 32;
     Fr one = Fr::one();
 #pragma unroll 1
@@ -222,6 +226,24 @@ DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
     }
     out = x;
     return true;
+}
+// the state of 5a from the state of a: (5a)^((q+1)/2) = 5^((q+1)/2) a^((q+1)/2), (5a)^q = 5^q a^q
+DR_HD FrSqrtState fr_sqrt_times5(const FrSqrtState& st) {
+    constexpr uint32_t zh_c[8] = DR_FR_TS_Z_HALF;
+    constexpr uint32_t zq_c[8] = DR_FR_TS_C;
+    Fr zh, zq;
+    for (int i = 0; i < 8; i++) {
+        zh.v[i] = zh_c[i];
+        zq.v[i] = zq_c[i];
+    }
+    return {st.x * zh, st.t * zq};
+}
+DR_HD_COLD bool fr_sqrt(Fr& out, const Fr& a) {
+    if (a.is_zero()) {
+        out = a;
+        return true;
+    }
+    return fr_sqrt_finish(out, fr_sqrt_begin(a));
 }
 
 DR_HD_COLD bool fr_is_square(const Fr& a) {
@@ -293,17 +315,28 @@ DR_HD_COLD TEAffine te_map_to_curve_ell2(const Fr& u) {
     Fr a_over_b = fr_const(aob_c), inv_b2 = fr_const(ib2_c), mb = fr_const(b_c);
     Fr one = Fr::one();
     Fr tv1 = fr_mul5(u.sqr());  // Z = 5
-    if (tv1 == one.neg()) tv1 = Fr::zero();
+    const bool exceptional = tv1 == one.neg();
+    if (exceptional) tv1 = Fr::zero();
     Fr x1 = a_over_b.neg() * (tv1 + one).inv();
     Fr gx1 = ((x1 + a_over_b) * x1 + inv_b2) * x1;
     Fr x2 = x1.neg() - a_over_b;
-    Fr gx2 = tv1 * gx1;
-    Fr y;
-    bool e2 = fr_sqrt(y, gx1);
+    Fr y = Fr::zero();
+    bool e2 = true;
     Fr x = x1;
-    if (!e2) {
-        x = x2;
-        fr_sqrt(y, gx2);  // exactly one of gx1, gx2 is a square
+    if (!gx1.is_zero()) {
+        // exactly one of gx1, gx2 = 5 u^2 gx1 is a square, and sqrt(gx2) = u sqrt(5 gx1) comes out of the same exponentiation
+        FrSqrtState st = fr_sqrt_begin(gx1);
+        e2 = fr_sqrt_finish(y, st);
+        if (!e2) {
+            x = x2;
+            if (exceptional) {
+                fr_sqrt(y, tv1 * gx1);  // gx2 = 0
+            } else {
+                Fr r;
+                fr_sqrt_finish(r, fr_sqrt_times5(st));
+                y = u * r;
+            }
+        }
     }
     bool e3 = (y.from_mont().v[0] & 1) != 0;
     if (e2 != e3) y = y.neg();

@@ -303,6 +303,7 @@ def main() -> None:
     c.append(f"#define DR_ELL2_INV_B2 {m8(pow(mont_b * mont_b, -1, P))}")
     c.append(f"#define DR_ELL2_B {m8(mont_b)}")
     c.append(f"#define DR_FR_TS_C {m8(pow(5, q, P))}  // 5^q: generator of the 2^32 roots of unity")
+    c.append(f"#define DR_FR_TS_Z_HALF {m8(pow(5, (q + 1) // 2, P))}  // 5^((q+1)/2): turns the Tonelli-Shanks state of a into that of 5a")
     c.append(f"#define DR_FR_TS_QM1_HALF {raw8((q - 1) // 2)}  // (q-1)/2, raw limbs")
     c.append(f"#define DR_FR_PM1_HALF {raw8((P - 1) // 2)}  // (p-1)/2, raw limbs")
     c.append(f"#define DR_FN_RAW {raw8(FIELDS['fn'])}")
