@@ -105,6 +105,17 @@ struct Ctx {
         DR_CUDA(cudaSetDevice(device));
 #endif
     }
+    uint32_t sm_count_cached = 0;
+    uint32_t sm_count() {
+        if (!sm_count_cached) {
+            sm_count_cached = 148;
+#if !defined(DR_HOST_EMULATION)
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) sm_count_cached = (uint32_t)v;
+#endif
+        }
+        return sm_count_cached;
+    }
     // side stream: starts after everything queued on the main stream so far / main stream waits for everything queued on it
     void fork_side() {
 #if !defined(DR_HOST_EMULATION)

@@ -102,6 +102,67 @@ __global__ void mb_g1_madd(G1* out, const G1Affine* pts, uint32_t npts, int iter
     for (int i = 0; i < iters; i++) g1_madd(acc, pts[(tid + 1 + i) % npts]);
     out[tid] = acc;
 }
+// FP64 pipe next to the int32 pipe: 8 independent DFMA chains, and the same interleaved with 8 IMAD chains in one thread
+__global__ void mb_dfma(double* out, uint32_t seed, int iters) {
+    double a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    const double m = 1.0000001;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            a0 = fma(a0, m, a1);
+            a1 = fma(a1, m, a2);
+            a2 = fma(a2, m, a3);
+            a3 = fma(a3, m, a4);
+            a4 = fma(a4, m, a5);
+            a5 = fma(a5, m, a6);
+            a6 = fma(a6, m, a7);
+            a7 = fma(a7, m, a0);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void mb_imad_dfma(double* out, uint32_t seed, int iters) {
+    double a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7;
+    uint32_t b0 = seed + threadIdx.x, b1 = b0 * 3, b2 = b0 * 5, b3 = b0 * 7, b4 = b0 * 11, b5 = b0 * 13, b6 = b0 * 17, b7 = b0 * 19;
+    const double m = 1.0000001;
+    const uint32_t mi = seed | 1;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            // 8 IMAD + 4 DFMA per round: the issue port is shared, the pipes are not
+            b0 = b0 * mi + b1;
+            a0 = fma(a0, m, a1);
+            b1 = b1 * mi + b2;
+            b2 = b2 * mi + b3;
+            a1 = fma(a1, m, a2);
+            b3 = b3 * mi + b4;
+            b4 = b4 * mi + b5;
+            a2 = fma(a2, m, a3);
+            b5 = b5 * mi + b6;
+            b6 = b6 * mi + b7;
+            a3 = fma(a3, m, a0);
+            b7 = b7 * mi + b0;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + (double)(b0 ^ b1 ^ b2 ^ b3 ^ b4 ^ b5 ^ b6 ^ b7);
+}
+// latency of ONE dependent chain per thread (what the one-thread-per-item kernels are bound by): x <- x * x
+template <class F>
+__global__ void mb_field_chain(F* out, uint32_t seed, int iters) {
+    F x = F::one();
+    x.v[0] ^= seed + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) x = x.sqr();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+template <class F>
+__global__ void mb_field_inv(F* out, uint32_t seed, int iters) {
+    F x = F::one();
+    x.v[0] ^= seed + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) x = x.inv() + F::one();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
 #endif
 
 }  // namespace dr
@@ -158,7 +219,8 @@ int dr_field_op(dr_ctx* c, int field, int op, const uint8_t* a, const uint8_t* b
     return DR_OK;
 }
 
-// kind: 0 IMAD (32-bit mad.lo), 1 IMAD.WIDE (32x32+64), 2 Fq mul, 3 Fr mul, 4 G1 mixed add.
+// kind: 0 IMAD (32-bit mad.lo), 1 IMAD.WIDE (32x32+64), 2 Fq mul, 3 Fr mul, 4 G1 mixed add, 5 DFMA, 6 IMAD + DFMA interleaved (2 : 1),
+// 7 / 8 one dependent Fr / Fq squaring chain per warp, one warp per SM (latency), 9 / 10 the same for Fr / Fq inversions.
 // Returns operations per second over the whole chip and the elapsed ms.
 int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_out) {
 #if defined(DR_HOST_EMULATION)
@@ -171,8 +233,9 @@ int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_o
         ctx->activate();
         cudaDeviceProp prop;
         DR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
-        const int threads = 256;
-        const int blocks = prop.multiProcessorCount * (kind >= 2 ? 2 : 8);
+        // kinds 7..10 measure latency: one warp per SM, so nothing hides the dependent chain
+        const int threads = kind >= 7 ? 32 : 256;
+        const int blocks = prop.multiProcessorCount * (kind >= 7 ? 1 : kind >= 2 && kind <= 4 ? 2 : 8);
         size_t nthreads = (size_t)blocks * threads;
         DevBuf<uint8_t> out(nthreads * sizeof(G1));
         DevBuf<G1Affine> pts;
@@ -203,6 +266,12 @@ int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_o
                 case 2: mb_field_mul<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 4.0 * iters; break;
                 case 3: mb_field_mul<Fr><<<blocks, threads, 0, ctx->stream>>>((Fr*)out.p, 12345u, iters); per_thread = 4.0 * iters; break;
                 case 4: mb_g1_madd<<<blocks, threads, 0, ctx->stream>>>((G1*)out.p, pts.p, 256u, iters); per_thread = 1.0 * iters; break;
+                case 5: mb_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)out.p, 12345u, iters); per_thread = 64.0 * iters; break;
+                case 6: mb_imad_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)out.p, 12345u, iters); per_thread = 96.0 * iters; break;  // 64 IMAD + 32 DFMA
+                case 7: mb_field_chain<Fr><<<blocks, threads, 0, ctx->stream>>>((Fr*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
+                case 8: mb_field_chain<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
+                case 9: mb_field_inv<Fr><<<blocks, threads, 0, ctx->stream>>>((Fr*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
+                case 10: mb_field_inv<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
                 default: throw Error(DR_EINVAL, "unknown micro-benchmark");
             }
             DR_CUDA(cudaGetLastError());

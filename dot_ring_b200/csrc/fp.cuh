@@ -476,6 +476,56 @@ struct alignas(16) Fp {
         bit.v[f >> 5] = 1u << (f & 31);
         return y * bit;
     }
+    // Quadratic character of the element: 1 (non-zero square), -1 (non-square), 0 (zero), by the binary Jacobi algorithm (shifts and
+    // subtractions on N-limb integers, branch-free steps like inv()).  The Montgomery factor 2^(32 N) is an even power of two, a
+    // square, so the symbol is taken straight from the Montgomery limbs.
+    DR_HD_COLD int legendre() const {
+        uint32_t a[N], n[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            a[i] = v[i];
+            n[i] = T::mod(i);
+        }
+        uint32_t flip = 0;  // parity of the sign changes
+#pragma unroll 1
+        for (;;) {
+            uint32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) nz |= a[i];
+            if (!nz) break;
+            const bool odd = a[0] & 1u;
+            // d = a - n (borrow <=> a < n)
+            uint32_t d[N], borrow = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                uint64_t t = (uint64_t)a[i] - n[i] - borrow;
+                d[i] = (uint32_t)t;
+                borrow = (uint32_t)(t >> 32) & 1u;
+            }
+            const bool swap = odd && borrow;  // a < n, both odd: (a / n) = (n / a) * (-1)^((a-1)(n-1)/4)
+            if (swap) flip ^= ((a[0] & 3u) == 3u && (n[0] & 3u) == 3u) ? 1u : 0u;
+            uint32_t ncarry = 1;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                uint64_t neg = (uint64_t)(~d[i]) + ncarry;  // n - a
+                ncarry = (uint32_t)(neg >> 32);
+                const uint32_t big = swap ? (uint32_t)neg : d[i];  // |a - n|
+                const uint32_t small = swap ? a[i] : n[i];
+                a[i] = odd ? big : a[i];
+                n[i] = odd ? small : n[i];
+            }
+            // a is even now (it was, or it is a difference of two odd numbers): halve, (2 / n) = -1 iff n = 3, 5 mod 8
+            const uint32_t r = n[0] & 7u;
+            flip ^= (r == 3u || r == 5u) ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < N; i++) a[i] = (a[i] >> 1) | (i + 1 < N ? a[i + 1] << 31 : 0u);
+        }
+        uint32_t rest = n[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; i++) rest |= n[i];
+        if (rest) return 0;  // gcd != 1: the element is zero (the modulus is prime)
+        return flip ? -1 : 1;
+    }
     DR_HD static Fp from_u32(uint32_t x) {
         Fp r = zero();
         r.v[0] = x;

@@ -173,11 +173,36 @@ DR_HD_COLD TEExt te_msm_small(const TEAffine* pts, const uint32_t (*ks)[8], int 
     return acc;
 }
 
-DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
+// [n]P == O the long way (kept as the cross-check of te_in_prime_subgroup in the unit tests)
+DR_HD_COLD bool te_in_prime_subgroup_by_order(const TEAffine& p) {
     constexpr uint32_t n[8] = DR_FN_RAW;
     uint32_t k[8];
     for (int i = 0; i < 8; i++) k[i] = n[i];
-    return te_mul_raw(p, k, 8).is_identity();
+    const TEExt r = te_mul_raw(p, k, 8);
+    return !r.Z.is_zero() && r.is_identity();
+}
+// Membership in the prime-order subgroup for a point ON the curve, by 2-descent instead of a 253-bit multiplication.
+// a and d are both non-squares, so a d is a square, the curve has full rational 2-torsion and E(Fr) = Z2 x Z2 x Z_n: the prime
+// subgroup is exactly 2E, and P is in 2E iff the three descent values of its Montgomery image u = (1 + y) / (1 - y),
+//   B u,  B (u - u+),  B (u - u-)      (u+-: the roots of u^2 + A u + 1; their product is a square already)
+// are squares.  In Edwards coordinates, with s = sqrt(a d):
+//   (a - d)(a - d y^2)  and  2 (1 - y) ((a - s) - (d - s) y)   are both non-zero squares.
+// Two Legendre symbols (binary Jacobi algorithm) replace ~2700 field multiplications; the reference multiplies by the order
+// (curve.py:56-67), the verdict is the same.  x = 0 holds the identity (in) and the 2-torsion point (0, -1) (out).
+DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
+    constexpr uint32_t amd_c[8] = DR_TE_A_MINUS_D, ams_c[8] = DR_TE_A_MINUS_S, dms_c[8] = DR_TE_D_MINUS_S;
+    if (p.x.is_zero()) return p.y == Fr::one();
+    Fr amd, ams, dms;
+    for (int i = 0; i < 8; i++) {
+        amd.v[i] = amd_c[i];
+        ams.v[i] = ams_c[i];
+        dms.v[i] = dms_c[i];
+    }
+    const Fr one = Fr::one();
+    const Fr c1 = amd * (fr_mul5(one).neg() - te_d() * p.y.sqr());
+    if (c1.legendre() != 1) return false;
+    const Fr c2 = (one - p.y).dbl() * (ams - dms * p.y);
+    return c2.legendre() == 1;
 }
 
 // ---- square roots in Fr (2-adicity 32) ---------------------------------------------------------

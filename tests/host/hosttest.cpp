@@ -56,6 +56,24 @@ int ht_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fr_out(out, r);
     return ok;
 }
+// field: 0 Fq (48-byte big-endian), 1 Fr (32-byte little-endian).  inv: out = Kaliski inverse, out2 = Fermat inverse; returns the Legendre symbol
+int ht_inv_and_legendre(int field, const uint8_t* a, uint8_t* out, uint8_t* out2) {
+    if (field == 0) {
+        Fq x = fq_in(a);
+        fq_out(out, x.inv());
+        fq_out(out2, x.inv_fermat());
+        return x.legendre();
+    }
+    Fr x = fr_in(a);
+    fr_out(out, x.inv());
+    fr_out(out2, x.inv_fermat());
+    return x.legendre();
+}
+// prime-subgroup membership of an on-curve point, both ways: bit 0 = 2-descent (two Legendre symbols), bit 1 = multiplication by the order
+int ht_te_subgroup(const uint8_t* xy64) {
+    TEAffine p{fr_in(xy64), fr_in(xy64 + 32)};
+    return (te_in_prime_subgroup(p) ? 1 : 0) | (te_in_prime_subgroup_by_order(p) ? 2 : 0);
+}
 // reduce len bytes (little-endian) mod the Bandersnatch group order; out 32 LE
 void ht_fn_from_bytes_mod(const uint8_t* in, int len, uint8_t* out) {
     Fn x = fp_from_le_bytes_mod<Fn>(in, len).from_mont();

@@ -13,6 +13,7 @@ import pytest
 
 from oracle import bandersnatch as bs
 from oracle import bls12_381 as bls
+from oracle import fr
 from tests.helpers import load
 
 HERE = Path(__file__).resolve().parent / "host"
@@ -137,6 +138,46 @@ def test_batched_affine_round_exceptional_cases(lib):
     lib.ht_affine_round(data, 2 * len(pairs), out)
     for i, (x, y) in enumerate(pairs):
         assert out.raw[96 * i : 96 * i + 96] == bls.g1_serialize(bls.g1_add(x, y)), i
+
+
+def test_kaliski_inverse_and_legendre_symbol(lib):
+    """fp.cuh inv() (binary Montgomery inverse) against Fermat's x^(p-2) and Python's pow; legendre() against Euler's criterion."""
+    rng = random.Random(12)
+    for field, mod, size, order in ((0, bls.P, 48, "big"), (1, fr.R, 32, "little")):
+        edge = [0, 1, 2, 3, 4, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 200, (1 << 32) - 1, 1 << 32]
+        for v in edge + [rng.randrange(mod) for _ in range(300)]:
+            out, out2 = _buf(size), _buf(size)
+            sym = lib.ht_inv_and_legendre(field, v.to_bytes(size, order), out, out2)
+            want = pow(v, -1, mod) if v else 0
+            assert int.from_bytes(out.raw, order) == want == int.from_bytes(out2.raw, order), (field, v)
+            euler = 0 if v == 0 else (1 if pow(v, (mod - 1) // 2, mod) == 1 else -1)
+            assert sym == euler, (field, v)
+
+
+def test_subgroup_test_by_two_descent(lib):
+    """te.cuh te_in_prime_subgroup: two Legendre symbols must agree with [n]P == O on points of all four cosets of E / 2E,
+    on the identity and on the 2-torsion point (0, -1)."""
+    rng = random.Random(13)
+    seen = {1: 0, 0: 0}
+    t2 = (0, bs.P - 1)
+    for _ in range(60):
+        while True:
+            y = rng.randrange(bs.P)
+            den = (bs.A - bs.D * y * y) % bs.P
+            x = bs.fr_sqrt((1 - y * y) * pow(den, -1, bs.P) % bs.P) if den else None
+            if x is not None:
+                break
+        for pt in ((x, y), (bs.P - x, y)):
+            got = lib.ht_te_subgroup(pt[0].to_bytes(32, "little") + pt[1].to_bytes(32, "little"))
+            assert got in (0, 3), (pt, got)
+            seen[got & 1] += 1
+            if got == 3:  # P in the subgroup: P + (0, -1) = (-x, -y) is not
+                q = ((-pt[0]) % bs.P, (-pt[1]) % bs.P)
+                assert lib.ht_te_subgroup(q[0].to_bytes(32, "little") + q[1].to_bytes(32, "little")) == 0
+    assert seen[1] > 5 and seen[0] > 20
+    g = bs.mul(bs.GENERATOR, 12345)
+    enc = lambda p: p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little")  # noqa: E731
+    assert lib.ht_te_subgroup(enc(g)) == 3 and lib.ht_te_subgroup(enc(bs.IDENTITY)) == 3 and lib.ht_te_subgroup(enc(t2)) == 0
 
 
 def test_bandersnatch_against_reference_goldens(lib):

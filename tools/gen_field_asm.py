@@ -297,6 +297,20 @@ def main() -> None:
         q //= 2
         s2 += 1
     assert s2 == 32 and pow(5, (P - 1) // 2, P) == P - 1
+    # prime-subgroup test by 2-descent (te.cuh te_in_prime_subgroup): s = sqrt(a d) exists because a and d are both non-squares
+    s_ad = pow(te_a * te_d % P, (q + 1) // 2, P)
+    t_ad, cc, mm = pow(te_a * te_d % P, q, P), pow(5, q, P), 32
+    while t_ad != 1:  # Tonelli-Shanks
+        i, t2 = 0, t_ad
+        while t2 != 1:
+            t2, i = t2 * t2 % P, i + 1
+        b = pow(cc, 1 << (mm - i - 1), P)
+        s_ad, cc, mm = s_ad * b % P, b * b % P, i
+        t_ad = t_ad * cc % P
+    assert s_ad * s_ad % P == te_a * te_d % P
+    c.append(f"#define DR_TE_A_MINUS_D {m8(te_a - te_d)}")
+    c.append(f"#define DR_TE_A_MINUS_S {m8(te_a - s_ad)}  // a - sqrt(a d)")
+    c.append(f"#define DR_TE_D_MINUS_S {m8(te_d - s_ad)}  // d - sqrt(a d)")
     c.append(f"#define DR_TE_D {m8(te_d)}")
     c.append(f"#define DR_TE_2D {m8(2 * te_d)}")
     c.append(f"#define DR_ELL2_A_OVER_B {m8(mont_a * pow(mont_b, -1, P))}")
