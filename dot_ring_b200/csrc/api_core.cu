@@ -430,8 +430,7 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
     ctx->activate();
     uint32_t cbits = (uint32_t)window_bits & 0xff, wide = ((uint32_t)window_bits >> 8) & 0xff, glv = ((uint32_t)window_bits >> 16) & 1;
     if (window_bits <= 0) {
-        // the cheapest table that leaves max(24 GB, a quarter of its size) of the free device memory for everything else: on a
-        // 180 GB part 14-bit windows with four 15-bit ones (18 additions per coefficient, 106 GB for 6145 points), else uniform
+        // the table with the fewest additions per coefficient that the free device memory can hold next to the prover's scratch
         cbits = 8;
         wide = 0;
 #if !defined(DR_HOST_EMULATION)
@@ -443,7 +442,14 @@ int dr_srs_load(dr_ctx* c, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g
             size_t reserve = bytes / 4 > ((size_t)24 << 30) ? bytes / 4 : ((size_t)24 << 30);
             return bytes + reserve <= free_b;
         };
-        if (fits(14, 4)) {
+        // first choice on a 180 GB part: 16-bit windows over the GLV halves (16 additions per coefficient, 161 GB for 6145 points),
+        // as long as 14 GB stay free next to it: the ring tables (2.6 GB) and a 4096-proof pass (7.5 GB of scratch)
+        const size_t glv_bytes = make_geom(16, (uint32_t)n_g1, 0, 1).total_entries() * sizeof(G1Affine);
+        if (glv_bytes + ((size_t)14 << 30) <= free_b) {
+            cbits = 16;
+            wide = 0;
+            glv = 1;
+        } else if (fits(14, 4)) {
             cbits = 14;
             wide = 4;
         } else {

@@ -19,7 +19,10 @@
 
 namespace dr {
 
-constexpr uint32_t COMMIT_THREADS = 128;
+#ifndef DR_COMMIT_THREADS
+#define DR_COMMIT_THREADS 128  // A/B builds: NVCC_EXTRA="-DDR_COMMIT_THREADS=96 -DDR_COMMIT_MINB=5"
+#endif
+constexpr uint32_t COMMIT_THREADS = DR_COMMIT_THREADS;
 
 int set_error(int code, const std::string& msg);
 

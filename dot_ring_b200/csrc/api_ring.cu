@@ -19,15 +19,22 @@ static TEAffine te_from_param(const uint8_t* xy) {
     return p;
 }
 
+// Per-pass device scratch.  Buffers with disjoint lifetimes share storage: the 16N-element low-degree extensions are dead once
+// the constraints are evaluated, so the combined quotient coefficients (cagg), the aggregated opening polynomial (aggopen) and
+// the linearisation polynomial (lin), all born later, live inside that block: 27 N + 1 field elements per proof instead of 35 N.
 struct ProveScratch {
     size_t cap = 0;
     uint32_t N = 0;
     DevBuf<ProofState> st;
     DevBuf<ProveInput> in;
-    DevBuf<Fr> wit_coef, lde, agg, cagg, quot, aggopen, lin, ntt_tmp;
+    DevBuf<Fr> wit_coef, lde, agg, quot, ntt_tmp;
+    struct View {
+        Fr* p = nullptr;
+    } cagg, aggopen, lin;
     DevBuf<G1Affine> res;
     DevBuf<uint8_t> out, zraw;
     DevBuf<uint32_t> status;
+    static size_t elements_per_proof(uint32_t N) { return (size_t)27 * N + 1; }
     void ensure(size_t n, uint32_t N_) {
         if (n <= cap && N_ == N) return;
         cap = n;
@@ -37,11 +44,11 @@ struct ProveScratch {
         in.alloc(n);
         wit_coef.alloc(n * 4 * N);
         lde.alloc(n * 16 * N);
+        cagg.p = lde.p;                               // n x 4N
+        aggopen.p = lde.p + n * 4 * (size_t)N;        // n x (3N + 1)
+        lin.p = lde.p + n * (7 * (size_t)N + 1);      // n x N
         agg.alloc(n * 4 * N);
-        cagg.alloc(n * 4 * N);
         quot.alloc(n * q);
-        aggopen.alloc(n * q);
-        lin.alloc(n * N);
         res.alloc(n * 4);
         out.alloc(n * 784);
         zraw.alloc(n * 12 * 32);
@@ -306,7 +313,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
         free_b += dev_cache().cached;  // recycled blocks are available to this call
         ProveScratch& cur = scratch_for(ctx);
-        size_t per_proof = (35 + (N > 4096 ? 16 : 0)) * (size_t)N * sizeof(Fr) + sizeof(ProofState) + 4096;
+        size_t per_proof = (ProveScratch::elements_per_proof(N) + (N > 4096 ? 16 * (size_t)N : 0)) * sizeof(Fr) + sizeof(ProofState) + 4096;
         size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
         // keep 1 GB (or half of what is left, if less) for the other buffers of this and later calls
         const size_t keep = have / 2 < ((size_t)1 << 30) ? have / 2 : ((size_t)1 << 30);
@@ -359,9 +366,13 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         } else {
             launch(ctx->stream, Dim3((m * 12 + 127) / 128), 128, 0, ZkRowsBody(), (const uint8_t*)nullptr, sc.st.p, m);
         }
-        // Pedersen part: the half the ring proof needs (blinding factor, blinded key) on the main stream, two lanes per proof; the
+        // Pedersen part: the half the ring proof needs (blinding factor, blinded key) on the main stream, eight lanes per proof; the
         // rest (nonces, R, Ok, responses) on the side stream, joined before the proofs are assembled
-        launch(ctx->stream, Dim3((2 * m + tb - 1) / tb), tb, tb * sizeof(TEAffine), PedersenStartBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p, sc.st.p, m);
+        {
+            const uint32_t per_block = tb / COOP_LANES;  // eight lanes per proof
+            launch(ctx->stream, Dim3((m + per_block - 1) / per_block), tb, pedersen_start_smem(tb), PedersenStartBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p,
+                   sc.st.p, m);
+        }
         ctx->fork_side();
         launch(ctx->side, Dim3((m + 31) / 32), 32, 0, PedersenFinishBody(), rg, (const ProveInput*)sc.in.p, sc.st.p, m);
         {

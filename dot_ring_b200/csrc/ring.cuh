@@ -19,6 +19,7 @@
 #include "ntt.cuh"
 #include "rt.cuh"
 #include "te.cuh"
+#include "te_coop.cuh"
 
 namespace dr {
 
@@ -239,16 +240,14 @@ DR_HD TEAffine vrf_encode_to_curve(const S& rg, const uint8_t* msg, uint32_t msg
 }
 
 // ---- A. Pedersen VRF prove (pedersen/vrf.py:86-126) -------------------------------------------------------
-// First half: everything up to the blinded key.  Writes O | Ybar into out192; returns the public key, the blinded key, the
-// blinding factor and the transcript state the second half continues from.  `input` is the hash-to-curve point.
+// First half: everything up to the blinded key, in two steps around the blinding-base multiplication so that the cooperative
+// prover can run the multiplications on several lanes.
+// Step 1: public key and output point (given in extended coordinates), VRF transcript, blinding factor.  Writes O into out192.
 template <class S>
-DR_HD_COLD void pedersen_prove_begin(const S& rg, const uint8_t* sk32, const TEAffine& input, const uint8_t* ad, uint32_t ad_len, uint8_t* out192, TEAffine& pk,
-                                     TEAffine& blinded, uint32_t* blinding_raw, VrfHash& tr) {
-    Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
-    uint32_t xr[8];
-    fn_raw_limbs(xr, x);
+DR_HD_COLD void pedersen_begin_transcript(const S& rg, const Fn& x, const TEAffine& input, const TEExt& pk_ext, const TEExt& output_ext, const uint8_t* ad,
+                                          uint32_t ad_len, uint8_t* out192, TEAffine& pk, uint32_t* blinding_raw, VrfHash& tr) {
     TEAffine output;
-    te_to_affine2(te_mul_fixed(rg.g_tab, xr), te_mul_raw(input, xr, 8), pk, output);
+    te_to_affine2(pk_ext, output_ext, pk, output);
     // vrf_transcript (primitives.py:102-144) with one I/O pair
     tr.init(rg.hash_kind);
     tr.update(rg.suite_id, rg.suite_id_len);
@@ -265,10 +264,24 @@ DR_HD_COLD void pedersen_prove_begin(const S& rg, const uint8_t* sk32, const TEA
     tb.update_byte(0x12);
     Fn b = vrf_nonce(tb, x);
     fn_raw_limbs(blinding_raw, b);
-    blinded = te_to_affine(te_add(te_mul_fixed(rg.b_tab, blinding_raw), TEExt::from_affine(pk)));
-    sha_absorb_point(tr, blinded);
     te_encode(out192, output);
+}
+// Step 2: blinded key Ybar = pk + b * B (b * B given), absorbed into the transcript.  Writes Ybar into out192 + 32.
+DR_HD_COLD void pedersen_begin_blind(const TEAffine& pk, const TEExt& bB_ext, uint8_t* out192, TEAffine& blinded, VrfHash& tr) {
+    blinded = te_to_affine(te_add(bB_ext, TEExt::from_affine(pk)));
+    sha_absorb_point(tr, blinded);
     te_encode(out192 + 32, blinded);
+}
+// Writes O | Ybar into out192; returns the public key, the blinded key, the blinding factor and the transcript state the second
+// half continues from.  `input` is the hash-to-curve point.
+template <class S>
+DR_HD_COLD void pedersen_prove_begin(const S& rg, const uint8_t* sk32, const TEAffine& input, const uint8_t* ad, uint32_t ad_len, uint8_t* out192, TEAffine& pk,
+                                     TEAffine& blinded, uint32_t* blinding_raw, VrfHash& tr) {
+    Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
+    uint32_t xr[8];
+    fn_raw_limbs(xr, x);
+    pedersen_begin_transcript(rg, x, input, te_mul_fixed(rg.g_tab, xr), te_mul_raw(input, xr, 8), ad, ad_len, out192, pk, blinding_raw, tr);
+    pedersen_begin_blind(pk, te_mul_fixed(rg.b_tab, blinding_raw), out192, blinded, tr);
 }
 // Second half: nonces, R, Ok, challenge, responses.  Writes R | Ok | s | sb into out192 + 64.
 template <class S>
@@ -334,31 +347,84 @@ struct TeFixedTableBody {
     }
 };
 
-// First half of the Pedersen prover, two threads per proof: the two Elligator 2 maps of hash-to-curve (the longest serial chains of
-// the prover: a field inversion and a square root each) run side by side, then the even lane carries on alone.
+// First half of the Pedersen prover, eight threads per proof (te_coop.cuh).  This kernel is on the critical path of a pass whatever
+// its width, so its serial chains are spread over the lanes: the two Elligator 2 maps of hash-to-curve (a field inversion and a
+// square root each) run side by side, sk * H(alpha) is a cooperative variable-base multiplication, sk * G and b * B are split by
+// table windows.  What remains on one lane: the affine conversions, the SHA-512 / SHAKE transcripts and the point encodings.
+DR_HD size_t pedersen_start_smem(uint32_t threads) { return (threads / COOP_LANES) * (sizeof(TeCoopState) + 2 * sizeof(TEAffine)); }
 struct PedersenStartBody {
     DR_HD void operator()(const BlockCtx& ctx, RingDev rg, const ProveInput* in, const uint8_t* blob, ProofState* st, uint32_t count) const {
-        TEAffine* maps = (TEAffine*)ctx.smem;  // [nthreads]
+        const uint32_t items = ctx.nthreads / COOP_LANES;
+        TeCoopState* cs = (TeCoopState*)ctx.smem;
+        TEAffine* maps = (TEAffine*)(cs + items);  // [items][2]
+        // A. hash-to-curve maps on lanes 0 and 1
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t p = (ctx.bx * ctx.nthreads + t) >> 1;
-            if (p < count) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            if (lane == 0) cs[item].live = p < count ? 1u : 0u;
+            if (p < count && lane < 2) {
                 const ProveInput& pi = in[p];
                 uint8_t u[96];
                 h2c_uniform_bytes(rg, blob + pi.alpha_off, pi.alpha_len, u);
-                maps[t] = te_map_to_curve_ell2(fr_from_be48_mod(u + 48 * (t & 1)));
+                maps[2 * item + lane] = te_map_to_curve_ell2(fr_from_be48_mod(u + 48 * lane));
             }
         }
         DR_BLOCK_SYNC();
+        // B. input point = 4 * (map(u0) + map(u1))  (te_affine_point.py:213-222); operands of sk * input
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t p = (ctx.bx * ctx.nthreads + t) >> 1;
-            if (p < count && !(t & 1)) {
-                const ProveInput& pi = in[p];
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            if (p < count && lane == 0) {
+                TeCoopState& s = cs[item];
+                TEExt sum = te_add(TEExt::from_affine(maps[2 * item]), TEExt::from_affine(maps[2 * item + 1]));
+                const TEAffine input = te_to_affine(te_dbl(te_dbl(sum)));
+                st[p].vrf_input = input;
+                s.tab[0].X = input.x;
+                s.tab[0].Y = input.y;
+                s.tab[0].Z = Fr::one();
+                s.tab[0].T = input.x * input.y;
+                fn_raw_limbs(s.k, fp_from_le_bytes_mod<Fn>(in[p].sk, 32));
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_mul_coop(ctx, cs, 8);
+        // C. sk * G by windows
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = cs[t / COOP_LANES];
+            if (s.live) te_mul_fixed_coop_partial(t % COOP_LANES, rg.g_tab, s.k, s.part);
+        }
+        DR_BLOCK_SYNC();
+        // D. public key, output point, transcript, blinding factor (one lane); the public key waits in s.m for step F
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            if (p < count && lane == 0) {
+                TeCoopState& s = cs[item];
                 ProofState& ps = st[p];
-                // te_affine_point.py:213-222: 4 * (map(u0) + map(u1))
-                TEExt sum = te_add(TEExt::from_affine(maps[t]), TEExt::from_affine(maps[t + 1]));
-                ps.vrf_input = te_to_affine(te_dbl(te_dbl(sum)));
-                TEAffine pk, blinded;
-                pedersen_prove_begin(rg, pi.sk, ps.vrf_input, blob + pi.ad_off, pi.ad_len, ps.pedersen, pk, blinded, ps.t, ps.vrf_tr);
+                const ProveInput& pi = in[p];
+                const TEExt output{s.acc.X, s.acc.Y, s.acc.Z, s.acc.T};
+                TEAffine pk;
+                pedersen_begin_transcript(rg, fp_from_le_bytes_mod<Fn>(pi.sk, 32), ps.vrf_input, te_fold_fixed_coop(s.part), output, blob + pi.ad_off, pi.ad_len, ps.pedersen,
+                                          pk, ps.t, ps.vrf_tr);
+                s.m[0] = pk.x;
+                s.m[1] = pk.y;
+                for (int i = 0; i < 8; i++) s.k[i] = ps.t[i];
+            }
+        }
+        DR_BLOCK_SYNC();
+        // E. b * B by windows
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = cs[t / COOP_LANES];
+            if (s.live) te_mul_fixed_coop_partial(t % COOP_LANES, rg.b_tab, s.k, s.part);
+        }
+        DR_BLOCK_SYNC();
+        // F. blinded key; ring-membership check of the producer key
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            if (p < count && lane == 0) {
+                TeCoopState& s = cs[item];
+                ProofState& ps = st[p];
+                const ProveInput& pi = in[p];
+                const TEAffine pk{s.m[0], s.m[1]};
+                TEAffine blinded;
+                pedersen_begin_blind(pk, te_fold_fixed_coop(s.part), ps.pedersen, blinded, ps.vrf_tr);
                 ps.k = pi.k;
                 ps.relation = blinded;
                 // producer_key must be pk(sk) and sit at row k of the ring (vrf/ring/vrf.py:196-197, members.py:71-81)

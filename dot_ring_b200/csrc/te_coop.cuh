@@ -1,0 +1,177 @@
+// Cooperative Bandersnatch scalar multiplication: eight threads per item.
+//
+// The provers run one item per thread where the batch is small (a 512-proof shard of an 8-GPU run, a single `prove` call), and
+// there a 253-bit variable-base multiplication is ~2700 field multiplications in ONE dependent chain: every multiplication is a
+// carry chain of ~300 integer instructions whose latency nothing hides.  The extended-coordinate formulas are two layers of
+// independent products (dbl-2008-hwcd: 4 + 4, add-2008-hwcd: 5 + 4), so the lanes of an item compute one product each per layer
+// and exchange them through shared memory: a doubling costs two multiplication latencies instead of eight, an addition two
+// instead of nine.  Fixed-base multiplications (8-bit windows over a precomputed table, te.cuh te_mul_fixed) are split by
+// windows instead: four table additions per lane, then one lane folds the eight partial sums.
+//
+// Written in the phase style of rt.cuh: every function is called by ALL threads of the block with block-uniform control flow;
+// item = thread / 8, lane = thread % 8; all state lives in shared memory (TeCoopState, one per item).
+#pragma once
+#include "rt.cuh"
+#include "te.cuh"
+
+namespace dr {
+
+constexpr uint32_t COOP_LANES = 8;
+
+struct TeCoopPoint {
+    Fr X, Y, Z, T, dT;  // extended coordinates; dT = d * T (only kept for table entries, the second operand of an addition)
+};
+
+struct TeCoopState {
+    TeCoopPoint acc;
+    Fr m[5];              // products of the first layer
+    TeCoopPoint tab[15];  // 1P .. 15P
+    uint32_t k[8];        // scalar, raw little-endian limbs
+    uint32_t live;        // 0: this slot holds no item (lanes idle, phases still run)
+    TEExt part[COOP_LANES];  // fixed-base partial sums
+};
+
+// first layer of a doubling of `p`: A = X^2, B = Y^2, C = 2 Z^2, E' = (X + Y)^2
+DR_HD void coop_dbl_layer1(uint32_t lane, const TeCoopPoint& p, Fr* m) {
+    switch (lane) {
+        case 0: m[0] = p.X.sqr(); break;
+        case 1: m[1] = p.Y.sqr(); break;
+        case 2: m[2] = p.Z.sqr().dbl(); break;
+        case 3: m[3] = (p.X + p.Y).sqr(); break;
+        default: break;
+    }
+}
+// second layer: dbl-2008-hwcd with a = -5
+DR_HD void coop_dbl_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
+    if (lane > 3) return;
+    const Fr A = m[0], B = m[1], C = m[2];
+    const Fr D = fr_mul5(A).neg();
+    const Fr E = m[3] - A - B;
+    const Fr G = D + B;
+    const Fr F = G - C;
+    const Fr H = D - B;
+    switch (lane) {
+        case 0: out.X = E * F; break;
+        case 1: out.Y = G * H; break;
+        case 2: out.Z = F * G; break;
+        default: out.T = E * H; break;
+    }
+}
+// first layer of p + q (q carries dT): A = X1 X2, B = Y1 Y2, C = T1 (d T2), D = Z1 Z2, E' = (X1 + Y1)(X2 + Y2)
+DR_HD void coop_add_layer1(uint32_t lane, const TeCoopPoint& p, const TeCoopPoint& q, Fr* m) {
+    switch (lane) {
+        case 0: m[0] = p.X * q.X; break;
+        case 1: m[1] = p.Y * q.Y; break;
+        case 2: m[2] = p.T * q.dT; break;
+        case 3: m[3] = p.Z * q.Z; break;
+        case 4: m[4] = (p.X + p.Y) * (q.X + q.Y); break;
+        default: break;
+    }
+}
+DR_HD void coop_add_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
+    if (lane > 3) return;
+    const Fr E = m[4] - m[0] - m[1];
+    const Fr F = m[3] - m[2];
+    const Fr G = m[3] + m[2];
+    const Fr H = m[1] + fr_mul5(m[0]);
+    switch (lane) {
+        case 0: out.X = E * F; break;
+        case 1: out.Y = G * H; break;
+        case 2: out.Z = F * G; break;
+        default: out.T = E * H; break;
+    }
+}
+
+// acc <- k * P for every live item of the block.  Before the call (and a block sync): st[item].tab[0] = P as (x, y, 1, x y),
+// st[item].k = scalar (raw limbs, `nlimbs` of them significant), st[item].live set.  After the call (which ends in a sync)
+// st[item].acc holds X, Y, Z, T.  4-bit fixed windows, most significant first, like te_mul_raw; the formulas are complete on
+// the prime-order subgroup (and for the identity), so leading zero windows simply double the identity.
+DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) {
+    // table: 2P = dbl(P), 3P = 2P + P, 4P = dbl(2P), ...
+    DR_THREAD_LOOP(t, ctx) {
+        TeCoopState& s = st[t / COOP_LANES];
+        if (s.live && t % COOP_LANES == 0) s.tab[0].dT = s.tab[0].T * te_d();
+    }
+    DR_BLOCK_SYNC();
+    for (uint32_t i = 2; i <= 15; i++) {
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = st[t / COOP_LANES];
+            if (s.live) {
+                if (i & 1) coop_add_layer1(t % COOP_LANES, s.tab[i - 2], s.tab[0], s.m);
+                else coop_dbl_layer1(t % COOP_LANES, s.tab[i / 2 - 1], s.m);
+            }
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = st[t / COOP_LANES];
+            if (s.live) {
+                if (i & 1) coop_add_layer2(t % COOP_LANES, s.m, s.tab[i - 1]);
+                else coop_dbl_layer2(t % COOP_LANES, s.m, s.tab[i - 1]);
+            }
+        }
+        DR_BLOCK_SYNC();
+    }
+    DR_THREAD_LOOP(t, ctx) {
+        TeCoopState& s = st[t / COOP_LANES];
+        const uint32_t lane = t % COOP_LANES;
+        if (s.live) {
+            for (uint32_t e = lane ? lane : COOP_LANES; e < 15; e += COOP_LANES) s.tab[e].dT = s.tab[e].T * te_d();  // entry 0 already has it
+            if (lane == 0) {
+                s.acc.X = Fr::zero();
+                s.acc.Y = Fr::one();
+                s.acc.Z = Fr::one();
+                s.acc.T = Fr::zero();
+            }
+        }
+    }
+    DR_BLOCK_SYNC();
+    for (int w = 8 * nlimbs - 1; w >= 0; w--) {
+        if (w != 8 * nlimbs - 1) {
+            for (int rep = 0; rep < 4; rep++) {
+                DR_THREAD_LOOP(t, ctx) {
+                    TeCoopState& s = st[t / COOP_LANES];
+                    if (s.live) coop_dbl_layer1(t % COOP_LANES, s.acc, s.m);
+                }
+                DR_BLOCK_SYNC();
+                DR_THREAD_LOOP(t, ctx) {
+                    TeCoopState& s = st[t / COOP_LANES];
+                    if (s.live) coop_dbl_layer2(t % COOP_LANES, s.m, s.acc);
+                }
+                DR_BLOCK_SYNC();
+            }
+        }
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = st[t / COOP_LANES];
+            const uint32_t d = (s.k[w >> 3] >> (4 * (w & 7))) & 15u;
+            if (s.live && d) coop_add_layer1(t % COOP_LANES, s.acc, s.tab[d - 1], s.m);
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = st[t / COOP_LANES];
+            const uint32_t d = (s.k[w >> 3] >> (4 * (w & 7))) & 15u;
+            if (s.live && d) coop_add_layer2(t % COOP_LANES, s.m, s.acc);
+        }
+        DR_BLOCK_SYNC();
+    }
+}
+
+// part[lane] <- sum over the lane's four windows of the fixed-base table entries selected by k (te_mul_fixed split by windows).
+// One phase, no sync inside: the caller syncs, then one lane folds the eight partial sums with te_fold_fixed_coop.
+DR_HD void te_mul_fixed_coop_partial(uint32_t lane, const TEPre* tab, const uint32_t* k, TEExt* part) {
+    TEExt acc = TEExt::identity();
+    constexpr int per = TE_FIXED_WINDOWS / (int)COOP_LANES;
+#pragma unroll 1
+    for (int w = per * (int)lane; w < per * ((int)lane + 1); w++) {
+        uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 255;
+        if (d) acc = te_madd(acc, tab[256 * w + d]);
+    }
+    part[lane] = acc;
+}
+DR_HD TEExt te_fold_fixed_coop(const TEExt* part) {
+    TEExt acc = part[0];
+#pragma unroll 1
+    for (uint32_t l = 1; l < COOP_LANES; l++) acc = te_add(acc, part[l]);
+    return acc;
+}
+
+}  // namespace dr

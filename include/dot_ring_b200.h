@@ -68,8 +68,9 @@ int dr_ctx_device_info(dr_ctx* ctx, char* name_buf, size_t name_len, int* sm_cou
  * take c + 1 bits instead (0 = uniform).  W = ceil((256 - k) / c) table additions per coefficient, table bytes =
  * n_g1 * (W + k) * 2^(c-1) * 96.  Bit 16 = GLV: every scalar is split as k1 + k2 * lambda (128-bit halves, lambda the eigenvalue of
  * the G1 endomorphism), the table covers 128 bits (W = ceil((128 - k) / c), c up to 16, a slightly longer last window) and a
- * coefficient costs 2W additions: c = 16 gives 16 additions in 161 GB for 6145 points.  0 = auto: the cheapest table that leaves max(24 GB, a quarter of its size) of the free device
- * memory: on a 180 GB B200 c = 14, k = 4 (18 additions, 106 GB for the bundled 6145-point SRS; uniform 14 bits = 19 additions, 92 GB).
+ * coefficient costs 2W additions: c = 16 gives 16 additions in 161 GB for 6145 points.  0 = auto: that GLV table when it leaves 14 GB of the
+ * free device memory (a 180 GB B200 with the bundled 6145-point SRS), else c = 14, k = 4 (18 additions, 106 GB) when that leaves max(24 GB, a
+ * quarter of its size), else the widest uniform windows that do (uniform 14 bits = 19 additions, 92 GB).
  */
 int dr_srs_load(dr_ctx* ctx, const uint8_t* g1_be96, size_t n_g1, const uint8_t* g2_be192, int window_bits, dr_srs** out);
 void dr_srs_destroy(dr_srs* srs);

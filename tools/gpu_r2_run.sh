@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round-2 GPU visit: tests, bench lines, probe, launch list, ncu captures.  Usage: bash tools/gpu_r2_run.sh <tag> [steps...]
-# steps: tests bench bench512 probe list ncu_prove ncu_verify ncu_commit.  ncu reports are reduced to CSV on the box (tools/ncu_extract.py)
+# steps: tests bench bench512 probe micro commit_ab list ncu_prove ncu_verify ncu_commit.  ncu reports are reduced to CSV on the box (tools/ncu_extract.py)
 # because gpurun only brings back 64 MiB; each ncu run follows a plain run of the same command that exited 0.
 set -u
 TAG=$1; shift
@@ -25,6 +25,12 @@ if has bench512; then
 fi
 if has probe; then
   python tools/gpu_probe_r2.py 1024 20000 10 > ${O}_probe.log 2>&1; echo "probe rc=$?"; cat ${O}_probe.log
+fi
+if has micro; then
+  python tools/gpu_microbench_r2.py > ${O}_microbench.json 2>&1; cat ${O}_microbench.json
+fi
+if has commit_ab; then
+  python tools/gpu_commit_ab.py default build/var/lib_m3.so build/var/lib_t96m5.so build/var/lib_t64m8.so > ${O}_commit_ab.log 2>&1; cat ${O}_commit_ab.log
 fi
 CMD="python tools/gpu_probe_r2.py 512 4096 10"
 if has list; then
