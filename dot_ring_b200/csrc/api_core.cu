@@ -98,7 +98,7 @@ void ntt_device(Ctx* ctx, const NttPlan& plan, const Fr* in, Fr* out, size_t bat
 void PhaseTimer::mark(Ctx* ctx, int phase) {
     size_t i = phase_of.size();
     phase_of.push_back(phase);
-    if (phase != 6) current = phase;
+    if (phase != 6 && phase < 7) current = phase;
 #if !defined(DR_HOST_EMULATION)
     if (events.size() <= i) {
         cudaEvent_t e;
@@ -300,8 +300,8 @@ int dr_ctx_create(int device, dr_ctx** out) {
     DR_CUDA(cudaSetDevice(device));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
-    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    DR_CUDA(cudaEventCreate(&ctx->ev_fork));
+    DR_CUDA(cudaEventCreate(&ctx->ev_join));
     // Fix the per-thread stack once: kernels here need between 0 and ~16 KB of local memory, and letting the runtime grow the
     // backing store lazily costs a device-wide reallocation (hundreds of ms) whenever a larger kernel follows a smaller one.
     if (const char* e = getenv("DOT_RING_B200_STACK_BYTES")) {

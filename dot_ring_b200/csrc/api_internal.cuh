@@ -40,8 +40,10 @@ struct Ctx;
 
 // Accumulates device time per pipeline phase with events recorded between the launches.
 struct PhaseTimer {
-    static constexpr int NPH = 7;  // 0..5: pipeline phases (dr_ring_prove_phase_ms); 6: the dense commit kernel alone (CommitBodyT launches)
-    float total[NPH] = {0, 0, 0, 0, 0, 0, 0};
+    // 0..5: pipeline phases (dr_ring_prove_phase_ms); 6: the dense commit kernel alone (CommitBodyT launches); 7: call entry -> first
+    // phase of a pass (input copies, set-up); 8: last phase -> results on the host (output copies, side stream join, final sync)
+    static constexpr int NPH = 9;
+    float total[NPH] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t kernel_launches = 0;  // CommitBodyT launches counted into total[6]
     bool active = false;           // between reset() and the last collect() of a prove call
     int current = -1;
@@ -131,6 +133,17 @@ struct Ctx {
         DR_CUDA(cudaEventRecord(ev_join, side));
         DR_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
 #endif
+    }
+    // ms between the last fork and the completion of the side stream's work (after a stream sync); diagnostics only
+    float side_span_ms() {
+        float ms = 0;
+#if !defined(DR_HOST_EMULATION)
+        if (cudaEventElapsedTime(&ms, ev_fork, ev_join) != cudaSuccess) {
+            cudaGetLastError();
+            ms = -1;
+        }
+#endif
+        return ms;
     }
     const NttPlan& plan(uint32_t n, const Fr& omega_mont);
     void release_scratch() {

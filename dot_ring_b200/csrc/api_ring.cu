@@ -345,6 +345,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
 
     for (size_t base = 0; base < n; base += pass_width) {
         const uint32_t m = (uint32_t)((n - base < pass_width) ? n - base : pass_width);
+        pt.mark(ctx, 7);
         hin.assign(m, ProveInput{});
         for (uint32_t i = 0; i < m; i++) {
             ProveInput& pi = hin[i];
@@ -438,10 +439,11 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         pt.mark(ctx, 5);
         ctx->join_side();
         launch(ctx->stream, Dim3(pb), tb, 0, FinalizeBody(), (const ProofState*)sc.st.p, m, sc.out.p, sc.status.p);
-        pt.mark(ctx, -1);
+        pt.mark(ctx, 8);
         dev_zero(ctx->stream, sc.in.p, m * sizeof(ProveInput));  // secret keys do not outlive the pass on the device
         d2h(ctx->stream, proofs784 + 784 * base, sc.out.p, (size_t)m * 784);
         d2h(ctx->stream, status + base, sc.status.p, (size_t)m * sizeof(uint32_t));
+        pt.mark(ctx, -1);
         stream_sync(ctx->stream);
         pt.collect(ctx);
     }
@@ -457,6 +459,9 @@ int dr_ring_prove_phase_ms(dr_ctx* c, float out[6]) {
     Ctx* ctx = (Ctx*)c;
     if (!ctx || !out) throw Error(DR_EINVAL, "bad argument");
     for (int i = 0; i < 6; i++) out[i] = ctx->phases.total[i];
+    if (getenv("DOT_RING_B200_DEBUG"))
+        fprintf(stderr, "[dot_ring_b200] prove: copy-in / set-up %.3f ms, copy-out %.3f ms, commit kernel %.3f ms, side stream fork -> done %.3f ms\n", ctx->phases.total[7],
+                ctx->phases.total[8], ctx->phases.total[6], ctx->side_span_ms());
     DR_API_END
 }
 

@@ -377,10 +377,10 @@ struct PedersenStartBody {
                 TEExt sum = te_add(TEExt::from_affine(maps[2 * item]), TEExt::from_affine(maps[2 * item + 1]));
                 const TEAffine input = te_to_affine(te_dbl(te_dbl(sum)));
                 st[p].vrf_input = input;
-                s.tab[0].X = input.x;
-                s.tab[0].Y = input.y;
-                s.tab[0].Z = Fr::one();
-                s.tab[0].T = input.x * input.y;
+                s.tab[0].c[CX] = input.x;
+                s.tab[0].c[CY] = input.y;
+                s.tab[0].c[CZ] = Fr::one();
+                s.tab[0].c[CT] = input.x * input.y;
                 fn_raw_limbs(s.k, fp_from_le_bytes_mod<Fn>(in[p].sk, 32));
             }
         }
@@ -399,7 +399,7 @@ struct PedersenStartBody {
                 TeCoopState& s = cs[item];
                 ProofState& ps = st[p];
                 const ProveInput& pi = in[p];
-                const TEExt output{s.acc.X, s.acc.Y, s.acc.Z, s.acc.T};
+                const TEExt output{s.acc.c[CX], s.acc.c[CY], s.acc.c[CZ], s.acc.c[CT]};
                 TEAffine pk;
                 pedersen_begin_transcript(rg, fp_from_le_bytes_mod<Fn>(pi.sk, 32), ps.vrf_input, te_fold_fixed_coop(s.part), output, blob + pi.ad_off, pi.ad_len, ps.pedersen,
                                           pk, ps.t, ps.vrf_tr);

@@ -19,8 +19,9 @@ namespace dr {
 constexpr uint32_t COOP_LANES = 8;
 
 struct TeCoopPoint {
-    Fr X, Y, Z, T, dT;  // extended coordinates; dT = d * T (only kept for table entries, the second operand of an addition)
+    Fr c[5];  // X, Y, Z, T, dT: extended coordinates; dT = d * T (only kept for table entries, the second operand of an addition)
 };
+enum { CX = 0, CY = 1, CZ = 2, CT = 3, CDT = 4 };
 
 struct TeCoopState {
     TeCoopPoint acc;
@@ -31,15 +32,23 @@ struct TeCoopState {
     TEExt part[COOP_LANES];  // fixed-base partial sums
 };
 
-// first layer of a doubling of `p`: A = X^2, B = Y^2, C = 2 Z^2, E' = (X + Y)^2
+// Every layer is ONE multiplication executed by all lanes in lockstep: the lanes differ in their operands only (a warp that
+// branched per lane would run the four or five products one after another, which is exactly what this file exists to avoid).
+DR_HD Fr coop_pick(uint32_t i, const Fr& a0, const Fr& a1, const Fr& a2, const Fr& a3) {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = i == 0 ? a0.v[l] : i == 1 ? a1.v[l] : i == 2 ? a2.v[l] : a3.v[l];
+    return r;
+}
+
+// first layer of a doubling of `p`: A = X^2, B = Y^2, C = 2 Z^2, E' = (X + Y)^2   (lanes 0..3)
 DR_HD void coop_dbl_layer1(uint32_t lane, const TeCoopPoint& p, Fr* m) {
-    switch (lane) {
-        case 0: m[0] = p.X.sqr(); break;
-        case 1: m[1] = p.Y.sqr(); break;
-        case 2: m[2] = p.Z.sqr().dbl(); break;
-        case 3: m[3] = (p.X + p.Y).sqr(); break;
-        default: break;
-    }
+    if (lane > 3) return;
+    const Fr own = p.c[lane < 3 ? lane : 0];  // X, Y, Z, X
+    const Fr sum = own + p.c[CY];             // only lane 3 uses it: X + Y
+    const Fr a = Fr::select(lane == 3, sum, own);
+    const Fr sq = a.sqr();
+    m[lane] = Fr::select(lane == 2, sq.dbl(), sq);
 }
 // second layer: dbl-2008-hwcd with a = -5
 DR_HD void coop_dbl_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
@@ -50,23 +59,21 @@ DR_HD void coop_dbl_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
     const Fr G = D + B;
     const Fr F = G - C;
     const Fr H = D - B;
-    switch (lane) {
-        case 0: out.X = E * F; break;
-        case 1: out.Y = G * H; break;
-        case 2: out.Z = F * G; break;
-        default: out.T = E * H; break;
-    }
+    // X = E F, Y = G H, Z = F G, T = E H
+    const Fr a = coop_pick(lane, E, G, F, E), b = coop_pick(lane, F, H, G, H);
+    out.c[lane] = a * b;
 }
-// first layer of p + q (q carries dT): A = X1 X2, B = Y1 Y2, C = T1 (d T2), D = Z1 Z2, E' = (X1 + Y1)(X2 + Y2)
+// first layer of p + q (q carries dT): A = X1 X2, B = Y1 Y2, C = T1 (d T2), D = Z1 Z2, E' = (X1 + Y1)(X2 + Y2)   (lanes 0..4)
 DR_HD void coop_add_layer1(uint32_t lane, const TeCoopPoint& p, const TeCoopPoint& q, Fr* m) {
-    switch (lane) {
-        case 0: m[0] = p.X * q.X; break;
-        case 1: m[1] = p.Y * q.Y; break;
-        case 2: m[2] = p.T * q.dT; break;
-        case 3: m[3] = p.Z * q.Z; break;
-        case 4: m[4] = (p.X + p.Y) * (q.X + q.Y); break;
-        default: break;
-    }
+    if (lane > 4) return;
+    // operand coordinates per lane: (X, X) (Y, Y) (T, dT) (Z, Z) (X + Y, X + Y)
+    const uint32_t ia = lane == 2 ? CT : lane == 3 ? CZ : lane == 1 ? CY : CX;
+    const uint32_t ib = lane == 2 ? CDT : ia;
+    Fr a = p.c[ia], b = q.c[ib];
+    const Fr sa = a + p.c[CY], sb = b + q.c[CY];  // only lane 4 uses them
+    a = Fr::select(lane == 4, sa, a);
+    b = Fr::select(lane == 4, sb, b);
+    m[lane] = a * b;
 }
 DR_HD void coop_add_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
     if (lane > 3) return;
@@ -74,12 +81,8 @@ DR_HD void coop_add_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
     const Fr F = m[3] - m[2];
     const Fr G = m[3] + m[2];
     const Fr H = m[1] + fr_mul5(m[0]);
-    switch (lane) {
-        case 0: out.X = E * F; break;
-        case 1: out.Y = G * H; break;
-        case 2: out.Z = F * G; break;
-        default: out.T = E * H; break;
-    }
+    const Fr a = coop_pick(lane, E, G, F, E), b = coop_pick(lane, F, H, G, H);
+    out.c[lane] = a * b;
 }
 
 // acc <- k * P for every live item of the block.  Before the call (and a block sync): st[item].tab[0] = P as (x, y, 1, x y),
@@ -90,7 +93,7 @@ DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) {
     // table: 2P = dbl(P), 3P = 2P + P, 4P = dbl(2P), ...
     DR_THREAD_LOOP(t, ctx) {
         TeCoopState& s = st[t / COOP_LANES];
-        if (s.live && t % COOP_LANES == 0) s.tab[0].dT = s.tab[0].T * te_d();
+        if (s.live && t % COOP_LANES == 0) s.tab[0].c[CDT] = s.tab[0].c[CT] * te_d();
     }
     DR_BLOCK_SYNC();
     for (uint32_t i = 2; i <= 15; i++) {
@@ -115,12 +118,12 @@ DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) {
         TeCoopState& s = st[t / COOP_LANES];
         const uint32_t lane = t % COOP_LANES;
         if (s.live) {
-            for (uint32_t e = lane ? lane : COOP_LANES; e < 15; e += COOP_LANES) s.tab[e].dT = s.tab[e].T * te_d();  // entry 0 already has it
+            for (uint32_t e = lane ? lane : COOP_LANES; e < 15; e += COOP_LANES) s.tab[e].c[CDT] = s.tab[e].c[CT] * te_d();  // entry 0 already has it
             if (lane == 0) {
-                s.acc.X = Fr::zero();
-                s.acc.Y = Fr::one();
-                s.acc.Z = Fr::one();
-                s.acc.T = Fr::zero();
+                s.acc.c[CX] = Fr::zero();
+                s.acc.c[CY] = Fr::one();
+                s.acc.c[CZ] = Fr::one();
+                s.acc.c[CT] = Fr::zero();
             }
         }
     }
