@@ -99,6 +99,9 @@ static SuiteDev suite_from_abi(const dr_vrf_suite* s) {
     return d;
 }
 
+// cooperative verification kernels: eight lanes per item (te_coop.cuh), eight items per block
+constexpr uint32_t VRF_VERIFY_THREADS = 64, VRF_VERIFY_ITEMS = VRF_VERIFY_THREADS / COOP_LANES;
+
 // uploads the per-item (offset, length) table and the blob; returns the device buffers
 struct ItemsDev {
     DevBuf<VerifyInput> in;
@@ -149,7 +152,7 @@ static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t 
     launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, RingVerifyAlgebraBody(), vk, payloads, stride, relations, rel_stride, (const uint8_t*)dco.p, m, vs.p);
     uint32_t all = 0;
     const bool by_msm = aggregate && n >= RING_VERIFY_MSM_THRESHOLD.load();
-    if (!by_msm) launch(ctx->stream, Dim3((VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
+    if (!by_msm) launch(ctx->stream, Dim3((2 * VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
     if (by_msm) {
         // two variable-base MSMs instead of 13 scalar multiplications per proof
         const uint32_t threads = 64, nparts = (m + threads - 1) / threads;
@@ -257,8 +260,11 @@ int dr_pedersen_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, con
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs192, n * 192);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 192u, 4u, 4 * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenVerifyBody(), su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u,
-           (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);
+    su.g_tab = g_table->tab.p;
+    su.b_tab = b_table->tab.p;
+    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su,
+           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
@@ -288,8 +294,8 @@ static void ietf_verify_batch(Ctx* ctx, const dr_vrf_suite* suite, uint32_t thin
     h2d(ctx->stream, denc.p, enc.data(), enc.size());
     h2d(ctx->stream, dpr.p, proofs, (size_t)plen * n);
     launch(ctx->stream, Dim3((npts * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)denc.p, 32u * npts, npts, npts * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfVerifyBody(), su, thin, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p,
-           (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), IetfVerifyBody(), su, thin,
+           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
@@ -404,8 +410,8 @@ int dr_ring_verify_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, c
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs784, n * 784);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 784u, 4u, 4 * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenVerifyBody(), ring->suite, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u,
-           (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), ring->suite,
+           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     // relation = blinded public key (second Pedersen point); payload follows the 192-byte Pedersen part
     ring_proof_verify_device(ctx, ring->vk, n, dpr.p + 192, 784, pts.p + 1, 4, coeffs_le32, dst.p, aggregate, verdict, all_ok);
     DR_API_END

@@ -25,10 +25,12 @@ enum { CX = 0, CY = 1, CZ = 2, CT = 3, CDT = 4 };
 
 struct TeCoopState {
     TeCoopPoint acc;
-    Fr m[5];              // products of the first layer
-    TeCoopPoint tab[15];  // 1P .. 15P
-    uint32_t k[8];        // scalar, raw little-endian limbs
-    uint32_t live;        // 0: this slot holds no item (lanes idle, phases still run)
+    Fr m[5];               // products of the first layer
+    TeCoopPoint tab[15];   // 1P .. 15P
+    TeCoopPoint tab2[15];  // 1Q .. 15Q (two-point Straus only)
+    uint32_t k[8];         // scalar of P, raw little-endian limbs
+    uint32_t k2[8];        // scalar of Q
+    uint32_t live;         // 0: this slot holds no item (lanes idle, phases still run)
     TEExt part[COOP_LANES];  // fixed-base partial sums
 };
 
@@ -85,46 +87,59 @@ DR_HD void coop_add_layer2(uint32_t lane, const Fr* m, TeCoopPoint& out) {
     out.c[lane] = a * b;
 }
 
-// acc <- k * P for every live item of the block.  Before the call (and a block sync): st[item].tab[0] = P as (x, y, 1, x y),
-// st[item].k = scalar (raw limbs, `nlimbs` of them significant), st[item].live set.  After the call (which ends in a sync)
-// st[item].acc holds X, Y, Z, T.  4-bit fixed windows, most significant first, like te_mul_raw; the formulas are complete on
-// the prime-order subgroup (and for the identity), so leading zero windows simply double the identity.
-DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) {
-    // table: 2P = dbl(P), 3P = 2P + P, 4P = dbl(2P), ...
+// tab[1..14] <- 2T .. 15T from tab[0] = T (any extended representation, Z need not be 1), dT for every entry.  Ends in a sync.
+DR_HD void te_table_coop(const BlockCtx& ctx, TeCoopState* st, bool second) {
     DR_THREAD_LOOP(t, ctx) {
         TeCoopState& s = st[t / COOP_LANES];
-        if (s.live && t % COOP_LANES == 0) s.tab[0].c[CDT] = s.tab[0].c[CT] * te_d();
+        TeCoopPoint* tab = second ? s.tab2 : s.tab;
+        if (s.live && t % COOP_LANES == 0) tab[0].c[CDT] = tab[0].c[CT] * te_d();
     }
     DR_BLOCK_SYNC();
-    for (uint32_t i = 2; i <= 15; i++) {
+    for (uint32_t i = 2; i <= 15; i++) {  // 2P = dbl(P), 3P = 2P + P, 4P = dbl(2P), ...
         DR_THREAD_LOOP(t, ctx) {
             TeCoopState& s = st[t / COOP_LANES];
+            TeCoopPoint* tab = second ? s.tab2 : s.tab;
             if (s.live) {
-                if (i & 1) coop_add_layer1(t % COOP_LANES, s.tab[i - 2], s.tab[0], s.m);
-                else coop_dbl_layer1(t % COOP_LANES, s.tab[i / 2 - 1], s.m);
+                if (i & 1) coop_add_layer1(t % COOP_LANES, tab[i - 2], tab[0], s.m);
+                else coop_dbl_layer1(t % COOP_LANES, tab[i / 2 - 1], s.m);
             }
         }
         DR_BLOCK_SYNC();
         DR_THREAD_LOOP(t, ctx) {
             TeCoopState& s = st[t / COOP_LANES];
+            TeCoopPoint* tab = second ? s.tab2 : s.tab;
             if (s.live) {
-                if (i & 1) coop_add_layer2(t % COOP_LANES, s.m, s.tab[i - 1]);
-                else coop_dbl_layer2(t % COOP_LANES, s.m, s.tab[i - 1]);
+                if (i & 1) coop_add_layer2(t % COOP_LANES, s.m, tab[i - 1]);
+                else coop_dbl_layer2(t % COOP_LANES, s.m, tab[i - 1]);
             }
         }
         DR_BLOCK_SYNC();
     }
     DR_THREAD_LOOP(t, ctx) {
         TeCoopState& s = st[t / COOP_LANES];
+        TeCoopPoint* tab = second ? s.tab2 : s.tab;
         const uint32_t lane = t % COOP_LANES;
-        if (s.live) {
-            for (uint32_t e = lane ? lane : COOP_LANES; e < 15; e += COOP_LANES) s.tab[e].c[CDT] = s.tab[e].c[CT] * te_d();  // entry 0 already has it
-            if (lane == 0) {
-                s.acc.c[CX] = Fr::zero();
-                s.acc.c[CY] = Fr::one();
-                s.acc.c[CZ] = Fr::one();
-                s.acc.c[CT] = Fr::zero();
-            }
+        if (s.live)
+            for (uint32_t e = lane ? lane : COOP_LANES; e < 15; e += COOP_LANES) tab[e].c[CDT] = tab[e].c[CT] * te_d();  // entry 0 already has it
+    }
+    DR_BLOCK_SYNC();
+}
+
+// acc <- k * P (+ k2 * Q when nlimbs2 > 0) for every live item of the block: Straus with shared doublings.  Before the call (and a
+// block sync): st[item].tab[0] = P (and tab2[0] = Q) in extended coordinates, st[item].k / k2 = the scalars (raw limbs, nlimbs /
+// nlimbs2 of them significant, nlimbs >= nlimbs2), st[item].live set.  After the call (which ends in a sync) st[item].acc holds
+// X, Y, Z, T.  4-bit fixed windows, most significant first, like te_mul_raw / te_msm_small; the formulas are complete on the
+// prime-order subgroup (and for the identity), so leading zero windows simply double the identity.
+DR_HD void te_straus_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs, int nlimbs2) {
+    te_table_coop(ctx, st, false);
+    if (nlimbs2 > 0) te_table_coop(ctx, st, true);
+    DR_THREAD_LOOP(t, ctx) {
+        TeCoopState& s = st[t / COOP_LANES];
+        if (s.live && t % COOP_LANES == 0) {
+            s.acc.c[CX] = Fr::zero();
+            s.acc.c[CY] = Fr::one();
+            s.acc.c[CZ] = Fr::one();
+            s.acc.c[CT] = Fr::zero();
         }
     }
     DR_BLOCK_SYNC();
@@ -143,20 +158,32 @@ DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) {
                 DR_BLOCK_SYNC();
             }
         }
-        DR_THREAD_LOOP(t, ctx) {
-            TeCoopState& s = st[t / COOP_LANES];
-            const uint32_t d = (s.k[w >> 3] >> (4 * (w & 7))) & 15u;
-            if (s.live && d) coop_add_layer1(t % COOP_LANES, s.acc, s.tab[d - 1], s.m);
+        for (int which = 0; which < (w < 8 * nlimbs2 ? 2 : 1); which++) {
+            DR_THREAD_LOOP(t, ctx) {
+                TeCoopState& s = st[t / COOP_LANES];
+                const uint32_t d = ((which ? s.k2 : s.k)[w >> 3] >> (4 * (w & 7))) & 15u;
+                if (s.live && d) coop_add_layer1(t % COOP_LANES, s.acc, (which ? s.tab2 : s.tab)[d - 1], s.m);
+            }
+            DR_BLOCK_SYNC();
+            DR_THREAD_LOOP(t, ctx) {
+                TeCoopState& s = st[t / COOP_LANES];
+                const uint32_t d = ((which ? s.k2 : s.k)[w >> 3] >> (4 * (w & 7))) & 15u;
+                if (s.live && d) coop_add_layer2(t % COOP_LANES, s.m, s.acc);
+            }
+            DR_BLOCK_SYNC();
         }
-        DR_BLOCK_SYNC();
-        DR_THREAD_LOOP(t, ctx) {
-            TeCoopState& s = st[t / COOP_LANES];
-            const uint32_t d = (s.k[w >> 3] >> (4 * (w & 7))) & 15u;
-            if (s.live && d) coop_add_layer2(t % COOP_LANES, s.m, s.acc);
-        }
-        DR_BLOCK_SYNC();
     }
 }
+DR_HD void te_mul_coop(const BlockCtx& ctx, TeCoopState* st, int nlimbs) { te_straus_coop(ctx, st, nlimbs, 0); }
+
+// helpers for the callers: load an operand / read the result
+DR_HD void coop_set_point(TeCoopPoint& dst, const TEExt& p) {
+    dst.c[CX] = p.X;
+    dst.c[CY] = p.Y;
+    dst.c[CZ] = p.Z;
+    dst.c[CT] = p.T;
+}
+DR_HD TEExt coop_get_point(const TeCoopPoint& src) { return {src.c[CX], src.c[CY], src.c[CZ], src.c[CT]}; }
 
 // part[lane] <- sum over the lane's four windows of the fixed-base table entries selected by k (te_mul_fixed split by windows).
 // One phase, no sync inside: the caller syncs, then one lane folds the eight partial sums with te_fold_fixed_coop.

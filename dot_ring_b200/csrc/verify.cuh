@@ -8,9 +8,9 @@
 //   dot_ring/ring_proof/transcript/phases.py:46-69      derive_challenges_after_vk
 //   dot_ring/ring_proof/verify.py:51-210                quotient / linearisation terms, two LinearPcsVerifications
 //   dot_ring/ring_proof/pcs/kzg.py:56-108,304-338       random-linear-combined KZG check, 2 Miller loops + final exp
-// Work is split so that every launch has (items x sub-tasks) threads: point decodes (sqrt + subgroup check) and
-// G1 scalar multiplications are one thread per (item, point); transcripts / scalar algebra / pairing are one
-// thread per item.  Verdict codes: 1 valid, 0 invalid, 2 malformed (where the reference raises ValueError).
+// Work is split so that every launch has (items x sub-tasks) threads: point decodes (sqrt + subgroup check) are one thread per
+// (item, point), G1 scalar multiplications one per (item, term, GLV half), the Bandersnatch equations of the VRF schemes run on
+// eight cooperating lanes per item (te_coop.cuh), ring transcripts / scalar algebra on one thread per item, the pairing on a warp.  Verdict codes: 1 valid, 0 invalid, 2 malformed (where the reference raises ValueError).
 #pragma once
 #include "pairing.cuh"
 #include "pairing_warp.cuh"
@@ -20,7 +20,7 @@ namespace dr {
 
 struct SuiteDev {  // VRF suite constants (dot_ring/curve/specs/bandersnatch.py:48-107)
     TEAffine generator, blinding_base;
-    const TEPre* g_tab;  // te_mul_fixed tables; set by the provers only (the verifiers' multiplications are joint, te_msm_small)
+    const TEPre* g_tab;  // te_mul_fixed tables of the generator / blinding base (provers and the Pedersen verifier)
     const TEPre* b_tab;
     uint32_t suite_id_len;
     uint8_t suite_id[32];
@@ -56,138 +56,257 @@ struct TeDecodeManyBody {
     }
 };
 
-// Pedersen verification equations for one decoded proof; pts = O, Ybar, R, Ok.  Returns status bits.
-template <class S>
-DR_HD_COLD uint32_t pedersen_verify_core(const S& su, const TEAffine* pts, const uint8_t* ok4, const uint8_t* proof192, const uint8_t* msg, uint32_t msg_len,
-                                         const uint8_t* ad, uint32_t ad_len) {
-    if (!(ok4[0] && ok4[1] && ok4[2] && ok4[3])) return ST_MALFORMED;
-    uint32_t ks[3][8];
-    load_le_limbs8(ks[0], proof192 + 128, 32);  // s
-    load_le_limbs8(ks[1], proof192 + 160, 32);  // sb
-    if (Fn::geq_mod(ks[0]) || Fn::geq_mod(ks[1])) return ST_MALFORMED;
-    TEAffine input = vrf_encode_to_curve(su, msg, msg_len);
-    VrfHash tr;
-    tr.init(su.hash_kind);
-    tr.update(su.suite_id, su.suite_id_len);
-    tr.update_byte(0x02);
-    uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    tr.update(le, 8);
-    sha_absorb_point(tr, input);
-    sha_absorb_point(tr, pts[0]);
-    for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(ad_len >> (8 * i)) : 0;
-    tr.update(le, 8);
-    tr.update(ad, ad_len);
-    sha_absorb_point(tr, pts[1]);
-    tr.update_byte(0x40);
-    sha_absorb_point(tr, pts[2]);
-    sha_absorb_point(tr, pts[3]);
-    uint8_t cb[16];
-    vrf_squeeze(tr, cb, 16);
-    uint32_t c[8];
-    load_le_limbs8(c, cb, 16);
-    // s*I - c*O == Ok
-    TEAffine p2[3];
-    uint32_t k2[3][8];
-    p2[0] = input;
-    p2[1] = te_neg(pts[0]);
-    for (int i = 0; i < 8; i++) {
-        k2[0][i] = ks[0][i];
-        k2[1][i] = c[i];
-    }
-    bool ok = te_ext_eq_affine(te_msm_small(p2, k2, 2), pts[3]);
-    // s*G + sb*B - c*Ybar == R
-    p2[0] = su.generator;
-    p2[1] = su.blinding_base;
-    p2[2] = te_neg(pts[1]);
-    for (int i = 0; i < 8; i++) {
-        k2[1][i] = ks[1][i];
-        k2[2][i] = c[i];
-    }
-    ok = ok && te_ext_eq_affine(te_msm_small(p2, k2, 3), pts[2]);
-    return ok ? 0u : ST_PEDERSEN_BAD;
-}
-
-// one thread per proof; pts / ok hold the 4 decoded points of every proof
+// Pedersen verification, eight threads per proof (te_coop.cuh); pts / ok hold the 4 decoded points of every proof.
+// One thread per proof ran ~7 k dependent field multiplications (7 ms whatever the batch size, 255 registers, 12 % occupancy); here
+// the Elligator maps take two lanes, s*I - c*O is a cooperative two-point Straus, c*Ybar a cooperative 128-bit multiplication and
+// s*G + sb*B come from the fixed-base window tables, split by windows over the lanes.
+DR_HD size_t vrf_verify_coop_smem(uint32_t threads) { return (threads / COOP_LANES) * (sizeof(TeCoopState) + 2 * sizeof(TEAffine) + 16); }
 struct PedersenVerifyBody {
     DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t proof_stride, const TEAffine* pts,
                           const uint8_t* ok, uint32_t count, uint32_t* status) const {
+        const uint32_t items = ctx.nthreads / COOP_LANES;
+        TeCoopState* cs = (TeCoopState*)ctx.smem;
+        TEAffine* maps = (TEAffine*)(cs + items);             // [items][2]
+        uint32_t* good = (uint32_t*)(maps + 2 * items);        // [items]: first equation holds
+        auto malformed = [&](uint32_t p) {
+            const uint8_t* o = ok + 4 * (size_t)p;
+            uint32_t ks[8], kb[8];
+            load_le_limbs8(ks, proofs + (size_t)proof_stride * p + 128, 32);
+            load_le_limbs8(kb, proofs + (size_t)proof_stride * p + 160, 32);
+            return !(o[0] && o[1] && o[2] && o[3]) || Fn::geq_mod(ks) || Fn::geq_mod(kb);
+        };
+        // A. decode status; hash-to-curve maps on lanes 0 and 1
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t i = ctx.bx * ctx.nthreads + t;
-            if (i < count) {
-                const VerifyInput& vi = in[i];
-                status[i] = pedersen_verify_core(su, pts + 4 * (size_t)i, ok + 4 * (size_t)i, proofs + (size_t)proof_stride * i, blob + vi.in_off, vi.in_len, blob + vi.ad_off,
-                                                 vi.ad_len);
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            const bool bad = p < count && malformed(p);
+            if (lane == 0) {
+                cs[item].live = p < count && !bad ? 1u : 0u;
+                if (p < count) status[p] = bad ? ST_MALFORMED : 0u;
+            }
+            if (p < count && !bad && lane < 2) {
+                const VerifyInput& vi = in[p];
+                uint8_t u[96];
+                h2c_uniform_bytes(su, blob + vi.in_off, vi.in_len, u);
+                maps[2 * item + lane] = te_map_to_curve_ell2(fr_from_be48_mod(u + 48 * lane));
+            }
+        }
+        DR_BLOCK_SYNC();
+        // B. input point, transcript, challenge; operands of s*I - c*O
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const VerifyInput& vi = in[p];
+                const TEAffine* pt = pts + 4 * (size_t)p;  // O, Ybar, R, Ok
+                const uint8_t* pr = proofs + (size_t)proof_stride * p;
+                TEExt sum = te_add(TEExt::from_affine(maps[2 * item]), TEExt::from_affine(maps[2 * item + 1]));
+                const TEAffine input = te_to_affine(te_dbl(te_dbl(sum)));
+                VrfHash tr;
+                tr.init(su.hash_kind);
+                tr.update(su.suite_id, su.suite_id_len);
+                tr.update_byte(0x02);
+                uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+                tr.update(le, 8);
+                sha_absorb_point(tr, input);
+                sha_absorb_point(tr, pt[0]);
+                for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(vi.ad_len >> (8 * i)) : 0;
+                tr.update(le, 8);
+                tr.update(blob + vi.ad_off, vi.ad_len);
+                sha_absorb_point(tr, pt[1]);
+                tr.update_byte(0x40);
+                sha_absorb_point(tr, pt[2]);
+                sha_absorb_point(tr, pt[3]);
+                uint8_t cb[16];
+                vrf_squeeze(tr, cb, 16);
+                coop_set_point(s.tab[0], TEExt::from_affine(input));
+                coop_set_point(s.tab2[0], TEExt::from_affine(te_neg(pt[0])));
+                load_le_limbs8(s.k, pr + 128, 32);  // s
+                load_le_limbs8(s.k2, cb, 16);       // c
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_straus_coop(ctx, cs, 8, 4);
+        // C. s*I - c*O == Ok ?  then the operand of -c*Ybar
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const TEAffine* pt = pts + 4 * (size_t)p;
+                good[item] = te_ext_eq_affine(coop_get_point(s.acc), pt[3]) ? 1u : 0u;
+                coop_set_point(s.tab[0], TEExt::from_affine(te_neg(pt[1])));
+                for (int i = 0; i < 8; i++) s.k[i] = s.k2[i];
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_straus_coop(ctx, cs, 4, 0);
+        // D. s*G by table windows; E. fold it, sb*B by table windows; F. s*G + sb*B - c*Ybar == R ?
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live) {
+                uint32_t ks[8];
+                load_le_limbs8(ks, proofs + (size_t)proof_stride * p + 128, 32);
+                te_mul_fixed_coop_partial(lane, su.g_tab, ks, s.part);
+            }
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            TeCoopState& s = cs[t / COOP_LANES];
+            if (s.live && t % COOP_LANES == 0) coop_set_point(s.acc, te_add(coop_get_point(s.acc), te_fold_fixed_coop(s.part)));
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live) {
+                uint32_t kb[8];
+                load_le_limbs8(kb, proofs + (size_t)proof_stride * p + 160, 32);
+                te_mul_fixed_coop_partial(lane, su.b_tab, kb, s.part);
+            }
+        }
+        DR_BLOCK_SYNC();
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const TEAffine* pt = pts + 4 * (size_t)p;
+                const TEExt total = te_add(coop_get_point(s.acc), te_fold_fixed_coop(s.part));
+                status[p] = (good[item] && te_ext_eq_affine(total, pt[2])) ? 0u : ST_PEDERSEN_BAD;
             }
         }
     }
 };
 
-// Tiny (ietf/tiny.py:72-83) and Thin (ietf/thin.py:84-99) verification, one thread per item.  Both schemes share the
+// Tiny (ietf/tiny.py:72-83) and Thin (ietf/thin.py:84-99) verification, eight threads per item.  Both schemes share the
 // transcript over the two I/O pairs (G, PK), (I, O) and the delinearised pair (G + z I, PK + z O); they differ in the
 // scheme byte and in what the proof carries:  tiny  O (32) | c (16) | s (32): recompute R, compare the challenge;
 //                                              thin  O (32) | R (32) | s (32): derive c from R, check s I' - c O' == R.
 // pts = decoded points per item: [O, PK] (tiny) or [O, R, PK] (thin).  status bit0 malformed, bit1 invalid.
+// z*I and z*O are cooperative 128-bit multiplications, s*I' - c*O' a cooperative two-point Straus (te_coop.cuh).
 struct IetfVerifyBody {
     DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, uint32_t thin, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, const TEAffine* pts,
                           const uint8_t* ok, uint32_t count, uint32_t* status) const {
         const uint32_t npts = thin ? 3 : 2, plen = thin ? 96 : 80;
+        const uint32_t items = ctx.nthreads / COOP_LANES;
+        TeCoopState* cs = (TeCoopState*)ctx.smem;
+        TEAffine* maps = (TEAffine*)(cs + items);  // [items][2]; after step B: maps[2 item] = the input point
+        auto malformed = [&](uint32_t p) {
+            uint32_t ks[8];
+            load_le_limbs8(ks, proofs + (size_t)plen * p + (thin ? 64 : 48), 32);  // s
+            bool decoded = true;
+            for (uint32_t j = 0; j < npts; j++) decoded = decoded && ok[(size_t)npts * p + j];
+            return !decoded || Fn::geq_mod(ks);
+        };
+        // A. decode status; hash-to-curve maps on lanes 0 and 1
         DR_THREAD_LOOP(t, ctx) {
-            uint32_t i = ctx.bx * ctx.nthreads + t;
-            if (i < count) {
-                const VerifyInput& vi = in[i];
-                const uint8_t* pr = proofs + (size_t)plen * i;
-                uint32_t st = 0;
-                uint32_t ks[2][8];
-                load_le_limbs8(ks[0], pr + (thin ? 64 : 48), 32);  // s
-                bool decoded = true;
-                for (uint32_t j = 0; j < npts; j++) decoded = decoded && ok[(size_t)npts * i + j];
-                if (!decoded || Fn::geq_mod(ks[0])) st = ST_MALFORMED;
-                if (!st) {
-                    const TEAffine out = pts[(size_t)npts * i], pk = pts[(size_t)npts * i + npts - 1];
-                    TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            const bool bad = p < count && malformed(p);
+            if (lane == 0) {
+                cs[item].live = p < count && !bad ? 1u : 0u;
+                if (p < count) status[p] = bad ? ST_MALFORMED : 0u;
+            }
+            if (p < count && !bad && lane < 2) {
+                const VerifyInput& vi = in[p];
+                uint8_t u[96];
+                h2c_uniform_bytes(su, blob + vi.in_off, vi.in_len, u);
+                maps[2 * item + lane] = te_map_to_curve_ell2(fr_from_be48_mod(u + 48 * lane));
+            }
+        }
+        DR_BLOCK_SYNC();
+        // transcript up to the additional data (shared by steps B and E)
+        auto transcript = [&](uint32_t p, const TEAffine& input, VrfHash& tr) {
+            const VerifyInput& vi = in[p];
+            tr.init(su.hash_kind);
+            tr.update(su.suite_id, su.suite_id_len);
+            tr.update_byte(thin ? 0x01 : 0x00);
+            uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+            tr.update(le, 8);
+            sha_absorb_point(tr, su.generator);
+            sha_absorb_point(tr, pts[(size_t)npts * p + npts - 1]);
+            sha_absorb_point(tr, input);
+            sha_absorb_point(tr, pts[(size_t)npts * p]);
+            for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
+            tr.update(le, 8);
+            tr.update(blob + vi.ad_off, vi.ad_len);
+        };
+        // B. input point; delinearisation scalar z (primitives.py:128-144); operand of z*I
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                TEExt sum = te_add(TEExt::from_affine(maps[2 * item]), TEExt::from_affine(maps[2 * item + 1]));
+                const TEAffine input = te_to_affine(te_dbl(te_dbl(sum)));
+                maps[2 * item] = input;
+                VrfHash tr;
+                transcript(p, input, tr);
+                tr.update_byte(0x30);
+                uint8_t zb[16];
+                vrf_squeeze(tr, zb, 16);
+                load_le_limbs8(s.k, zb, 16);
+                coop_set_point(s.tab[0], TEExt::from_affine(input));
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_straus_coop(ctx, cs, 4, 0);
+        // C. I' = G + z*I (first operand of the final Straus); operand of z*O
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const TEExt merged_in = te_add(TEExt::from_affine(su.generator), coop_get_point(s.acc));
+                coop_set_point(s.tab2[0], merged_in);  // parked: the next multiplication only uses tab
+                coop_set_point(s.tab[0], TEExt::from_affine(pts[(size_t)npts * p]));
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_straus_coop(ctx, cs, 4, 0);
+        // D. O' = PK + z*O; operands of s*I' - c*O'
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const uint8_t* pr = proofs + (size_t)plen * p;
+                const TEExt merged_out = te_add(TEExt::from_affine(pts[(size_t)npts * p + npts - 1]), coop_get_point(s.acc));
+                const TEExt merged_in = coop_get_point(s.tab2[0]);
+                coop_set_point(s.tab[0], merged_in);
+                coop_set_point(s.tab2[0], te_neg(merged_out));
+                load_le_limbs8(s.k, pr + (thin ? 64 : 48), 32);  // s
+                if (thin) {  // c from the transcript extended by R
                     VrfHash tr;
-                    tr.init(su.hash_kind);
-                    tr.update(su.suite_id, su.suite_id_len);
-                    tr.update_byte(thin ? 0x01 : 0x00);
-                    uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
-                    tr.update(le, 8);
-                    sha_absorb_point(tr, su.generator);
-                    sha_absorb_point(tr, pk);
-                    sha_absorb_point(tr, input);
-                    sha_absorb_point(tr, out);
-                    for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
-                    tr.update(le, 8);
-                    tr.update(blob + vi.ad_off, vi.ad_len);
-                    // delinearisation scalar z (primitives.py:128-144), merged pair (G + z I, PK + z O)
-                    VrfHash td = tr;
-                    td.update_byte(0x30);
-                    uint8_t zb[16];
-                    vrf_squeeze(td, zb, 16);
-                    uint32_t z[8];
-                    load_le_limbs8(z, zb, 16);
-                    TEExt min = te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4));
-                    TEExt mout = te_add(TEExt::from_affine(pk), te_mul_raw(out, z, 4));
-                    TEAffine p2[2] = {te_to_affine(min), te_neg(te_to_affine(mout))};
+                    transcript(p, maps[2 * item], tr);
                     tr.update_byte(0x40);
-                    if (thin) {
-                        const TEAffine r = pts[(size_t)npts * i + 1];
-                        sha_absorb_point(tr, r);
-                        uint8_t cb[16];
-                        vrf_squeeze(tr, cb, 16);
-                        load_le_limbs8(ks[1], cb, 16);
-                        if (!te_ext_eq_affine(te_msm_small(p2, ks, 2), r)) st = ST_PEDERSEN_BAD;
-                    } else {
-                        load_le_limbs8(ks[1], pr + 32, 16);  // c
-                        TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
-                        sha_absorb_point(tr, r);
-                        uint8_t cb[16];
-                        vrf_squeeze(tr, cb, 16);
-                        bool same = true;
-                        for (int b = 0; b < 16; b++) same = same && (cb[b] == pr[32 + b]);
-                        if (!same) st = ST_PEDERSEN_BAD;
-                    }
+                    sha_absorb_point(tr, pts[(size_t)npts * p + 1]);
+                    uint8_t cb[16];
+                    vrf_squeeze(tr, cb, 16);
+                    load_le_limbs8(s.k2, cb, 16);
+                } else {
+                    load_le_limbs8(s.k2, pr + 32, 16);  // c
                 }
-                status[i] = st;
+            }
+        }
+        DR_BLOCK_SYNC();
+        te_straus_coop(ctx, cs, 8, 4);
+        // E. verdict
+        DR_THREAD_LOOP(t, ctx) {
+            const uint32_t item = t / COOP_LANES, lane = t % COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live && lane == 0) {
+                const uint8_t* pr = proofs + (size_t)plen * p;
+                const TEExt res = coop_get_point(s.acc);  // s*I' - c*O'
+                bool valid;
+                if (thin) {
+                    valid = te_ext_eq_affine(res, pts[(size_t)npts * p + 1]);
+                } else {
+                    VrfHash tr;
+                    transcript(p, maps[2 * item], tr);
+                    tr.update_byte(0x40);
+                    sha_absorb_point(tr, te_to_affine(res));
+                    uint8_t cb[16];
+                    vrf_squeeze(tr, cb, 16);
+                    valid = true;
+                    for (int b = 0; b < 16; b++) valid = valid && (cb[b] == pr[32 + b]);
+                }
+                status[p] = valid ? 0u : ST_PEDERSEN_BAD;
             }
         }
     }
@@ -285,7 +404,7 @@ struct VerifyState {
     uint32_t status;
     G1Affine g1[7];  // C_b, C_accip, C_accx, C_accy, C_q, Phi_zeta, Phi_zeta_omega
     Fr sc[VERIFY_TERMS];
-    G1 term[VERIFY_TERMS];
+    G1 term[2 * VERIFY_TERMS];  // sc[j] * base_j as two GLV halves: term[2j] = k1 * P, term[2j + 1] = k2 * phi(P)
 };
 
 // 7 G1 decompressions per payload, one thread per point (proof_payload.py:93-118, kzg.py:137-144)
@@ -413,9 +532,14 @@ struct RingVerifyAlgebraBody {
 
 // k * P for a Montgomery Fr scalar and an affine base: 4-bit windows over the affine multiples 1P .. 15P (one shared
 // inversion), so every window costs 4 doublings + 1 mixed addition
+DR_HD_COLD G1 g1_mul_raw(const G1Affine& p, const uint32_t* k, int nlimbs);
 DR_HD_COLD G1 g1_mul_fr(const G1Affine& p, const Fr& k_mont) {
-    if (p.is_inf()) return G1::inf();
     Fr k = k_mont.from_mont();
+    return g1_mul_raw(p, k.v, 8);
+}
+// k: raw little-endian limbs
+DR_HD_COLD G1 g1_mul_raw(const G1Affine& p, const uint32_t* k, int nlimbs) {
+    if (p.is_inf()) return G1::inf();
     G1 proj[16];
     proj[1] = G1::from_affine(p);
 #pragma unroll 1
@@ -447,27 +571,36 @@ DR_HD_COLD G1 g1_mul_fr(const G1Affine& p, const Fr& k_mont) {
     }
     G1 r = G1::inf();
 #pragma unroll 1
-    for (int i = 7; i >= 0; i--) {
+    for (int i = nlimbs - 1; i >= 0; i--) {
 #pragma unroll 1
         for (int sft = 28; sft >= 0; sft -= 4) {
             if (!r.is_inf()) r = g1_dbl(g1_dbl(g1_dbl(g1_dbl(r))));
-            uint32_t d = (k.v[i] >> sft) & 15;
+            uint32_t d = (k[i] >> sft) & 15;
             if (d) g1_madd(r, tab[d]);
         }
     }
     return r;
 }
 
-// one thread per (proof, term)
+// one thread per (proof, term, GLV half): sc * P = k1 * P + k2 * phi(P) with 128-bit k1, k2 (msm.cuh glv_half), phi(x, y) = (beta x, y):
+// half the doublings of a 255-bit multiplication, on twice the threads
 struct RingVerifyTermsBody {
     DR_HD void operator()(const BlockCtx& ctx, VerifierKeyDev vk, uint32_t count, VerifyState* vs) const {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t i = ctx.bx * ctx.nthreads + t;
-            if (i < VERIFY_TERMS * count) {
-                uint32_t p = i / VERIFY_TERMS, j = i % VERIFY_TERMS;
+            if (i < 2 * VERIFY_TERMS * count) {
+                uint32_t p = i / (2 * VERIFY_TERMS), r = i % (2 * VERIFY_TERMS), j = r >> 1, h = r & 1;
                 VerifyState& s = vs[p];
-                const G1Affine& base = j < 7 ? s.g1[j] : j < 9 ? s.g1[j - 2] : vk.fixed[j - 9];
-                s.term[j] = (s.status & ST_MALFORMED) ? G1::inf() : g1_mul_fr(base, s.sc[j]);
+                G1Affine base = j < 7 ? s.g1[j] : j < 9 ? s.g1[j - 2] : vk.fixed[j - 9];
+                G1 out = G1::inf();
+                if (!(s.status & ST_MALFORMED) && !base.is_inf()) {
+                    Fr k = s.sc[j].from_mont();
+                    uint32_t half[8];
+                    glv_half(k.v, h, half);
+                    if (h) base.x = base.x * glv_beta();
+                    out = g1_mul_raw(base, half, 4);
+                }
+                s.term[r] = out;
             }
         }
     }
@@ -475,10 +608,10 @@ struct RingVerifyTermsBody {
 
 DR_HD void ring_verify_sides(const VerifyState& s, G1& lhs, G1& rhs) {
     lhs = s.term[0];
-    for (int j = 1; j < 7; j++) g1_add(lhs, s.term[j]);
-    for (int j = 9; j < VERIFY_TERMS; j++) g1_add(lhs, s.term[j]);
-    rhs = s.term[7];
-    g1_add(rhs, s.term[8]);
+    for (int j = 1; j < 2 * 7; j++) g1_add(lhs, s.term[j]);
+    for (int j = 2 * 9; j < 2 * VERIFY_TERMS; j++) g1_add(lhs, s.term[j]);
+    rhs = s.term[2 * 7];
+    for (int j = 2 * 7 + 1; j < 2 * 9; j++) g1_add(rhs, s.term[j]);
 }
 
 // per-item verdicts: one 32-thread block per proof runs the warp-cooperative pairing check.
@@ -499,16 +632,12 @@ struct RingVerifyFinishBody {
             return;
         }
         DR_THREAD_LOOP(t, ctx) {
-            if (t == 0) {
-                G1 lhs = s.term[0];
-                for (int j = 1; j < 7; j++) g1_add(lhs, s.term[j]);
-                for (int j = 9; j < VERIFY_TERMS; j++) g1_add(lhs, s.term[j]);
-                P[0] = lhs;
-            }
-            if (t == 1) {
-                G1 rhs = s.term[7];
-                g1_add(rhs, s.term[8]);
-                P[1] = g1_neg(rhs);  // e(lhs, [1]_2) * e(-rhs, [tau]_2) == 1
+            if (t < 2) {  // both lanes fold one side (same code path: no divergence)
+                const int lo = t == 0 ? 0 : 2 * 7, mid = t == 0 ? 2 * 7 : 2 * 9, lo2 = t == 0 ? 2 * 9 : 0, hi2 = t == 0 ? 2 * VERIFY_TERMS : 0;
+                G1 acc = s.term[lo];
+                for (int j = lo + 1; j < mid; j++) g1_add(acc, s.term[j]);
+                for (int j = lo2; j < hi2; j++) g1_add(acc, s.term[j]);
+                P[t] = t == 0 ? acc : g1_neg(acc);  // e(lhs, [1]_2) * e(-rhs, [tau]_2) == 1
             }
         }
         DR_BLOCK_SYNC();

@@ -88,9 +88,16 @@ c3 = {"ring_create_incl_root_gpu_s": dt_ring, "cpu_ring_ingest_s": t_oring, "cpu
 for nn, batch in ((2048, 4096), (6145, 1024), (2048, 1)):
     ms, _ = srs.commit_bench(nn, batch, 3, seed=nn)
     c3["commit"].append({"n": nn, "batch": batch, "ms": ms, "coefficients_per_s": nn * batch / (ms * 1e-3)})
+imad_peak = ctx.microbench("imad", 20000)[0]
+out["imad_peak_measured"] = imad_peak
 for k in range(11, 21):
-    ms, c, res = ctx.g1_msm_bench(1 << k, 3, 7, 0, msm_cases.TAU)
-    c3["msm_sweep"].append({"log2_n": k, "window_bits": c, "ms": ms, "points_per_s": (1 << k) / (ms * 1e-3), "parity": res == msm_cases.expected_synthetic(1 << k, 7, 0) if k in (11, 14, 20) else None})
+    nn = 1 << k
+    ms, c, res = ctx.g1_msm_bench(nn, 3, 7, 0, msm_cases.TAU)
+    # canonical Pippenger work: min_c ceil(255/c) (10 n + 14 2^c) Fq mul, 600 IMAD each
+    canon = min(-(-255 // cc) * (nn * 10 + (1 << cc) * 14) for cc in range(2, 21)) * 600
+    c3["msm_sweep"].append({"log2_n": k, "window_bits": c, "ms": ms, "points_per_s": nn / (ms * 1e-3), "parity": res == msm_cases.expected_synthetic(nn, 7, 0),
+                            "roofline": {"bound": "imad", "achieved": canon / (ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s (canonical Pippenger count, SURVEY 8d)",
+                                         "frac": canon / (ms * 1e-3) / imad_peak}})
 # CPU: the oracle's C Pippenger on 2^14 real points would need 16k SRS points; time 6145
 from oracle import bls12_381 as bls  # noqa: E402
 osrs = rp.load_srs()
@@ -133,9 +140,12 @@ for kind in ("tiny", "pedersen"):
         else:
             ovrf.pedersen_verify(bs.SHA512, ovrf.PedersenProof.decode(proofs[i]), alphas[i], ads[i])
     cpu = 5 / (T() - t0)
+    canon_imad = 9000 * 272  # ~9 k Fr multiplications per verification (2 full + 2 half-length double-mults + ~4 sqrt / inversions), 272 IMAD each
     c4[kind] = {"n": N, "corrupted": len(range(0, N, 100)), "verdicts_exact": bool(good), "c_abi_host_buffers_s": dt, "verifies_per_s": N / dt, "cpu_verifies_per_s_1core": cpu,
-                "reference_published_ms": {"tiny": 1.97, "pedersen": 1.74}[kind]}
+                "reference_published_ms": {"tiny": 1.97, "pedersen": 1.74}[kind],
+                "roofline": {"bound": "imad", "achieved": canon_imad * N / dt / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s (canonical 2.45 M IMAD per verification, SURVEY 8d; host buffers in the timed region)",
+                             "frac": canon_imad * N / dt / imad_peak}}
     print("config4", kind, c4[kind], flush=True)
 out["config4_vrf_batch"] = c4
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/configs_report.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("REPORT_OUT", "gpurun_out/configs_report.json"), "w"), indent=1)

@@ -24,7 +24,7 @@ if has bench512; then
   done
 fi
 if has probe; then
-  python tools/gpu_probe_r2.py 1024 20000 10 > ${O}_probe.log 2>&1; echo "probe rc=$?"; cat ${O}_probe.log
+  python tools/gpu_probe_r2.py 1024 ${PROBE_ITEMS:-100000} 10 > ${O}_probe.log 2>&1; echo "probe rc=$?"; cat ${O}_probe.log
 fi
 if has timeline; then
   python tools/gpu_probe_timeline.py 10 > ${O}_timeline.log 2>&1; echo "timeline rc=$?"; grep -v "^\[dot_ring_b200\] prove: free" ${O}_timeline.log | tail -n 80
