@@ -114,6 +114,7 @@ class Library:
         L.dr_ring_proof_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int)]
         L.dr_ring_verify_batch.argtypes = [c_void_p, c_void_p, c_size_t] + [c_void_p] * 7 + [c_int, c_void_p, POINTER(c_int)]
         L.dr_ring_verify_set_msm_threshold.argtypes = [c_size_t]
+        L.dr_vrf_verify_set_coop_threshold.argtypes = [c_size_t]
         L.dr_pairing_check_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         L.dr_te_decode_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p]
         L.dr_te_msm.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]

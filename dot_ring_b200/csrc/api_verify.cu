@@ -99,8 +99,24 @@ static SuiteDev suite_from_abi(const dr_vrf_suite* s) {
     return d;
 }
 
-// cooperative verification kernels: eight lanes per item (te_coop.cuh), eight items per block
+// cooperative verification kernels: eight lanes per item (te_coop.cuh), eight items per block.  They cut the latency of an item
+// 3 - 4x but keep at most five of eight lanes busy, so batches large enough to fill the machine with one item per thread
+// (measured cross-over: a few thousand items) use the serial kernels.
 constexpr uint32_t VRF_VERIFY_THREADS = 64, VRF_VERIFY_ITEMS = VRF_VERIFY_THREADS / COOP_LANES;
+static std::atomic<size_t> VRF_VERIFY_COOP_BELOW{8192};
+
+static void launch_pedersen_verify(Ctx* ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t stride, const TEAffine* pts,
+                                   const uint8_t* ok, uint32_t m, uint32_t* status) {
+    if (m >= VRF_VERIFY_COOP_BELOW.load()) {
+        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenVerifySerialBody(), su, in, blob, proofs, stride, pts, ok, m, status);
+        return;
+    }
+    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);  // the context keeps them alive
+    su.g_tab = g_table->tab.p;
+    su.b_tab = b_table->tab.p;
+    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su, in, blob, proofs,
+           stride, pts, ok, m, status);
+}
 
 // uploads the per-item (offset, length) table and the blob; returns the device buffers
 struct ItemsDev {
@@ -222,6 +238,11 @@ int dr_ring_verify_set_msm_threshold(size_t n) {
     return DR_OK;
 }
 
+int dr_vrf_verify_set_coop_threshold(size_t n) {
+    VRF_VERIFY_COOP_BELOW = n;
+    return DR_OK;
+}
+
 int dr_pairing_check_batch(dr_ctx* c, const uint8_t* a1_be96, const uint8_t* b1_be192, const uint8_t* a2_be96, const uint8_t* b2_be192, size_t n, uint8_t* equal) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
@@ -260,11 +281,7 @@ int dr_pedersen_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, con
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs192, n * 192);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 192u, 4u, 4 * m, pts.p, dok.p);
-    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);
-    su.g_tab = g_table->tab.p;
-    su.b_tab = b_table->tab.p;
-    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su,
-           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    launch_pedersen_verify(ctx, su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
@@ -294,8 +311,12 @@ static void ietf_verify_batch(Ctx* ctx, const dr_vrf_suite* suite, uint32_t thin
     h2d(ctx->stream, denc.p, enc.data(), enc.size());
     h2d(ctx->stream, dpr.p, proofs, (size_t)plen * n);
     launch(ctx->stream, Dim3((npts * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)denc.p, 32u * npts, npts, npts * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), IetfVerifyBody(), su, thin,
-           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    if (m >= VRF_VERIFY_COOP_BELOW.load())
+        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfVerifySerialBody(), su, thin, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p,
+               (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    else
+        launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), IetfVerifyBody(), su, thin,
+               (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
@@ -410,8 +431,7 @@ int dr_ring_verify_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, c
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs784, n * 784);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 784u, 4u, 4 * m, pts.p, dok.p);
-    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), ring->suite,
-           (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    launch_pedersen_verify(ctx, ring->suite, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     // relation = blinded public key (second Pedersen point); payload follows the 192-byte Pedersen part
     ring_proof_verify_device(ctx, ring->vk, n, dpr.p + 192, 784, pts.p + 1, 4, coeffs_le32, dst.p, aggregate, verdict, all_ok);
     DR_API_END

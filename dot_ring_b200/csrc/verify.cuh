@@ -56,6 +56,144 @@ struct TeDecodeManyBody {
     }
 };
 
+// Pedersen verification equations for one decoded proof; pts = O, Ybar, R, Ok.  Returns status bits.
+template <class S>
+DR_HD_COLD uint32_t pedersen_verify_core(const S& su, const TEAffine* pts, const uint8_t* ok4, const uint8_t* proof192, const uint8_t* msg, uint32_t msg_len,
+                                         const uint8_t* ad, uint32_t ad_len) {
+    if (!(ok4[0] && ok4[1] && ok4[2] && ok4[3])) return ST_MALFORMED;
+    uint32_t ks[3][8];
+    load_le_limbs8(ks[0], proof192 + 128, 32);  // s
+    load_le_limbs8(ks[1], proof192 + 160, 32);  // sb
+    if (Fn::geq_mod(ks[0]) || Fn::geq_mod(ks[1])) return ST_MALFORMED;
+    TEAffine input = vrf_encode_to_curve(su, msg, msg_len);
+    VrfHash tr;
+    tr.init(su.hash_kind);
+    tr.update(su.suite_id, su.suite_id_len);
+    tr.update_byte(0x02);
+    uint8_t le[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    tr.update(le, 8);
+    sha_absorb_point(tr, input);
+    sha_absorb_point(tr, pts[0]);
+    for (int i = 0; i < 8; i++) le[i] = i < 4 ? (uint8_t)(ad_len >> (8 * i)) : 0;
+    tr.update(le, 8);
+    tr.update(ad, ad_len);
+    sha_absorb_point(tr, pts[1]);
+    tr.update_byte(0x40);
+    sha_absorb_point(tr, pts[2]);
+    sha_absorb_point(tr, pts[3]);
+    uint8_t cb[16];
+    vrf_squeeze(tr, cb, 16);
+    uint32_t c[8];
+    load_le_limbs8(c, cb, 16);
+    // s*I - c*O == Ok
+    TEAffine p2[3];
+    uint32_t k2[3][8];
+    p2[0] = input;
+    p2[1] = te_neg(pts[0]);
+    for (int i = 0; i < 8; i++) {
+        k2[0][i] = ks[0][i];
+        k2[1][i] = c[i];
+    }
+    bool ok = te_ext_eq_affine(te_msm_small(p2, k2, 2), pts[3]);
+    // s*G + sb*B - c*Ybar == R
+    p2[0] = su.generator;
+    p2[1] = su.blinding_base;
+    p2[2] = te_neg(pts[1]);
+    for (int i = 0; i < 8; i++) {
+        k2[1][i] = ks[1][i];
+        k2[2][i] = c[i];
+    }
+    ok = ok && te_ext_eq_affine(te_msm_small(p2, k2, 3), pts[2]);
+    return ok ? 0u : ST_PEDERSEN_BAD;
+}
+
+// One thread per proof (large batches: every lane of a warp busy with its own item, throughput-bound); pts / ok hold the 4 decoded
+// points of every proof.  Small batches use the eight-lane kernels below (latency-bound).
+struct PedersenVerifySerialBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t proof_stride, const TEAffine* pts,
+                          const uint8_t* ok, uint32_t count, uint32_t* status) const {
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                status[i] = pedersen_verify_core(su, pts + 4 * (size_t)i, ok + 4 * (size_t)i, proofs + (size_t)proof_stride * i, blob + vi.in_off, vi.in_len, blob + vi.ad_off,
+                                                 vi.ad_len);
+            }
+        }
+    }
+};
+
+// Tiny (ietf/tiny.py:72-83) and Thin (ietf/thin.py:84-99) verification, one thread per item (large batches).  Both schemes share the
+// transcript over the two I/O pairs (G, PK), (I, O) and the delinearised pair (G + z I, PK + z O); they differ in the
+// scheme byte and in what the proof carries:  tiny  O (32) | c (16) | s (32): recompute R, compare the challenge;
+//                                              thin  O (32) | R (32) | s (32): derive c from R, check s I' - c O' == R.
+// pts = decoded points per item: [O, PK] (tiny) or [O, R, PK] (thin).  status bit0 malformed, bit1 invalid.
+struct IetfVerifySerialBody {
+    DR_HD void operator()(const BlockCtx& ctx, SuiteDev su, uint32_t thin, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, const TEAffine* pts,
+                          const uint8_t* ok, uint32_t count, uint32_t* status) const {
+        const uint32_t npts = thin ? 3 : 2, plen = thin ? 96 : 80;
+        DR_THREAD_LOOP(t, ctx) {
+            uint32_t i = ctx.bx * ctx.nthreads + t;
+            if (i < count) {
+                const VerifyInput& vi = in[i];
+                const uint8_t* pr = proofs + (size_t)plen * i;
+                uint32_t st = 0;
+                uint32_t ks[2][8];
+                load_le_limbs8(ks[0], pr + (thin ? 64 : 48), 32);  // s
+                bool decoded = true;
+                for (uint32_t j = 0; j < npts; j++) decoded = decoded && ok[(size_t)npts * i + j];
+                if (!decoded || Fn::geq_mod(ks[0])) st = ST_MALFORMED;
+                if (!st) {
+                    const TEAffine out = pts[(size_t)npts * i], pk = pts[(size_t)npts * i + npts - 1];
+                    TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
+                    VrfHash tr;
+                    tr.init(su.hash_kind);
+                    tr.update(su.suite_id, su.suite_id_len);
+                    tr.update_byte(thin ? 0x01 : 0x00);
+                    uint8_t le[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+                    tr.update(le, 8);
+                    sha_absorb_point(tr, su.generator);
+                    sha_absorb_point(tr, pk);
+                    sha_absorb_point(tr, input);
+                    sha_absorb_point(tr, out);
+                    for (int b = 0; b < 8; b++) le[b] = b < 4 ? (uint8_t)(vi.ad_len >> (8 * b)) : 0;
+                    tr.update(le, 8);
+                    tr.update(blob + vi.ad_off, vi.ad_len);
+                    // delinearisation scalar z (primitives.py:128-144), merged pair (G + z I, PK + z O)
+                    VrfHash td = tr;
+                    td.update_byte(0x30);
+                    uint8_t zb[16];
+                    vrf_squeeze(td, zb, 16);
+                    uint32_t z[8];
+                    load_le_limbs8(z, zb, 16);
+                    TEExt min = te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4));
+                    TEExt mout = te_add(TEExt::from_affine(pk), te_mul_raw(out, z, 4));
+                    TEAffine p2[2] = {te_to_affine(min), te_neg(te_to_affine(mout))};
+                    tr.update_byte(0x40);
+                    if (thin) {
+                        const TEAffine r = pts[(size_t)npts * i + 1];
+                        sha_absorb_point(tr, r);
+                        uint8_t cb[16];
+                        vrf_squeeze(tr, cb, 16);
+                        load_le_limbs8(ks[1], cb, 16);
+                        if (!te_ext_eq_affine(te_msm_small(p2, ks, 2), r)) st = ST_PEDERSEN_BAD;
+                    } else {
+                        load_le_limbs8(ks[1], pr + 32, 16);  // c
+                        TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
+                        sha_absorb_point(tr, r);
+                        uint8_t cb[16];
+                        vrf_squeeze(tr, cb, 16);
+                        bool same = true;
+                        for (int b = 0; b < 16; b++) same = same && (cb[b] == pr[32 + b]);
+                        if (!same) st = ST_PEDERSEN_BAD;
+                    }
+                }
+                status[i] = st;
+            }
+        }
+    }
+};
+
 // Pedersen verification, eight threads per proof (te_coop.cuh); pts / ok hold the 4 decoded points of every proof.
 // One thread per proof ran ~7 k dependent field multiplications (7 ms whatever the batch size, 255 registers, 12 % occupancy); here
 // the Elligator maps take two lanes, s*I - c*O is a cooperative two-point Straus, c*Ybar a cooperative 128-bit multiplication and

@@ -275,6 +275,10 @@ int dr_ring_verify_batch(dr_ctx* ctx, dr_ring* ring, size_t n, const uint8_t* bl
  * per proof (default 8192; same verdicts, tests lower it to exercise the path on small batches). */
 int dr_ring_verify_set_msm_threshold(size_t n);
 
+/* Tiny / Thin / Pedersen batches below `n` items (default 8192) run the eight-lane cooperative kernels (3 - 4x lower latency per item),
+ * larger ones the one-thread-per-item kernels (higher throughput); same verdicts, tests drive both through this knob. */
+int dr_vrf_verify_set_coop_threshold(size_t n);
+
 /* ---- pairing check ------------------------------------------------------------------------------------------
  * Replaces `blst_miller_loop` + `blst_final_verify` (dot_ring/ring_proof/pcs/pairing.py:24-31) for a batch:
  * equal[i] = ( e(a1_i, b1_i) == e(a2_i, b2_i) ), G1 as 96-byte and G2 as 192-byte zcash uncompressed encodings

@@ -63,3 +63,16 @@ def test_edge_cases(ctx, srs):
     edge_cases.te_msm_matches_oracle(ctx)
     edge_cases.ring_capacity_and_bad_keys(srs)
     edge_cases.ragged_inputs_match_oracle(srs, ((512, 5),), n_items=2)
+
+
+def test_vrf_vectors_through_the_large_batch_kernels(ctx):
+    """Tiny / Thin / Pedersen batches above the cross-over use the one-thread-per-item kernels: same vectors, same verdicts."""
+    lib = ctx.library.lib
+    lib.dr_vrf_verify_set_coop_threshold(0)
+    try:
+        cases.pedersen_vectors(ctx)
+        cases.tiny_vectors(ctx)
+        cases.thin_vectors(ctx)
+        cases.vrf_batch_fixtures(ctx)
+    finally:
+        lib.dr_vrf_verify_set_coop_threshold(8192)

@@ -166,3 +166,16 @@ def test_domain_4096_with_a_larger_srs_matches_oracle(ctx):
     from tests import extended_domain
 
     extended_domain.prove_verify_against_oracle(ctx, domain=4096, n_keys=40, n_proofs=3, oracle_proofs=1, window_bits=8)
+
+
+def test_vrf_vectors_through_the_large_batch_kernels(ctx):
+    """Tiny / Thin / Pedersen batches above the cross-over use the one-thread-per-item kernels: same vectors, same verdicts."""
+    lib = ctx.library.lib
+    lib.dr_vrf_verify_set_coop_threshold(0)
+    try:
+        cases.pedersen_vectors(ctx)
+        cases.tiny_vectors(ctx)
+        cases.thin_vectors(ctx)
+        cases.vrf_batch_fixtures(ctx)
+    finally:
+        lib.dr_vrf_verify_set_coop_threshold(8192)
