@@ -181,6 +181,45 @@ const LagrangeTable& Srs::lagrange_table(uint32_t N, uint32_t logN, const Fr& om
 #define DR_COMMIT_MINB 4
 #endif
 
+// Slices per polynomial: the grid is (slices, batch) CTAs of which 4 are resident per SM, so batch * slices should fill a whole
+// number of waves -- a 2.6-wave grid runs as long as a 3-wave one (measured: 512 proofs x 3 slices cost 13 % more per proof
+// than 4096 x 1, which happens to be 6.92 waves).  Among the splits that keep >= 32 points per CTA take the one with the best
+// wave occupancy, smaller splits first (every CTA ends in a 7-level reduction tree).
+static uint32_t commit_slices(Ctx* ctx, uint32_t n, uint32_t batch) {
+    uint32_t slices = 1;
+    const uint32_t resident = ctx->sm_count() * DR_COMMIT_MINB;
+    const uint32_t finest = n / 32 ? n / 32 : 1;  // >= 32 points per CTA
+    if ((uint64_t)batch * finest <= resident) return finest;  // not even one wave: as many CTAs as the polynomial allows (single proofs, small batches)
+    const uint32_t max_slices = finest < 256 ? finest : 256;
+    double best = -1.0;
+    for (uint32_t s = 1; s <= max_slices; s++) {
+        const double waves = (double)batch * s / resident;
+        const double whole = (double)(uint64_t)(waves + 0.999999);
+        const double score = (waves < 1.0 ? waves : waves / whole) - 0.004 * s;
+        if (score > best + 1e-9) {
+            best = score;
+            slices = s;
+        }
+    }
+    return slices;
+}
+
+// the dense commit kernel alone: partials[b * slices + s] = XYZZ sum of slice s of polynomial b
+static void commit_launch(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, uint32_t slices, G1* partials) {
+    const uint32_t threads = COMMIT_THREADS;
+    PhaseTimer& pt = ctx->phases;
+    const int enclosing = pt.current;
+    if (pt.active) {
+        pt.mark(ctx, 6);
+        pt.kernel_launches++;
+    }
+    if (srs->geom.glv)
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials);
+    else
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials);
+    if (pt.active) pt.mark(ctx, enclosing);
+}
+
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine) {
     if (n == 0 || batch == 0) return;
     if (n > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
@@ -208,44 +247,29 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
         launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
         return;
     }
-    // Slices per polynomial: the grid is (slices, batch) CTAs of which 4 are resident per SM, so batch * slices should fill a whole
-    // number of waves -- a 2.6-wave grid runs as long as a 3-wave one (measured: 512 proofs x 3 slices cost 13 % more per proof
-    // than 4096 x 1, which happens to be 6.92 waves).  Among the splits that keep >= 64 points per CTA take the one with the best
-    // wave occupancy, smaller splits first (every CTA ends in a 7-level reduction tree).
-    uint32_t slices = 1;
-    {
-        const uint32_t resident = ctx->sm_count() * DR_COMMIT_MINB;
-        const uint32_t finest = n / 32 ? n / 32 : 1;  // >= 32 points per CTA
-        if ((uint64_t)batch * finest <= resident) {
-            slices = finest;  // not even one wave: as many CTAs as the polynomial allows (single proofs, small batches)
-        } else {
-            const uint32_t max_slices = finest < 256 ? finest : 256;
-            double best = -1.0;
-            for (uint32_t s = 1; s <= max_slices; s++) {
-                const double waves = (double)batch * s / resident;
-                const double whole = (double)(uint64_t)(waves + 0.999999);
-                const double score = (waves < 1.0 ? waves : waves / whole) - 0.004 * s;
-                if (score > best + 1e-9) {
-                    best = score;
-                    slices = s;
-                }
-            }
-        }
-    }
+    const uint32_t slices = commit_slices(ctx, n, batch);
     ctx->partials.ensure((size_t)batch * slices);
-    const uint32_t threads = COMMIT_THREADS;
-    PhaseTimer& pt = ctx->phases;
-    const int enclosing = pt.current;
-    if (pt.active) {
-        pt.mark(ctx, 6);
-        pt.kernel_launches++;
-    }
-    if (srs->geom.glv)
-        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
-    else
-        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, ctx->partials.p);
-    if (pt.active) pt.mark(ctx, enclosing);
+    commit_launch(ctx, srs, scalars, stride, n, batch, slices, ctx->partials.p);
     launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
+}
+
+// Two commitments of the same batch whose results nothing needs in between (the prover's two opening proofs): both commit kernels,
+// then ONE finish launch over 2 * batch sums -- a finish is a latency-bound kernel (one field inversion per sum) and a pass pays
+// each of them in full whatever its width.  out_affine: batch results of the first, then batch results of the second.
+void commit_device_pair(Ctx* ctx, Srs* srs, const Fr* scalars_a, size_t stride_a, uint32_t n_a, const Fr* scalars_b, size_t stride_b, uint32_t n_b, uint32_t batch,
+                        G1Affine* out_affine) {
+    const bool plain = !(ctx->commit_mode == 1 && !srs->geom.glv);
+    const uint32_t sa = n_a && batch ? commit_slices(ctx, n_a, batch) : 0, sb = n_b && batch ? commit_slices(ctx, n_b, batch) : 0;
+    if (!plain || !sa || sa != sb) {
+        commit_device(ctx, srs, scalars_a, stride_a, n_a, batch, out_affine);
+        commit_device(ctx, srs, scalars_b, stride_b, n_b, batch, out_affine + batch);
+        return;
+    }
+    if (n_a > srs->n || n_b > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
+    ctx->partials.ensure((size_t)2 * batch * sa);
+    commit_launch(ctx, srs, scalars_a, stride_a, n_a, batch, sa, ctx->partials.p);
+    commit_launch(ctx, srs, scalars_b, stride_b, n_b, batch, sa, ctx->partials.p + (size_t)batch * sa);
+    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, sa, 2 * batch, out_affine);
 }
 
 }  // namespace dr

@@ -212,5 +212,8 @@ void msm_points_device(Ctx* ctx, const G1Affine* points, const uint8_t* scalars_
 
 // scalars: `batch` vectors of n Montgomery Fr, vector b at scalars + b*stride.  Result: affine points.
 void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, G1Affine* out_affine);
+// two commitments of one batch with a shared finish: out_affine[0 .. batch) = first, [batch .. 2 batch) = second
+void commit_device_pair(Ctx* ctx, Srs* srs, const Fr* scalars_a, size_t stride_a, uint32_t n_a, const Fr* scalars_b, size_t stride_b, uint32_t n_b, uint32_t batch,
+                        G1Affine* out_affine);
 
 }  // namespace dr

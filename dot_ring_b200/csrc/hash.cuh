@@ -63,32 +63,37 @@ struct Sha512 {
             w[i] = x;
         }
         uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-#pragma unroll 4
-        for (int i = 0; i < 80; i++) {
-            uint64_t wi;
-            if (i < 16) {
-                wi = w[i];
-            } else {
-                uint64_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-                uint64_t s0 = rotr(w15, 1) ^ rotr(w15, 8) ^ (w15 >> 7);
-                uint64_t s1 = rotr(w2, 19) ^ rotr(w2, 61) ^ (w2 >> 6);
-                wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
-                w[i & 15] = wi;
+        // 5 groups of 16 rounds, each group fully unrolled: the message-schedule window w[16] is indexed by compile-time constants
+        // only and stays in registers
+#pragma unroll 1
+        for (int blk = 0; blk < 80; blk += 16) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                uint64_t wi;
+                if (blk == 0) {
+                    wi = w[k];
+                } else {
+                    uint64_t w15 = w[(k + 1) & 15], w2 = w[(k + 14) & 15];
+                    uint64_t s0 = rotr(w15, 1) ^ rotr(w15, 8) ^ (w15 >> 7);
+                    uint64_t s1 = rotr(w2, 19) ^ rotr(w2, 61) ^ (w2 >> 6);
+                    wi = w[k] + s0 + w[(k + 9) & 15] + s1;
+                    w[k] = wi;
+                }
+                uint64_t S1 = rotr(e, 14) ^ rotr(e, 18) ^ rotr(e, 41);
+                uint64_t ch = (e & f) ^ (~e & g);
+                uint64_t t1 = hh + S1 + ch + K(blk + k) + wi;
+                uint64_t S0 = rotr(a, 28) ^ rotr(a, 34) ^ rotr(a, 39);
+                uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
+                uint64_t t2 = S0 + mj;
+                hh = g;
+                g = f;
+                f = e;
+                e = d + t1;
+                d = c;
+                c = b;
+                b = a;
+                a = t1 + t2;
             }
-            uint64_t S1 = rotr(e, 14) ^ rotr(e, 18) ^ rotr(e, 41);
-            uint64_t ch = (e & f) ^ (~e & g);
-            uint64_t t1 = hh + S1 + ch + K(i) + wi;
-            uint64_t S0 = rotr(a, 28) ^ rotr(a, 34) ^ rotr(a, 39);
-            uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
-            uint64_t t2 = S0 + mj;
-            hh = g;
-            g = f;
-            f = e;
-            e = d + t1;
-            d = c;
-            c = b;
-            b = a;
-            a = t1 + t2;
         }
         h[0] += a;
         h[1] += b;
@@ -151,27 +156,42 @@ struct Shake128 {
                                      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
         constexpr int rotc[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
         constexpr int piln[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+        // the state is copied into locals and every inner loop is unrolled, so all indices are compile-time constants and the 25
+        // lanes stay in registers (with rolled inner loops the state lived in local memory: ~4x the latency of a permutation,
+        // which the one-thread-per-proof transcript kernels pay in full)
+        uint64_t s[25];
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] = a[i];
 #pragma unroll 1
         for (int round = 0; round < 24; round++) {
             uint64_t bc[5];
-            for (int i = 0; i < 5; i++) bc[i] = a[i] ^ a[i + 5] ^ a[i + 10] ^ a[i + 15] ^ a[i + 20];
+#pragma unroll
+            for (int i = 0; i < 5; i++) bc[i] = s[i] ^ s[i + 5] ^ s[i + 10] ^ s[i + 15] ^ s[i + 20];
+#pragma unroll
             for (int i = 0; i < 5; i++) {
                 uint64_t t = bc[(i + 4) % 5] ^ rotl(bc[(i + 1) % 5], 1);
-                for (int j = 0; j < 25; j += 5) a[j + i] ^= t;
+#pragma unroll
+                for (int j = 0; j < 25; j += 5) s[j + i] ^= t;
             }
-            uint64_t t = a[1];
+            uint64_t t = s[1];
+#pragma unroll
             for (int i = 0; i < 24; i++) {
-                int j = piln[i];
-                uint64_t b0 = a[j];
-                a[j] = rotl(t, rotc[i]);
+                const int j = piln[i];
+                uint64_t b0 = s[j];
+                s[j] = rotl(t, rotc[i]);
                 t = b0;
             }
+#pragma unroll
             for (int j = 0; j < 25; j += 5) {
-                for (int i = 0; i < 5; i++) bc[i] = a[j + i];
-                for (int i = 0; i < 5; i++) a[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) bc[i] = s[j + i];
+#pragma unroll
+                for (int i = 0; i < 5; i++) s[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
             }
-            a[0] ^= rc[round];
+            s[0] ^= rc[round];
         }
+#pragma unroll
+        for (int i = 0; i < 25; i++) a[i] = s[i];
     }
 
     DR_HD void absorb(const uint8_t* data, uint32_t len) {

@@ -56,17 +56,20 @@ int ht_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fr_out(out, r);
     return ok;
 }
-// field: 0 Fq (48-byte big-endian), 1 Fr (32-byte little-endian).  inv: out = Kaliski inverse, out2 = Fermat inverse; returns the Legendre symbol
-int ht_inv_and_legendre(int field, const uint8_t* a, uint8_t* out, uint8_t* out2) {
+// field: 0 Fq (48-byte big-endian), 1 Fr (32-byte little-endian).  out = inv() (division steps), out2 = Fermat inverse, out3 = Kaliski's
+// binary inverse; returns the Legendre symbol
+int ht_inv_and_legendre(int field, const uint8_t* a, uint8_t* out, uint8_t* out2, uint8_t* out3) {
     if (field == 0) {
         Fq x = fq_in(a);
         fq_out(out, x.inv());
         fq_out(out2, x.inv_fermat());
+        fq_out(out3, x.inv_kaliski());
         return x.legendre();
     }
     Fr x = fr_in(a);
     fr_out(out, x.inv());
     fr_out(out2, x.inv_fermat());
+    fr_out(out3, x.inv_kaliski());
     return x.legendre();
 }
 // prime-subgroup membership of an on-curve point, both ways: bit 0 = 2-descent (two Legendre symbols), bit 1 = multiplication by the order

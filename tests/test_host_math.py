@@ -140,16 +140,17 @@ def test_batched_affine_round_exceptional_cases(lib):
         assert out.raw[96 * i : 96 * i + 96] == bls.g1_serialize(bls.g1_add(x, y)), i
 
 
-def test_kaliski_inverse_and_legendre_symbol(lib):
-    """fp.cuh inv() (binary Montgomery inverse) against Fermat's x^(p-2) and Python's pow; legendre() against Euler's criterion."""
+def test_modular_inverses_and_legendre_symbol(lib):
+    """fp.cuh inv() (Bernstein-Yang division steps), inv_kaliski() and Fermat's x^(p-2) against Python's pow; legendre() against
+    Euler's criterion."""
     rng = random.Random(12)
     for field, mod, size, order in ((0, bls.P, 48, "big"), (1, fr.R, 32, "little")):
         edge = [0, 1, 2, 3, 4, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 200, (1 << 32) - 1, 1 << 32]
-        for v in edge + [rng.randrange(mod) for _ in range(300)]:
-            out, out2 = _buf(size), _buf(size)
-            sym = lib.ht_inv_and_legendre(field, v.to_bytes(size, order), out, out2)
+        for v in edge + [rng.randrange(mod) for _ in range(300)] + [rng.randrange(1 << k) for k in range(1, 64, 3)] + [mod - rng.randrange(1, 1 << 40) for _ in range(20)]:
+            out, out2, out3 = _buf(size), _buf(size), _buf(size)
+            sym = lib.ht_inv_and_legendre(field, v.to_bytes(size, order), out, out2, out3)
             want = pow(v, -1, mod) if v else 0
-            assert int.from_bytes(out.raw, order) == want == int.from_bytes(out2.raw, order), (field, v)
+            assert int.from_bytes(out.raw, order) == want == int.from_bytes(out2.raw, order) == int.from_bytes(out3.raw, order), (field, v)
             euler = 0 if v == 0 else (1 if pow(v, (mod - 1) // 2, mod) == 1 else -1)
             assert sym == euler, (field, v)
 
