@@ -118,7 +118,7 @@ extern "C" {
 int dr_g1_msm(dr_ctx* c, const uint8_t* points_be96, const uint8_t* scalars_le32, size_t n, uint8_t out_be96[96]) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
-    if (!ctx || !out_be96 || (n && (!points_be96 || !scalars_le32)) || n >= (1u << 31)) throw Error(DR_EINVAL, "bad argument");
+    if (!ctx || !out_be96 || (n && (!points_be96 || !scalars_le32)) || n >= (1u << 30)) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
     if (n == 0) {
         memset(out_be96, 0, 96);
@@ -147,7 +147,7 @@ int dr_g1_msm(dr_ctx* c, const uint8_t* points_be96, const uint8_t* scalars_le32
 int dr_g1_synthetic_srs(dr_ctx* c, const uint8_t tau_le32[32], size_t offset, size_t n, uint8_t* out_be96) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
-    if (!ctx || !tau_le32 || (n && !out_be96) || offset + n >= (1u << 31)) throw Error(DR_EINVAL, "bad argument");
+    if (!ctx || !tau_le32 || (n && !out_be96) || offset + n >= (1u << 30)) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
     if (!n) return DR_OK;
     Fr tau;
@@ -169,7 +169,7 @@ int dr_g1_msm_bench(dr_ctx* c, size_t n, int iters, uint64_t seed, int distribut
                     uint8_t out_be96[96]) {
     DR_API_BEGIN
     Ctx* ctx = (Ctx*)c;
-    if (!ctx || n == 0 || n >= (1u << 31) || iters <= 0 || !tau_le32) throw Error(DR_EINVAL, "bad argument");
+    if (!ctx || n == 0 || n >= (1u << 30) || iters <= 0 || !tau_le32) throw Error(DR_EINVAL, "bad argument");
     ctx->activate();
     Fr tau;
     fr_from_le_bytes_raw(tau, tau_le32);
