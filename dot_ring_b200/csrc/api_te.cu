@@ -133,6 +133,7 @@ int dr_te_mul_batch(dr_ctx* c, const uint8_t* points32, size_t n_points, const u
         launch(ctx->stream, Dim3((uint32_t)((n + 63) / 64)), 64, 0, TeMulBody(), (const uint8_t*)dp.p, (uint32_t)n_points, (const uint8_t*)dk.p, (uint32_t)n, dout.p, dok.p);
         d2h(ctx->stream, out32, dout.p, n * 32);
         d2h(ctx->stream, ok, dok.p, n);
+        dev_zero(ctx->stream, dk.p, n * 32);  // the scalars may be secret keys (public-key derivation); the block is recycled
         stream_sync(ctx->stream);
     } catch (const Error& e) {
         return set_error(e.code, e.what());

@@ -361,6 +361,8 @@ static void vrf_prove_batch(Ctx* ctx, const dr_vrf_suite* suite, int kind, size_
                (const uint8_t*)dsk.p, m, dout.p);
     d2h(ctx->stream, out, dout.p, n * len);
     if (blinding32) d2h(ctx->stream, blinding32, dbl.p, n * 32);
+    dev_zero(ctx->stream, dsk.p, n * 32);  // the cached block must not hand secret keys to a later call
+    if (blinding32) dev_zero(ctx->stream, dbl.p, n * 32);
     stream_sync(ctx->stream);
 }
 

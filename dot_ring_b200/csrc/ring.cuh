@@ -525,11 +525,12 @@ struct WitnessBody {
                 TEExt chk = te_add(TEExt::from_affine(rg.seed), TEExt::from_affine(ps.relation));
                 if (!te_ext_eq_affine(chk, ps.s[SCALAR_BITS - 1])) ps.status |= 2u;
                 // transcript: copy the ring prefix, absorb the instance (phases.py:18-26)
-                ps.tr = *prefix;
-                shake_absorb_label(ps.tr, "instance", 8);
-                shake_absorb_fr(ps.tr, ps.relation.x);
-                shake_absorb_fr(ps.tr, ps.relation.y);
-                ps.tr.absorb_be32(64);
+                Shake128 tr = *prefix;
+                shake_absorb_label(tr, "instance", 8);
+                shake_absorb_fr(tr, ps.relation.x);
+                shake_absorb_fr(tr, ps.relation.y);
+                tr.absorb_be32(64);
+                ps.tr = tr;
             }
         }
     }
@@ -698,10 +699,14 @@ struct Transcript1Body {
             uint32_t p = ctx.bx * ctx.nthreads + t;
             if (p < count) {
                 ProofState& ps = st[p];
-                shake_absorb_label(ps.tr, "committed_cols", 14);
-                for (int i = 0; i < 4; i++) shake_absorb_g1(ps.tr, ps.commits[i]);
-                ps.tr.absorb_be32(4 * 96);
-                shake_challenges(ps.tr, "constraints_aggregation", 23, ps.alpha, 7);
+                Shake128 tr = ps.tr;  // absorb byte by byte into a local copy, not into HBM
+                shake_absorb_label(tr, "committed_cols", 14);
+                for (int i = 0; i < 4; i++) shake_absorb_g1(tr, ps.commits[i]);
+                tr.absorb_be32(4 * 96);
+                Fr alpha[7];
+                shake_challenges(tr, "constraints_aggregation", 23, alpha, 7);
+                for (int i = 0; i < 7; i++) ps.alpha[i] = alpha[i];
+                ps.tr = tr;
             }
         }
     }
@@ -887,10 +892,14 @@ struct Transcript2Body {
             uint32_t p = ctx.bx * ctx.nthreads + t;
             if (p < count) {
                 ProofState& ps = st[p];
-                shake_absorb_label(ps.tr, "quotient", 8);
-                shake_absorb_g1(ps.tr, ps.commits[4]);
-                ps.tr.absorb_be32(96);
-                shake_challenges(ps.tr, "evaluation_point", 16, &ps.zeta, 1);
+                Shake128 tr = ps.tr;
+                shake_absorb_label(tr, "quotient", 8);
+                shake_absorb_g1(tr, ps.commits[4]);
+                tr.absorb_be32(96);
+                Fr zeta;
+                shake_challenges(tr, "evaluation_point", 16, &zeta, 1);
+                ps.zeta = zeta;
+                ps.tr = tr;
             }
         }
     }
@@ -998,13 +1007,17 @@ struct Transcript3Body {
             uint32_t p = ctx.bx * ctx.nthreads + t;
             if (p < count) {
                 ProofState& ps = st[p];
-                shake_absorb_label(ps.tr, "register_evaluations", 20);
-                for (int i = 0; i < 7; i++) shake_absorb_fr(ps.tr, ps.evals[i]);
-                ps.tr.absorb_be32(7 * 32);
-                shake_absorb_label(ps.tr, "shifted_linearization_evaluation", 32);
-                shake_absorb_fr(ps.tr, ps.lzw);
-                ps.tr.absorb_be32(32);
-                shake_challenges(ps.tr, "kzg_aggregation", 15, ps.nu, 8);
+                Shake128 tr = ps.tr;
+                shake_absorb_label(tr, "register_evaluations", 20);
+                for (int i = 0; i < 7; i++) shake_absorb_fr(tr, ps.evals[i]);
+                tr.absorb_be32(7 * 32);
+                shake_absorb_label(tr, "shifted_linearization_evaluation", 32);
+                shake_absorb_fr(tr, ps.lzw);
+                tr.absorb_be32(32);
+                Fr nu[8];
+                shake_challenges(tr, "kzg_aggregation", 15, nu, 8);
+                for (int i = 0; i < 8; i++) ps.nu[i] = nu[i];
+                ps.tr = tr;
             }
         }
     }

@@ -16,12 +16,16 @@ REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "config", "e2e", "gpu_launches", "clocks", "roofline"]  # fmt: skip
 
 
-def _run(cmd, timeout=900):
+def _start(cmd):
     env = dict(os.environ, DOT_RING_B200_BENCH_DRYRUN="1")
-    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
-    assert out.returncode == 0, out.stderr[-2000:]
-    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
-    assert len(lines) == 1, out.stdout
+    return subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def _finish(proc, timeout=1500):
+    out, err = proc.communicate(timeout=timeout)
+    assert proc.returncode == 0, err[-2000:]
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out
     return json.loads(lines[0])
 
 
@@ -41,23 +45,21 @@ def _check_line(line, n_gpus, total, steps, scaling):
     assert line["e2e"]["value"] <= line["value"] * 1.001
 
 
-def test_bench_single_process_line():
-    line = _run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4", "--no-cpu-baseline"])
+def test_bench_lines_dry_run():
+    """The three launch modes of bench.py, run side by side (each builds an emulated 6145-point window table, ~1.5 minutes):
+    one process / one device (weak, --batch), torchrun with two gloo ranks (strong: one batch of 3 proofs sharded 2 + 1), and
+    one process driving two emulated devices through EnginePool (strong)."""
+    single = _start([sys.executable, "bench.py", "--steps", "1", "--warmup", "1", "--batch", "1", "--window-bits", "4", "--no-cpu-baseline"])
+    ranks = _start([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29617",
+                    "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "3", "--window-bits", "4"])  # fmt: skip
+    pool = _start([sys.executable, "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "2", "--window-bits", "4"])
+    line = _finish(single)
     _check_line(line, 1, 1, 1, "weak")
-
-
-def test_bench_two_ranks_gloo():
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29617",
-           "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "3", "--window-bits", "4"]  # fmt: skip
-    line = _run(cmd)
-    _check_line(line, 2, 3, 1, "strong")  # one batch of 3 proofs sharded 2 + 1 over the ranks
+    line = _finish(ranks)
+    _check_line(line, 2, 3, 1, "strong")
     assert line["config"]["launch"].startswith("torchrun")
     assert "cpu_baseline" not in line  # rank 0 at N=1 only
-
-
-def test_bench_one_process_two_devices_pool():
-    """`python bench.py --gpus 2` without torchrun: one process, EnginePool over two (emulated) devices, strong scaling."""
-    line = _run([sys.executable, "bench.py", "--gpus", "2", "--steps", "1", "--warmup", "1", "--total", "2", "--window-bits", "4"])
+    line = _finish(pool)
     _check_line(line, 2, 2, 1, "strong")
     assert "EnginePool" in line["config"]["launch"]
 
