@@ -654,14 +654,14 @@ class NativeRing:
         raw = out.raw
         return [(int.from_bytes(raw[64 * i : 64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32 : 64 * i + 64], "little")) for i in range(n)]
 
-    def prove_batch(self, alphas: list[bytes], ads: list[bytes], secret_keys: list[bytes], producer_index: list[int], zk_rows: list[int] | None = None):
-        """-> (list of 784-byte proofs, list of status words)."""
+    @staticmethod
+    def pack_prove_inputs(alphas: list[bytes], ads: list[bytes], secret_keys: list[bytes], producer_index: list[int], zk_rows=None) -> dict:
+        """Host-side packing of a prove batch into the flat buffers of dr_ring_prove_batch (done once per batch, also when the batch
+        is then sharded over several devices: the offsets are absolute, so a shard is just a sub-range of every array)."""
         n = len(alphas)
         if not (len(ads) == len(secret_keys) == len(producer_index) == n):
             raise ValueError("batch inputs must have equal length")
         blob, a_off, a_len, d_off, d_len = pack_items(alphas, ads)
-        proofs = ctypes.create_string_buffer(784 * max(n, 1))
-        status = (ctypes.c_uint32 * max(n, 1))()
         rows = np.ctypeslib.as_ctypes(np.array(producer_index if n else [0], dtype=np.uint32))
         zk = None
         if isinstance(zk_rows, (bytes, bytearray)):  # already 12 x 32-byte little-endian values per proof
@@ -672,15 +672,35 @@ class NativeRing:
             if len(zk_rows) != 12 * n:
                 raise ValueError("zk_rows must hold 12 field elements per proof")
             zk = b"".join(int(v).to_bytes(32, "little") for v in zk_rows)
+        return {"n": n, "blob": blob, "a_off": a_off, "a_len": a_len, "d_off": d_off, "d_len": d_len, "sk": b"".join(secret_keys), "rows": rows, "zk": zk,
+                "proofs": ctypes.create_string_buffer(784 * max(n, 1)), "status": (ctypes.c_uint32 * max(n, 1))()}
+
+    def prove_packed(self, pk: dict, lo: int = 0, hi: int | None = None) -> None:
+        """Prove items [lo, hi) of a packed batch; proofs and status words land in the batch's own output buffers."""
+        hi = pk["n"] if hi is None else hi
+        if hi <= lo:
+            return
+        u32 = lambda arr: ctypes.byref(arr, 4 * lo)  # noqa: E731
+        sk = (ctypes.c_char * (32 * (hi - lo))).from_buffer_copy(pk["sk"], 32 * lo) if lo or hi != pk["n"] else pk["sk"]
+        zk = None if pk["zk"] is None else (pk["zk"] if not lo and hi == pk["n"] else (ctypes.c_char * (384 * (hi - lo))).from_buffer_copy(pk["zk"], 384 * lo))
         lib = self.ctx.library
-        sk_blob = b"".join(secret_keys)
         if self.time_calls:  # one CUDA event pair on the ctx stream around the whole call (bench.py); every argument is ready by now
             self.ctx.timer_start()
-        lib.check(lib.lib.dr_ring_prove_batch(self.ctx.handle, self.handle, n, blob, a_off, a_len, d_off, d_len, sk_blob, rows, zk, proofs, status))
+        lib.check(lib.lib.dr_ring_prove_batch(self.ctx.handle, self.handle, hi - lo, pk["blob"], u32(pk["a_off"]), u32(pk["a_len"]), u32(pk["d_off"]), u32(pk["d_len"]), sk,
+                                              u32(pk["rows"]), zk, ctypes.byref(pk["proofs"], 784 * lo), ctypes.byref(pk["status"], 4 * lo)))
         if self.time_calls:
             self.last_call_ms = self.ctx.timer_stop()
-        raw = proofs.raw
-        return [raw[784 * i : 784 * i + 784] for i in range(n)], status[:n]
+
+    @staticmethod
+    def unpack_proofs(pk: dict):
+        n, raw = pk["n"], pk["proofs"].raw
+        return [raw[784 * i : 784 * i + 784] for i in range(n)], pk["status"][:n]
+
+    def prove_batch(self, alphas: list[bytes], ads: list[bytes], secret_keys: list[bytes], producer_index: list[int], zk_rows: list[int] | None = None):
+        """-> (list of 784-byte proofs, list of status words)."""
+        pk = self.pack_prove_inputs(alphas, ads, secret_keys, producer_index, zk_rows)
+        self.prove_packed(pk)
+        return self.unpack_proofs(pk)
 
     def verify_batch(self, inputs: list[bytes], ads: list[bytes], proofs: list[bytes], coeffs: list[int], aggregate: bool = False):
         """RingVRF decode + verify for 784-byte proofs -> (per-item verdicts 1 / 0 / 2, all_ok)."""

@@ -105,17 +105,17 @@ static SuiteDev suite_from_abi(const dr_vrf_suite* s) {
 constexpr uint32_t VRF_VERIFY_THREADS = 64, VRF_VERIFY_ITEMS = VRF_VERIFY_THREADS / COOP_LANES;
 static std::atomic<size_t> VRF_VERIFY_COOP_BELOW{8192};
 
-static void launch_pedersen_verify(Ctx* ctx, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t stride, const TEAffine* pts,
+static void launch_pedersen_verify(Ctx* ctx, Stream st, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t stride, const TEAffine* pts,
                                    const uint8_t* ok, uint32_t m, uint32_t* status) {
     if (m >= VRF_VERIFY_COOP_BELOW.load()) {
-        launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, PedersenVerifySerialBody(), su, in, blob, proofs, stride, pts, ok, m, status);
+        launch(st, Dim3((m + 63) / 64), 64, 0, PedersenVerifySerialBody(), su, in, blob, proofs, stride, pts, ok, m, status);
         return;
     }
     auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);  // the context keeps them alive
     su.g_tab = g_table->tab.p;
     su.b_tab = b_table->tab.p;
-    launch(ctx->stream, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su, in, blob, proofs,
-           stride, pts, ok, m, status);
+    launch(st, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su, in, blob, proofs, stride,
+           pts, ok, m, status);
 }
 
 // uploads the per-item (offset, length) table and the blob; returns the device buffers
@@ -151,7 +151,15 @@ static std::atomic<size_t> RING_VERIFY_MSM_THRESHOLD{8192};  // process-wide tes
 
 // shared tail of the two ring-verification entry points; relations / payloads already on the device
 static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t n, const uint8_t* payloads, uint32_t stride, const TEAffine* relations, uint32_t rel_stride,
-                                     const uint8_t* coeffs_le32, const uint32_t* extra_status, int aggregate, uint8_t* verdict, int* all_ok) {
+                                     const uint8_t* coeffs_le32, const uint32_t* extra_status, int aggregate, uint8_t* verdict, int* all_ok, bool extra_on_side = false) {
+    // extra_on_side: extra_status is being written by work on ctx->side (forked by the caller); joined before its first reader
+    struct SideJoin {  // an exception below must not leave the side stream running into freed buffers
+        Ctx* c;
+        bool pending;
+        ~SideJoin() {
+            if (pending) c->join_side();
+        }
+    } side_join{ctx, extra_on_side};
     if (!coeffs_le32) throw Error(DR_EINVAL, "random batching coefficients are required (2 x 32 bytes per proof)");
     for (size_t i = 0; i < 2 * n; i++) {
         Fr r;
@@ -169,6 +177,10 @@ static void ring_proof_verify_device(Ctx* ctx, const VerifierKeyDev& vk, size_t 
     uint32_t all = 0;
     const bool by_msm = aggregate && n >= RING_VERIFY_MSM_THRESHOLD.load();
     if (!by_msm) launch(ctx->stream, Dim3((2 * VERIFY_TERMS * m + 63) / 64), 64, 0, RingVerifyTermsBody(), vk, m, vs.p);
+    if (side_join.pending) {
+        ctx->join_side();
+        side_join.pending = false;
+    }
     if (by_msm) {
         // two variable-base MSMs instead of 13 scalar multiplications per proof
         const uint32_t threads = 64, nparts = (m + threads - 1) / threads;
@@ -281,7 +293,7 @@ int dr_pedersen_verify_batch(dr_ctx* c, const dr_vrf_suite* suite, size_t n, con
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs192, n * 192);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 192u, 4u, 4 * m, pts.p, dok.p);
-    launch_pedersen_verify(ctx, su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    launch_pedersen_verify(ctx, ctx->stream, su, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 192u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
     std::vector<uint32_t> st(n);
     d2h(ctx->stream, st.data(), dst.p, n * 4);
     stream_sync(ctx->stream);
@@ -433,9 +445,14 @@ int dr_ring_verify_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, c
     DevBuf<uint32_t> dst(n);
     h2d(ctx->stream, dpr.p, proofs784, n * 784);
     launch(ctx->stream, Dim3((4 * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)dpr.p, 784u, 4u, 4 * m, pts.p, dok.p);
-    launch_pedersen_verify(ctx, ring->suite, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u, (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);
+    // The Pedersen equations only meet the ring proof at the verdict, so they run on the side stream next to the payload decode, the
+    // transcript algebra and the G1 terms (a single verification is a chain of latency-bound kernels: this takes the longest one
+    // off the critical path; large batches lose nothing).
+    ctx->fork_side();
+    launch_pedersen_verify(ctx, ctx->side, ring->suite, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p, 784u, (const TEAffine*)pts.p,
+                           (const uint8_t*)dok.p, m, dst.p);
     // relation = blinded public key (second Pedersen point); payload follows the 192-byte Pedersen part
-    ring_proof_verify_device(ctx, ring->vk, n, dpr.p + 192, 784, pts.p + 1, 4, coeffs_le32, dst.p, aggregate, verdict, all_ok);
+    ring_proof_verify_device(ctx, ring->vk, n, dpr.p + 192, 784, pts.p + 1, 4, coeffs_le32, dst.p, aggregate, verdict, all_ok, true);
     DR_API_END
 }
 

@@ -219,24 +219,16 @@ class PooledRingNative:
         return max(per, key=sum)
 
     def prove_batch(self, alphas, ads, secret_keys, producer_index, zk_rows=None):
+        """The batch is packed ONCE on the calling thread (the packing holds the GIL: done per shard it would serialise the
+        workers); every device then proves a contiguous sub-range of the same flat buffers and writes its proofs into its slice
+        of one output buffer."""
         n = len(alphas)
         bounds = self.pool.shard_bounds(n, len(self.replicas))
         if len(bounds) <= 1:
             return self.replicas[0].prove_batch(alphas, ads, secret_keys, producer_index, zk_rows)
-
-        def zk_slice(lo, hi):
-            if zk_rows is None:
-                return None
-            if isinstance(zk_rows, (bytes, bytearray)):
-                return zk_rows[384 * lo : 384 * hi]
-            return zk_rows[12 * lo : 12 * hi]
-
-        parts = self.pool.map(
-            lambda i: self.replicas[i].prove_batch(alphas[bounds[i][0] : bounds[i][1]], ads[bounds[i][0] : bounds[i][1]], secret_keys[bounds[i][0] : bounds[i][1]],
-                                                   producer_index[bounds[i][0] : bounds[i][1]], zk_slice(*bounds[i])),
-            range(len(bounds)),
-        )
-        return [p for proofs, _ in parts for p in proofs], [s for _, status in parts for s in status]
+        pk = _native.NativeRing.pack_prove_inputs(alphas, ads, secret_keys, producer_index, zk_rows)
+        self.pool.map(lambda i: self.replicas[i].prove_packed(pk, bounds[i][0], bounds[i][1]), range(len(bounds)))
+        return _native.NativeRing.unpack_proofs(pk)
 
     def verify_batch(self, inputs, ads, proofs, coeffs, aggregate: bool = False):
         """Per-item mode: shards are independent.  Aggregated mode (`RingVRF.batch_verify`): every device folds its shard into

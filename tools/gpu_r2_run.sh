@@ -51,6 +51,11 @@ if has ncu_verify; then
   ncu --set full --clock-control none --kernel-name-base demangled -k regex:"IetfVerifyBody|PedersenVerifyBody|TeDecodeManyBody" -s 6 -c 5 -o ${O}_prof_verify_kernels $CMD > ${O}_ncu_full2.log 2>&1
   extract ${O}_prof_verify_kernels; cat ${O}_prof_verify_kernels.txt
 fi
+if has ncu_start; then
+  $CMD > ${O}_plain5.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"PedersenStartBody" -s 1 -c 1 -o ${O}_prof_start $CMD > ${O}_ncu_full5.log 2>&1
+  python tools/ncu_extract.py ${O}_prof_start.ncu-rep ${O}_prof_start.csv > ${O}_prof_start.txt 2>&1; cat ${O}_prof_start.txt; ls -la ${O}_prof_start.ncu-rep
+fi
 if has ncu_commit; then
   CMD3="python bench.py --steps 1 --warmup 1 --total 1024 --saturated-batch 0 --no-cpu-baseline"
   $CMD3 > ${O}_plain4.log 2>&1 &&
