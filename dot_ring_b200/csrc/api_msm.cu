@@ -4,18 +4,18 @@
 
 namespace dr {
 
-// window bits minimising W * (2n + MSM_BUCKET_WEIGHT * 2^(c-1)) mixed-addition equivalents over the 2n GLV halves.  A bucket costs far more
-// than the 2.8 additions of its arithmetic: the fold / running-sum / window kernels are short dependent chains on few threads (measured
-// at 2^20 points: 0.43 ns per bucket addition against ~11 ns per bucket), so the model charges a bucket 16 additions.
-#ifndef MSM_BUCKET_WEIGHT
-#define MSM_BUCKET_WEIGHT 16.0
-#endif
+// window bits minimising W * (2n + weight * 2^(c-1)) mixed-addition equivalents over the 2n GLV halves.  For large sets a bucket costs
+// far more than the 2.8 additions of its arithmetic: the fold / running-sum / window kernels are short dependent chains on few threads
+// (measured at 2^20 points: 0.43 ns per bucket addition against ~11 ns per bucket), so the model charges a bucket 16 additions from
+// 2^18 points on.  Below, those kernels are latency-bound whatever the bucket count and the plain arithmetic count picks better
+// (measured sweep, profiles/r02_probe_msm_sweep*.json: 3.0 vs 3.4 ms at 2^16, 5.1 vs 5.3 ms at 2^18, 11.9 vs 13.3 ms at 2^20).
 static uint32_t msm_window_bits(size_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
+    const double weight = n >= ((size_t)1 << 18) ? 16.0 : 2.8;
     for (uint32_t c = 4; c <= 17; c++) {
         double W = (MSM_GLV_BITS + c - 1) / c;
-        double cost = W * (2.0 * (double)n + MSM_BUCKET_WEIGHT * (double)(1u << (c - 1)));
+        double cost = W * (2.0 * (double)n + weight * (double)(1u << (c - 1)));
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
