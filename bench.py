@@ -442,9 +442,7 @@ def run_ours(args) -> None:
         "dtype": "u32 limbs (381-bit Fq / 255-bit Fr Montgomery)",
         "data": "synthetic",
         "config": {
-            "workload": (f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, one batch of {total} proofs per step sharded over {n_dev} GPU(s) "
-                         f"({per_gpu} per GPU) -- BASELINE configs[1]" if strong else
-                         f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {args.batch} proofs per GPU per step (BASELINE configs[1] shape, weak scaling)"),
+            "workload": workload_string(strong, total, n_dev, args.batch),
             "total_proofs_per_step": total,
             "proofs_per_gpu_per_step": per_gpu,
             "launch": "one process, EnginePool over %d devices" % pool_devices if pool_devices > 1 else ("torchrun, one rank per GPU" if world > 1 else "one process, one GPU"),
@@ -492,6 +490,14 @@ def run_ours(args) -> None:
     emit(line)
     if last:
         sys.stderr.write(f"[bench] last proof sha256 {hashlib.sha256(last[-1]).hexdigest()[:16]}\n")
+
+
+def workload_string(strong: bool, total: int, n_dev: int, batch: int | None) -> str:
+    """`config.workload`, shared by both arms so that the driver compares like with like."""
+    if strong:
+        return (f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, one batch of {total} proofs per step sharded over {n_dev} GPU(s) "
+                f"({total // n_dev} per GPU) -- BASELINE configs[1]")
+    return f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048, batch {batch} proofs per GPU per step (BASELINE configs[1] shape, weak scaling)"
 
 
 def _shard(total: int, parts: int, index: int) -> tuple[int, int]:
@@ -591,12 +597,13 @@ def run_reference(args) -> None:
         "warmup": args.warmup,
         "ms_per_step": wall * 1e3 / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "python ints / u64 limbs",
         "data": "synthetic",
-        "config": {"workload": f"Ring VRF prove, Bandersnatch, ring {RING_SIZE} / domain 2048; each step = 1 proof on each of {workers} host processes"},
-        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": workers, "kind": "port", "sample": f"{workers} x {args.steps} proofs, oracle port ({backend_name()})"},
+        "config": {"workload": workload_string(args.scaling == "strong", args.total, args.gpus, args.batch),
+                   "sample": f"bounded sample of that workload: each step = 1 proof on each of {workers} host processes (the CPU path has no batch dimension: its rate does not depend on the batch size)"},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": workers, "kind": "port", "sample": f"{workers} x {args.steps} proofs, oracle port ({backend_name()}): the reference's algorithm restated (its own package cannot be built offline, DESIGN.md section 7)"},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
