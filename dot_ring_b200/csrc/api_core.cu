@@ -350,6 +350,7 @@ void dr_ctx_destroy(dr_ctx* c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
+    current_stream() = ctx->stream;
 #endif
     ctx->plans.clear();
     ctx->release_scratch();
@@ -360,6 +361,7 @@ void dr_ctx_destroy(dr_ctx* c) {
     cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
+    current_stream() = nullptr;
 #endif
     delete ctx;
 }

@@ -108,6 +108,7 @@ struct Ctx {
     void activate() {
 #if !defined(DR_HOST_EMULATION)
         DR_CUDA(cudaSetDevice(device));
+        current_stream() = stream;  // the block cache orders reuse by the stream a block was freed on (rt.cuh)
 #endif
     }
     uint32_t sm_count_cached = 0;

@@ -96,11 +96,32 @@ inline std::atomic<uint64_t>& launch_counter() {  // several contexts (one per G
     return c;
 }
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per (kernel, device) and only ever raised: two host
+// threads (two contexts) launching the same kernel with different sizes must not lower it under each other's launch.
+template <class Kern>
+inline void allow_dynamic_smem(Kern kern, size_t smem) {
+    if (smem <= 48 * 1024) return;
+    static std::atomic<size_t> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<size_t>& cur = configured[dev & 63];
+    size_t seen = cur.load();
+    while (smem > seen) {
+        static std::mutex m;
+        std::lock_guard<std::mutex> lock(m);
+        seen = cur.load();
+        if (smem <= seen) break;
+        DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur.store(smem);
+        seen = smem;
+    }
+}
+
 template <class Body, class... Args>
 inline void launch(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body body, Args... args) {
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
     auto kern = kernel_entry<Body, Args...>;
-    if (smem > 48 * 1024) DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    allow_dynamic_smem(kern, smem);
     kern<<<dim3(grid.x, grid.y, grid.z), threads, smem, s>>>(body, args...);
     DR_CUDA(cudaGetLastError());
     launch_counter()++;
@@ -111,7 +132,7 @@ inline void launch_lb(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body b
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
     if (threads > (uint32_t)THREADS) throw Error(DR_ESTATE, "launch exceeds the kernel's launch bounds");
     auto kern = kernel_entry_lb<THREADS, BLOCKS, Body, Args...>;
-    if (smem > 48 * 1024) DR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    allow_dynamic_smem(kern, smem);
     kern<<<dim3(grid.x, grid.y, grid.z), threads, smem, s>>>(body, args...);
     DR_CUDA(cudaGetLastError());
     launch_counter()++;
@@ -120,12 +141,26 @@ inline void launch_lb(Stream s, Dim3 grid, uint32_t threads, size_t smem, Body b
 // Device allocations go through a small caching layer: every C-ABI call allocates its scratch with DevBuf and frees it on
 // return, and cudaMalloc / cudaFree of 100 MB-class buffers cost milliseconds each (and, measured on B200, occasional
 // stalls of hundreds of ms).  Freed blocks are kept per device (up to DR_DEV_CACHE_CAP bytes) and reused for requests of a
-// similar size; on an out-of-memory error the cache is emptied and the allocation retried.  Blocks are only recycled after
-// the owning call has synchronised its stream (the ABI is synchronous), the same guarantee cudaFree gives.
+// similar size; on an out-of-memory error the cache is emptied and the allocation retried.
+// A block may be freed while kernels that use it are still queued (a scratch buffer that grows in the middle of a call, a
+// temporary that goes out of scope before the call's final synchronisation).  Reuse on the SAME stream is ordered behind those
+// kernels; another context on the same device (a second stream, possibly another host thread) must not get the block before
+// they have run.  So every cached block remembers the stream it was freed on and an event recorded there at that moment:
+// the freeing stream may take it back at once, any other stream only after the event has completed.
+inline Stream& current_stream() {  // set by Ctx::activate(): the stream the calling thread's API call works on
+    static thread_local Stream s = nullptr;
+    return s;
+}
+struct CachedBlock {
+    void* p;
+    Stream owner;
+    cudaEvent_t freed;  // null: nothing was pending
+};
 struct DevCache {
     std::mutex m;
-    std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, size) -> block
-    std::map<void*, std::pair<int, size_t>> live;               // block -> (device, size)
+    std::multimap<std::pair<int, size_t>, CachedBlock> free_blocks;  // (device, size) -> block
+    std::map<void*, std::pair<int, size_t>> live;                     // block -> (device, size)
+    std::vector<cudaEvent_t> spare_events;
     size_t cached = 0;
     size_t cap = (size_t)24 << 30;
 };
@@ -136,7 +171,13 @@ inline DevCache& dev_cache() {
 inline void dev_cache_trim() {
     DevCache& c = dev_cache();
     std::lock_guard<std::mutex> lock(c.m);
-    for (auto& kv : c.free_blocks) cudaFree(kv.second);
+    for (auto& kv : c.free_blocks) {
+        if (kv.second.freed) {
+            cudaEventSynchronize(kv.second.freed);
+            c.spare_events.push_back(kv.second.freed);
+        }
+        cudaFree(kv.second.p);
+    }
     c.free_blocks.clear();
     c.cached = 0;
 }
@@ -150,9 +191,15 @@ inline void* dev_alloc(size_t bytes) {
     DevCache& c = dev_cache();
     {
         std::lock_guard<std::mutex> lock(c.m);
-        auto it = c.free_blocks.lower_bound({dev, size});
-        if (it != c.free_blocks.end() && it->first.first == dev && it->first.second <= size + size / 4) {
-            void* p = it->second;
+        for (auto it = c.free_blocks.lower_bound({dev, size}); it != c.free_blocks.end() && it->first.first == dev && it->first.second <= size + size / 4; ++it) {
+            CachedBlock& b = it->second;
+            const bool usable = b.owner == current_stream() || !b.freed || cudaEventQuery(b.freed) == cudaSuccess;
+            if (!usable) {
+                cudaGetLastError();  // cudaErrorNotReady is not an error
+                continue;
+            }
+            void* p = b.p;
+            if (b.freed) c.spare_events.push_back(b.freed);
             c.live[p] = it->first;
             c.cached -= it->first.second;
             c.free_blocks.erase(it);
@@ -176,8 +223,8 @@ inline void* dev_alloc(size_t bytes) {
 }
 inline void dev_free(void* p) {
     if (!p) return;
-    // A buffer released while an exception unwinds the call may still be read by kernels already queued on the stream; the
-    // normal path only frees after the call synchronised its stream.  Drain the device before the block can be handed out again.
+    // A buffer released while an exception unwinds the call may still be read by kernels already queued on the stream (or on
+    // the context's side stream): drain the device before the block can be handed out again.
     if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
     DevCache& c = dev_cache();
     std::unique_lock<std::mutex> lock(c.m);
@@ -192,10 +239,28 @@ inline void dev_free(void* p) {
     // very large blocks (window tables) go back to the driver; the rest is kept for the next call
     if (key.second > ((size_t)4 << 30) || c.cached + key.second > c.cap) {
         lock.unlock();
-        cudaFree(p);
+        cudaFree(p);  // synchronises with the device's outstanding work by itself
         return;
     }
-    c.free_blocks.insert({key, p});
+    CachedBlock b{p, current_stream(), nullptr};
+    if (!c.spare_events.empty()) {
+        b.freed = c.spare_events.back();
+        c.spare_events.pop_back();
+    } else if (cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        b.freed = nullptr;
+    }
+    if (b.freed) {
+        if (cudaEventRecord(b.freed, b.owner) != cudaSuccess) {  // e.g. the stream is already destroyed (context teardown): fall back to a full drain
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            c.spare_events.push_back(b.freed);
+            b.freed = nullptr;
+        }
+    } else {
+        cudaDeviceSynchronize();
+    }
+    c.free_blocks.insert({key, b});
     c.cached += key.second;
 }
 inline void h2d(Stream s, void* dst, const void* src, size_t bytes) {
