@@ -316,7 +316,7 @@ class Context:
 
     def microbench(self, kind: str, iters: int) -> tuple[float, float]:
         """(ops per second over the chip, elapsed ms) for 'imad' | 'imad_wide' | 'fq_mul' | 'fr_mul' | 'g1_madd'."""
-        k = {"imad": 0, "imad_wide": 1, "fq_mul": 2, "fr_mul": 3, "g1_madd": 4, "dfma": 5, "imad_dfma": 6, "fr_chain": 7, "fq_chain": 8, "fr_inv_chain": 9, "fq_inv_chain": 10}[kind]
+        k = {"imad": 0, "imad_wide": 1, "fq_mul": 2, "fr_mul": 3, "g1_madd": 4, "dfma": 5, "imad_dfma": 6, "fr_chain": 7, "fq_chain": 8, "fr_inv_chain": 9, "fq_inv_chain": 10, "fq_sqr": 11, "fr_sqr": 12}[kind]
         ops, ms = ctypes.c_double(), c_float()
         self.library.check(self.library.lib.dr_microbench(self.handle, k, iters, ctypes.byref(ops), ctypes.byref(ms)))
         return float(ops.value), float(ms.value)

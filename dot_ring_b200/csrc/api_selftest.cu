@@ -155,6 +155,23 @@ __global__ void mb_field_chain(F* out, uint32_t seed, int iters) {
     for (int i = 0; i < iters; i++) x = x.sqr();
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
+// squaring throughput: 4 independent chains per thread, like mb_field_mul
+template <class F>
+__global__ void mb_field_sqr(F* out, uint32_t seed, int iters) {
+    F a = F::one(), b = F::one(), c = F::one(), d = F::one();
+    a.v[0] ^= seed + threadIdx.x;
+    b.v[1] ^= seed * 3 + threadIdx.x;
+    c.v[2] ^= seed * 5 + threadIdx.x;
+    d.v[3] ^= seed * 7 + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        a = a.sqr();
+        b = b.sqr();
+        c = c.sqr();
+        d = d.sqr();
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a + b + c + d;
+}
 template <class F>
 __global__ void mb_field_inv(F* out, uint32_t seed, int iters) {
     F x = F::one();
@@ -220,7 +237,8 @@ int dr_field_op(dr_ctx* c, int field, int op, const uint8_t* a, const uint8_t* b
 }
 
 // kind: 0 IMAD (32-bit mad.lo), 1 IMAD.WIDE (32x32+64), 2 Fq mul, 3 Fr mul, 4 G1 mixed add, 5 DFMA, 6 IMAD + DFMA interleaved (2 : 1),
-// 7 / 8 one dependent Fr / Fq squaring chain per warp, one warp per SM (latency), 9 / 10 the same for Fr / Fq inversions.
+// 7 / 8 one dependent Fr / Fq squaring chain per warp, one warp per SM (latency), 9 / 10 the same for Fr / Fq inversions,
+// 11 / 12 Fq / Fr squaring throughput.
 // Returns operations per second over the whole chip and the elapsed ms.
 int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_out) {
 #if defined(DR_HOST_EMULATION)
@@ -234,8 +252,9 @@ int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_o
         cudaDeviceProp prop;
         DR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
         // kinds 7..10 measure latency: one warp per SM, so nothing hides the dependent chain
-        const int threads = kind >= 7 ? 32 : 256;
-        const int blocks = prop.multiProcessorCount * (kind >= 7 ? 1 : kind >= 2 && kind <= 4 ? 2 : 8);
+        const bool latency = kind >= 7 && kind <= 10;
+        const int threads = latency ? 32 : 256;
+        const int blocks = prop.multiProcessorCount * (latency ? 1 : (kind >= 2 && kind <= 4) || kind >= 11 ? 2 : 8);
         size_t nthreads = (size_t)blocks * threads;
         DevBuf<uint8_t> out(nthreads * sizeof(G1));
         DevBuf<G1Affine> pts;
@@ -272,6 +291,8 @@ int dr_microbench(dr_ctx* c, int kind, int iters, double* ops_per_s, float* ms_o
                 case 8: mb_field_chain<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
                 case 9: mb_field_inv<Fr><<<blocks, threads, 0, ctx->stream>>>((Fr*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
                 case 10: mb_field_inv<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 1.0 * iters; break;
+                case 11: mb_field_sqr<Fq><<<blocks, threads, 0, ctx->stream>>>((Fq*)out.p, 12345u, iters); per_thread = 4.0 * iters; break;
+                case 12: mb_field_sqr<Fr><<<blocks, threads, 0, ctx->stream>>>((Fr*)out.p, 12345u, iters); per_thread = 4.0 * iters; break;
                 default: throw Error(DR_EINVAL, "unknown micro-benchmark");
             }
             DR_CUDA(cudaGetLastError());

@@ -292,7 +292,7 @@ int dr_pairing_check_batch(dr_ctx* ctx, const uint8_t* a1_be96, const uint8_t* b
  * little-endian).  op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 sqr(a), 5 neg(a).
  * dr_microbench: whole-chip ops/s of kind 0 IMAD, 1 IMAD.WIDE, 2 Fq mul, 3 Fr mul, 4 G1 mixed add, 5 DFMA, 6 IMAD + DFMA interleaved 2 : 1 (is the
  * FP64 pipe free next to the integer pipe?); 7 / 8: one dependent Fr / Fq squaring chain per warp with one warp per SM (the latency the
- * one-thread-per-item kernels pay), 9 / 10: the same for inversions.  ops/s / (32 x SM count) is then the rate of ONE chain. */
+ * one-thread-per-item kernels pay), 9 / 10: the same for inversions; 11 / 12: Fq / Fr squaring throughput.  ops/s / (32 x SM count) is then the rate of ONE chain. */
 int dr_field_op(dr_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t count);
 int dr_microbench(dr_ctx* ctx, int kind, int iters, double* ops_per_s, float* ms_out);
 

@@ -178,6 +178,56 @@ def prog_mul(n: int, pl: list[int], m0: int, square: bool = False) -> Prog:
     return p
 
 
+def prog_sqr(n: int, pl: list[int], m0: int) -> Prog:
+    """Montgomery squaring by product scanning (FIPS): column k of a^2 + m p is accumulated in three registers.  The cross products
+    a_i a_j (i < j) are formed once and doubled, so a squaring issues (n^2 + n) / 2 + n^2 word products (lo + hi multiply-adds each)
+    instead of the 2 n^2 of a multiplication: 456 vs 600 IMAD for 12 limbs, 208 vs 272 for 8; the extra work is additions with
+    carry, which run on the ALU pipe next to the multiply-add pipe the kernels are bound by."""
+    p = Prog()
+    A = [f"a{k}" for k in range(n)]
+    Q = [f"q{k}" for k in range(2 * n + 3)]  # column k lives in (q_k, q_k+1, q_k+2)
+    M = [f"m{k}" for k in range(n)]
+
+    def acc3(t, x, y):  # (t0, t1, t2) += x * y
+        p.emit("mad.lo.cc", t[0], x, y, t[0])
+        p.emit("madc.hi.cc", t[1], x, y, t[1])
+        p.emit("addc", t[2], t[2], 0)
+
+    for r in Q[:3]:
+        p.emit("mov", r, 0)
+    for k in range(2 * n):
+        c = Q[k : k + 3]
+        if k > 0:
+            p.emit("mov", c[2], 0)
+        pairs = [(i, k - i) for i in range(max(0, k - n + 1), (k + 1) // 2) if i < k - i]
+        if pairs:
+            X = ["x0", "x1", "x2"]
+            i0, j0 = pairs[0]
+            p.emit("mul.lo", X[0], A[i0], A[j0])
+            p.emit("mul.hi", X[1], A[i0], A[j0])
+            p.emit("mov", X[2], 0)
+            for i, j in pairs[1:]:
+                acc3(X, A[i], A[j])
+            p.emit("add.cc", X[0], X[0], X[0])  # 2 x
+            p.emit("addc.cc", X[1], X[1], X[1])
+            p.emit("addc", X[2], X[2], X[2])
+            p.emit("add.cc", c[0], c[0], X[0])  # c += x
+            p.emit("addc.cc", c[1], c[1], X[1])
+            p.emit("addc", c[2], c[2], X[2])
+        if k % 2 == 0 and k // 2 < n:
+            acc3(c, A[k // 2], A[k // 2])
+        if k < n:
+            for j in range(k):
+                acc3(c, M[j], pl[k - j])
+            p.emit("mul.lo", M[k], c[0], m0)
+            acc3(c, M[k], pl[0])  # makes c[0] zero
+        else:
+            for j in range(k - n + 1, n):
+                acc3(c, M[j], pl[k - j])
+    final_sub(p, n, Q[n : 2 * n], [f"r{k}" for k in range(n)], pl)
+    return p
+
+
 def prog_add(n: int, pl) -> Prog:
     p = Prog()
     for k in range(n):
@@ -202,7 +252,7 @@ def check(name: str, prime: int, n: int, trials: int = 3000) -> dict[str, Prog]:
     pl = limbs(prime, n)
     m0 = (-pow(prime, -1, 1 << 32)) & M32
     rinv = pow(1 << (32 * n), -1, prime)
-    progs = {"mul": prog_mul(n, pl, m0), "sqr": prog_mul(n, pl, m0, square=True), "add": prog_add(n, pl), "sub": prog_sub(n, pl)}
+    progs = {"mul": prog_mul(n, pl, m0), "sqr": prog_sqr(n, pl, m0), "add": prog_add(n, pl), "sub": prog_sub(n, pl)}
     rng = random.Random(0xD07)
     edge = [0, 1, 2, prime - 1, prime - 2, (1 << 32) - 1, 1 << 32, (1 << (32 * n - 1)) % prime, prime >> 1, (prime >> 1) + 1]
     cases = [(x, y) for x in edge for y in edge] + [(rng.randrange(prime), rng.randrange(prime)) for _ in range(trials)]
@@ -215,7 +265,9 @@ def check(name: str, prime: int, n: int, trials: int = 3000) -> dict[str, Prog]:
             want = {"mul": a * b * rinv % prime, "sqr": a * a * rinv % prime, "add": (a + b) % prime, "sub": (a - b) % prime}[op]
             if got != want:
                 raise SystemExit(f"{name}.{op} mismatch for a={a:#x} b={b:#x}: got {got:#x} want {want:#x}")
-    print(f"{name}: {len(cases)} cases x {len(progs)} ops verified; mul = {len(progs['mul'].ins)} PTX instructions", file=sys.stderr)
+    imad = lambda pr: sum(1 for ins in pr.ins if ins[0].startswith(("mul.", "mad", "madc")))  # noqa: E731
+    print(f"{name}: {len(cases)} cases x {len(progs)} ops verified; mul = {len(progs['mul'].ins)} PTX instructions ({imad(progs['mul'])} multiply-adds), "
+          f"sqr = {len(progs['sqr'].ins)} ({imad(progs['sqr'])} multiply-adds)", file=sys.stderr)
     return progs
 
 
@@ -227,7 +279,7 @@ def render_fn(fname: str, n: int, prog: Prog, nin: int) -> str:
     body = prog.render(opidx)
     lines = [f"__device__ __forceinline__ void {fname}(uint32_t* __restrict__ r, const uint32_t* a" + (", const uint32_t* b" if nin == 2 else "") + ") {"]
     lines.append("    asm(\"{\\n\\t\"")
-    lines.append(f"        \".reg .u32 e<{n}>, o<{n}>, s<{n}>, mi, bm;\\n\\t\"")
+    lines.append(f"        \".reg .u32 e<{n}>, o<{n}>, s<{n}>, q<{2 * n + 3}>, m<{n}>, x<3>, mi, bm;\\n\\t\"")
     lines.append("        \".reg .pred pb;\\n\\t\"")
     for ln in body:
         lines.append(f"        \"{ln}\\n\\t\"")
