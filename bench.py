@@ -75,6 +75,9 @@ def canonical_fq_mul_per_msm(n: int) -> int:
 
 
 CANONICAL_IMAD_PER_PROOF = sum(canonical_fq_mul_per_msm(n) for n in MSM_SIZES) * 600  # 600 IMAD per 12-limb Montgomery mul
+# executed by one XYZZ mixed addition: 8 multiplications (600 IMAD each, the CIOS word-product count) + 2 squarings (456: the cross
+# products are formed once, tools/gen_field_asm.py prog_sqr)
+MADD_IMAD = 8 * 600 + 2 * 456
 
 
 class ClockSampler(threading.Thread):
@@ -416,11 +419,11 @@ def run_ours(args) -> None:
     wbits = ring.native.witness_table_bits() or 10
     # dominant kernel = the dense fixed-base commit (quotient + two openings); event-timed around its launches only
     dense_madds = sum(DENSE_MSM_SIZES) * windows
-    kernel_imad = dense_madds * 10 * 600 * mine * args.steps / pool_devices  # per device: 8M + 2S per mixed addition, 600 IMAD per Fq mul
+    kernel_imad = dense_madds * MADD_IMAD * mine * args.steps / pool_devices  # per device
     kernel_rate = kernel_imad / (kernel_ms * 1e-3) if kernel_ms else 0.0
     canonical_dense = sum(canonical_fq_mul_per_msm(n) for n in DENSE_MSM_SIZES) * 600
     madds_per_proof = dense_madds + sparse_witness_madds(wbits)
-    step_imad = madds_per_proof * 10 * 600 * mine * args.steps / pool_devices
+    step_imad = madds_per_proof * MADD_IMAD * mine * args.steps / pool_devices
     table_bytes_per_launch = dense_madds * 96 * per_device / 3  # average over the 3 launches of a pass
 
     if dist is not None:
@@ -462,12 +465,12 @@ def run_ours(args) -> None:
             "bound": "imad (int32 multiply-add pipe; neither hbm nor tensor: the path is 381-bit modular arithmetic)",
             "achieved": kernel_rate / 1e12,
             "peak": imad_peak / 1e12,
-            "unit": "T IMAD/s executed by the kernel (mixed G1 additions issued x 10 Fq mul x 600 IMAD), CUDA events around its launches only",
+            "unit": "T IMAD/s executed by the kernel (mixed G1 additions issued x (8 mul x 600 + 2 sqr x 456) IMAD), CUDA events around its launches only",
             "frac": kernel_rate / imad_peak,
             "kernel_ms_per_step": kernel_ms / args.steps,
             "kernel_launches_per_step": kernel_launches / args.steps,
             "kernel_share_of_step": kernel_ms / dev_ms if dev_ms else None,
-            "algorithmic_reduction": canonical_dense / (dense_madds * 6000),
+            "algorithmic_reduction": canonical_dense / (dense_madds * MADD_IMAD),
             "algorithmic_reduction_note": "canonical Pippenger IMAD of the same three MSMs (SURVEY.md 8d) / IMAD executed: the fixed-base table removes buckets and doublings",
             "whole_step_executed_frac": step_imad / (dev_ms * 1e-3) / imad_peak if dev_ms else None,
             "whole_step_canonical_frac": CANONICAL_IMAD_PER_PROOF * mine * args.steps / pool_devices / (dev_ms * 1e-3) / imad_peak if dev_ms else None,
