@@ -170,7 +170,11 @@ class KZG:
         pts = list(points)
         if len(pts) != len(scalars):
             raise ValueError("points and scalars must have the same length")
-        return default_engine().ctx.g1_msm(b"".join(bytes(p) for p in pts), [int(k) for k in scalars])
+        eng = default_engine()
+        data, ks = b"".join(bytes(p) for p in pts), [int(k) for k in scalars]
+        if hasattr(eng, "g1_msm"):  # EnginePool: very large point sets are split by range over the devices
+            return eng.g1_msm(data, ks)
+        return eng.ctx.g1_msm(data, ks)
 
     @classmethod
     def compress_g1(cls, point: bytes) -> bytes:

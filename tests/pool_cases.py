@@ -39,3 +39,16 @@ def check_pool_matches_single(api, pool, single_engine, n: int = 5) -> None:
     # shard arithmetic: contiguous, balanced, order-preserving
     assert pool.shard_bounds(5, 2) == [(0, 3), (3, 5)] and pool.shard_bounds(1, 2) == [(0, 1)] and pool.shard_bounds(0, 2) == []
     assert pool.shard_bounds(4096, 8) == [(512 * i, 512 * (i + 1)) for i in range(8)]
+
+
+def check_range_split_msm(pool, ctx, n: int = 40) -> None:
+    """EnginePool.g1_msm: the point-range split gives the same 96 bytes as one device."""
+    from dot_ring_b200.srs import read_srs_file
+
+    raw = read_srs_file(None, n)
+    rng = random.Random(8)
+    ks = [rng.randrange(1 << 255) for _ in range(n)]
+    ks[0], ks[1] = 0, 1
+    whole = ctx.g1_msm(raw.g1_be96, ks)
+    assert pool.g1_msm(raw.g1_be96, ks, min_points_per_device=7) == whole  # forces a split into len(pool) ranges
+    assert pool.g1_msm(raw.g1_be96, ks) == whole  # default threshold: not split

@@ -48,6 +48,7 @@ def test_engine_pool_shards_like_one_device(api):
     pool = engine_mod.EnginePool(devices=[0, 0], window_bits=4, library=lib, srs_points=1537)
     try:
         pool_cases.check_pool_matches_single(api, pool, engine_mod.default_engine(), n=5)
+        pool_cases.check_range_split_msm(pool, engine_mod.default_engine().ctx)
     finally:
         pool.close()
 

@@ -102,6 +102,7 @@ def test_engine_pool_matches_single_device(api):
     pool = engine_mod.EnginePool(devices=devices, window_bits=8, srs_points=1537)
     try:
         pool_cases.check_pool_matches_single(api, pool, engine_mod.default_engine(), n=37)
+        pool_cases.check_range_split_msm(pool, engine_mod.default_engine().ctx, n=3000)
     finally:
         pool.close()
 
