@@ -107,13 +107,13 @@ static std::atomic<size_t> VRF_VERIFY_COOP_BELOW{8192};
 
 static void launch_pedersen_verify(Ctx* ctx, Stream st, SuiteDev su, const VerifyInput* in, const uint8_t* blob, const uint8_t* proofs, uint32_t stride, const TEAffine* pts,
                                    const uint8_t* ok, uint32_t m, uint32_t* status) {
+    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);  // the context keeps them alive
+    su.g_tab = g_table->tab.p;
+    su.b_tab = b_table->tab.p;
     if (m >= VRF_VERIFY_COOP_BELOW.load()) {
         launch(st, Dim3((m + 63) / 64), 64, 0, PedersenVerifySerialBody(), su, in, blob, proofs, stride, pts, ok, m, status);
         return;
     }
-    auto g_table = ctx->fixed_table(su.generator), b_table = ctx->fixed_table(su.blinding_base);  // the context keeps them alive
-    su.g_tab = g_table->tab.p;
-    su.b_tab = b_table->tab.p;
     launch(st, Dim3((m + VRF_VERIFY_ITEMS - 1) / VRF_VERIFY_ITEMS), VRF_VERIFY_THREADS, vrf_verify_coop_smem(VRF_VERIFY_THREADS), PedersenVerifyBody(), su, in, blob, proofs, stride,
            pts, ok, m, status);
 }

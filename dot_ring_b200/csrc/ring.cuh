@@ -180,10 +180,10 @@ DR_HD void fn_raw_limbs(uint32_t* out, const Fn& x_mont) {
     Fn x = x_mont.from_mont();
     for (int i = 0; i < 8; i++) out[i] = x.v[i];
 }
-DR_HD_COLD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {
+DR_HD_COLD TEAffine te_mul_fn(const TEAffine& p, const Fn& k) {  // p in the prime subgroup
     uint32_t kr[8];
     fn_raw_limbs(kr, k);
-    return te_to_affine(te_mul_raw(p, kr, 8));
+    return te_to_affine(te_mul_glv(p, kr));
 }
 DR_HD void sha_absorb_point(VrfHash& s, const TEAffine& p) {
     uint8_t b[32];
@@ -280,7 +280,7 @@ DR_HD_COLD void pedersen_prove_begin(const S& rg, const uint8_t* sk32, const TEA
     Fn x = fp_from_le_bytes_mod<Fn>(sk32, 32);
     uint32_t xr[8];
     fn_raw_limbs(xr, x);
-    pedersen_begin_transcript(rg, x, input, te_mul_fixed(rg.g_tab, xr), te_mul_raw(input, xr, 8), ad, ad_len, out192, pk, blinding_raw, tr);
+    pedersen_begin_transcript(rg, x, input, te_mul_fixed(rg.g_tab, xr), te_mul_glv(input, xr), ad, ad_len, out192, pk, blinding_raw, tr);
     pedersen_begin_blind(pk, te_mul_fixed(rg.b_tab, blinding_raw), out192, blinded, tr);
 }
 // Second half: nonces, R, Ok, challenge, responses.  Writes R | Ok | s | sb into out192 + 64.
@@ -296,7 +296,7 @@ DR_HD_COLD void pedersen_prove_finish(const S& rg, const uint8_t* sk32, const TE
     fn_raw_limbs(kr, k);
     fn_raw_limbs(kbr, kb);
     TEAffine R, ok;
-    te_to_affine2(te_add(te_mul_fixed(rg.g_tab, kr), te_mul_fixed(rg.b_tab, kbr)), te_mul_raw(input, kr, 8), R, ok);
+    te_to_affine2(te_add(te_mul_fixed(rg.g_tab, kr), te_mul_fixed(rg.b_tab, kbr)), te_mul_glv(input, kr), R, ok);
     VrfHash tc = tr;
     tc.update_byte(0x40);
     sha_absorb_point(tc, R);
@@ -377,19 +377,27 @@ struct PedersenStartBody {
                 TEExt sum = te_add(TEExt::from_affine(maps[2 * item]), TEExt::from_affine(maps[2 * item + 1]));
                 const TEAffine input = te_to_affine(te_dbl(te_dbl(sum)));
                 st[p].vrf_input = input;
-                s.tab[0].c[CX] = input.x;
-                s.tab[0].c[CY] = input.y;
-                s.tab[0].c[CZ] = Fr::one();
-                s.tab[0].c[CT] = input.x * input.y;
-                fn_raw_limbs(s.k, fp_from_le_bytes_mod<Fn>(in[p].sk, 32));
+                // sk * input = k1 * (+-input) + k2 * (+-psi(input)) with 128-bit halves (te.cuh te_glv_split): half the doublings
+                uint32_t xr[8];
+                fn_raw_limbs(xr, fp_from_le_bytes_mod<Fn>(in[p].sk, 32));
+                bool n1, n2;
+                te_glv_split(xr, s.k, n1, s.k2, n2);
+                coop_set_point(s.tab[0], TEExt::from_affine(n1 ? te_neg(input) : input));
+                const TEExt psi = te_endomorphism(input);
+                coop_set_point(s.tab2[0], n2 ? te_neg(psi) : psi);
             }
         }
         DR_BLOCK_SYNC();
-        te_mul_coop(ctx, cs, 8);
+        te_straus_coop(ctx, cs, 4, 4);
         // C. sk * G by windows
         DR_THREAD_LOOP(t, ctx) {
-            TeCoopState& s = cs[t / COOP_LANES];
-            if (s.live) te_mul_fixed_coop_partial(t % COOP_LANES, rg.g_tab, s.k, s.part);
+            const uint32_t item = t / COOP_LANES, p = ctx.bx * items + item;
+            TeCoopState& s = cs[item];
+            if (s.live) {
+                uint32_t xr[8];
+                fn_raw_limbs(xr, fp_from_le_bytes_mod<Fn>(in[p].sk, 32));
+                te_mul_fixed_coop_partial(t % COOP_LANES, rg.g_tab, xr, s.part);
+            }
         }
         DR_BLOCK_SYNC();
         // D. public key, output point, transcript, blinding factor (one lane); the public key waits in s.m for step F

@@ -7,8 +7,10 @@
 //   dot_ring/curve/twisted_edwards/te_affine_point.py:69-316 (affine law, from_mont, x-recover)
 //   dot_ring/curve/twisted_edwards/te_curve.py:48-95         (Elligator 2 map)
 //   dot_ring/curve/point.py:150-214, dot_ring/vrf/codec.py:39-45, dot_ring/curve/curve.py:56-67
-// Points are unique group elements, so the multiplication schedule is ours (fixed 4-bit windows
-// with shared doublings) rather than the reference's GLV + 2-bit joint windows.
+//   dot_ring/curve/glv.py:128-189, specs/bandersnatch.py:65-67,177-286 (GLV: endomorphism, scalar split)
+// Points are unique group elements, so the multiplication schedule is ours: full-length multiplications of subgroup points go
+// through the endomorphism like the reference's (two 128-bit halves, half the doublings) but with 4-bit windows and shared
+// doublings (Straus) instead of its 2-bit joint windows; fixed bases use window tables without doublings.
 #pragma once
 #include "fp.cuh"
 
@@ -189,6 +191,156 @@ DR_HD_COLD bool te_in_prime_subgroup_by_order(const TEAffine& p) {
 //   (a - d)(a - d y^2)  and  2 (1 - y) ((a - s) - (d - s) y)   are both non-zero squares.
 // Two Legendre symbols (binary Jacobi algorithm) replace ~2700 field multiplications; the reference multiplies by the order
 // (curve.py:56-67), the verdict is the same.  x = 0 holds the identity (in) and the 2-torsion point (0, -1) (out).
+// ---- GLV (curve/glv.py:128-189; specs/bandersnatch.py:65-67,177-286) ---------------------------------------------------------
+// Bandersnatch has an endomorphism psi with psi(P) = lambda P on the prime subgroup, so k P = k1 P + k2 psi(P) with |k1|, |k2| < 2^127
+// and a joint multiplication does half the doublings.  The split uses the short lattice basis v1 = (a1, b1), v2 = (a2, -a1) of
+// {(x, y): x + y lambda = 0 mod n}:  c1 = floor(k a1 / n), c2 = floor(k b1 / n) (Barrett, exact to within one),
+//   k1 = k - c1 a1 - c2 a2,   k2 = c2 a1 - c1 b1.
+// Any (k1, k2) with k1 + k2 lambda = k is as good as the reference's (the group element is the same); magnitudes and signs out.
+DR_HD void limbs_mul(uint32_t* out, const uint32_t* a, int na, const uint32_t* b, int nb) {  // out[na + nb] = a * b
+    for (int i = 0; i < na + nb; i++) out[i] = 0;
+    for (int i = 0; i < na; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < nb; j++) {
+            uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+            out[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        out[i + nb] = (uint32_t)carry;
+    }
+}
+// k: 8 raw limbs below the group order.  k1, k2: 4-limb magnitudes (upper limbs of the 8-limb outputs are zero), neg1 / neg2: signs.
+DR_HD_COLD void te_glv_split(const uint32_t* k, uint32_t* k1, bool& neg1, uint32_t* k2, bool& neg2) {
+    constexpr uint32_t A1[4] = DR_TE_GLV_A1, B1[4] = DR_TE_GLV_B1, A2[4] = DR_TE_GLV_A2, G1[5] = DR_TE_GLV_G1, G2[4] = DR_TE_GLV_G2;
+    uint32_t a1[4], b1[4], a2[4], g1[5], g2[4];
+    for (int i = 0; i < 4; i++) {
+        a1[i] = A1[i];
+        b1[i] = B1[i];
+        a2[i] = A2[i];
+        g2[i] = G2[i];
+    }
+    for (int i = 0; i < 5; i++) g1[i] = G1[i];
+    uint32_t wide[13], c1[5], c2[4];
+    limbs_mul(wide, k, 8, g1, 5);
+    for (int i = 0; i < 5; i++) c1[i] = wide[8 + i];  // < 2^128: c1[4] == 0
+    limbs_mul(wide, k, 8, g2, 4);
+    for (int i = 0; i < 4; i++) c2[i] = wide[8 + i];
+    uint32_t p[9], q[9], acc[9];
+    // k1 = k - c1 a1 - c2 a2  (9-limb two's complement)
+    limbs_mul(p, c1, 4, a1, 4);
+    p[8] = 0;
+    limbs_mul(q, c2, 4, a2, 4);
+    q[8] = 0;
+    {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 9; i++) {
+            uint64_t t = (uint64_t)(i < 8 ? k[i] : 0u) - p[i] - borrow;
+            acc[i] = (uint32_t)t;
+            borrow = (t >> 32) & 1;
+        }
+        borrow = 0;
+        for (int i = 0; i < 9; i++) {
+            uint64_t t = (uint64_t)acc[i] - q[i] - borrow;
+            acc[i] = (uint32_t)t;
+            borrow = (t >> 32) & 1;
+        }
+    }
+    auto magnitude = [](const uint32_t* v, uint32_t* out, bool& neg) {
+        neg = (v[8] >> 31) != 0;
+        uint64_t carry = 1;
+        for (int i = 0; i < 8; i++) {
+            uint32_t w = v[i];
+            if (neg) {
+                uint64_t t = (uint64_t)(~w) + carry;
+                w = (uint32_t)t;
+                carry = t >> 32;
+            }
+            out[i] = w;
+        }
+    };
+    magnitude(acc, k1, neg1);
+    // k2 = c2 a1 - c1 b1
+    limbs_mul(p, c2, 4, a1, 4);
+    p[8] = 0;
+    limbs_mul(q, c1, 4, b1, 4);
+    q[8] = 0;
+    {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 9; i++) {
+            uint64_t t = (uint64_t)p[i] - q[i] - borrow;
+            acc[i] = (uint32_t)t;
+            borrow = (t >> 32) & 1;
+        }
+    }
+    magnitude(acc, k2, neg2);
+}
+// psi(P) in extended coordinates for an affine P of the prime subgroup (glv.py:165-189: x' = c (1 - y^2)(y^2 - b), y' = b (y^2 + b) x y,
+// z' = (y^2 - b) x y); the identity maps to the identity.
+DR_HD TEExt te_endomorphism(const TEAffine& p) {
+    constexpr uint32_t b_c[8] = DR_TE_GLV_B, c_c[8] = DR_TE_GLV_C;
+    Fr b, c;
+    for (int i = 0; i < 8; i++) {
+        b.v[i] = b_c[i];
+        c.v[i] = c_c[i];
+    }
+    if (p.x.is_zero()) return TEExt::identity();
+    const Fr y2 = p.y.sqr(), xy = p.x * p.y;
+    const Fr h = y2 - b;
+    const Fr xp = c * (Fr::one() - y2) * h, yp = b * (y2 + b) * xy, zp = h * xy;
+    return {xp * zp, yp * zp, zp.sqr(), xp * yp};
+}
+
+// sum_j k_j P_j for up to three points in EXTENDED coordinates and scalars of `nlimbs` limbs: Straus with shared doublings, 4-bit windows
+DR_HD_COLD TEExt te_straus_ext(const TEExt* pts, const uint32_t (*ks)[8], int n, int nlimbs) {
+    TEExt tab[3][16];
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        tab[j][0] = TEExt::identity();
+        tab[j][1] = pts[j];
+#pragma unroll 1
+        for (int i = 2; i < 16; i++) tab[j][i] = (i & 1) ? te_add(tab[j][i - 1], tab[j][1]) : te_dbl(tab[j][i >> 1]);
+    }
+    TEExt acc = TEExt::identity();
+    bool started = false;
+#pragma unroll 1
+    for (int i = nlimbs - 1; i >= 0; i--) {
+#pragma unroll 1
+        for (int s = 28; s >= 0; s -= 4) {
+            if (started) acc = te_dbl(te_dbl(te_dbl(te_dbl(acc))));
+#pragma unroll 1
+            for (int j = 0; j < n; j++) {
+                uint32_t d = (ks[j][i] >> s) & 15;
+                if (d) {
+                    acc = started ? te_add(acc, tab[j][d]) : tab[j][d];
+                    started = true;
+                }
+            }
+        }
+    }
+    return acc;
+}
+// k P for a point of the prime subgroup and a scalar below the group order, through the endomorphism: 127 doublings instead of 252
+DR_HD_COLD TEExt te_mul_glv(const TEAffine& p, const uint32_t* k) {
+    uint32_t ks[2][8];
+    bool n1, n2;
+    te_glv_split(k, ks[0], n1, ks[1], n2);
+    TEExt pts[2] = {TEExt::from_affine(n1 ? te_neg(p) : p), te_endomorphism(p)};
+    if (n2) pts[1] = te_neg(pts[1]);
+    return te_straus_ext(pts, ks, 2, 4);
+}
+
+// k P + c Q: P affine in the prime subgroup with a full-length scalar k (split by the endomorphism), Q any point with a scalar of at
+// most 128 bits -- the shape of every verification equation (s * input - c * output): one Straus pass over 32 windows
+DR_HD_COLD TEExt te_glv_straus2(const TEAffine& p, const uint32_t* k, const TEExt& q, const uint32_t* c128) {
+    uint32_t ks[3][8];
+    bool n1, n2;
+    te_glv_split(k, ks[0], n1, ks[1], n2);
+    for (int i = 0; i < 8; i++) ks[2][i] = i < 4 ? c128[i] : 0u;
+    TEExt pts[3] = {TEExt::from_affine(n1 ? te_neg(p) : p), te_endomorphism(p), q};
+    if (n2) pts[1] = te_neg(pts[1]);
+    return te_straus_ext(pts, ks, 3, 4);
+}
+
 DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
     constexpr uint32_t amd_c[8] = DR_TE_A_MINUS_D, ams_c[8] = DR_TE_A_MINUS_S, dms_c[8] = DR_TE_D_MINUS_S;
     if (p.x.is_zero()) return p.y == Fr::one();

@@ -85,25 +85,13 @@ DR_HD_COLD uint32_t pedersen_verify_core(const S& su, const TEAffine* pts, const
     vrf_squeeze(tr, cb, 16);
     uint32_t c[8];
     load_le_limbs8(c, cb, 16);
-    // s*I - c*O == Ok
-    TEAffine p2[3];
-    uint32_t k2[3][8];
-    p2[0] = input;
-    p2[1] = te_neg(pts[0]);
-    for (int i = 0; i < 8; i++) {
-        k2[0][i] = ks[0][i];
-        k2[1][i] = c[i];
-    }
-    bool ok = te_ext_eq_affine(te_msm_small(p2, k2, 2), pts[3]);
-    // s*G + sb*B - c*Ybar == R
-    p2[0] = su.generator;
-    p2[1] = su.blinding_base;
-    p2[2] = te_neg(pts[1]);
-    for (int i = 0; i < 8; i++) {
-        k2[1][i] = ks[1][i];
-        k2[2][i] = c[i];
-    }
-    ok = ok && te_ext_eq_affine(te_msm_small(p2, k2, 3), pts[2]);
+    // s*I - c*O == Ok: s split by the endomorphism, one 32-window Straus pass over (I, psi(I), -O)
+    bool ok = te_ext_eq_affine(te_glv_straus2(input, ks[0], TEExt::from_affine(te_neg(pts[0])), c), pts[3]);
+    // s*G + sb*B - c*Ybar == R: the two fixed bases from their window tables (no doublings), the blinded key by a 128-bit multiplication
+    const TEAffine nyb = te_neg(pts[1]);
+    TEExt lhs = te_add(te_mul_fixed(su.g_tab, ks[0]), te_mul_fixed(su.b_tab, ks[1]));
+    lhs = te_add(lhs, te_mul_raw(nyb, c, 4));
+    ok = ok && te_ext_eq_affine(lhs, pts[2]);
     return ok ? 0u : ST_PEDERSEN_BAD;
 }
 
@@ -168,7 +156,9 @@ struct IetfVerifySerialBody {
                     load_le_limbs8(z, zb, 16);
                     TEExt min = te_add(TEExt::from_affine(su.generator), te_mul_raw(input, z, 4));
                     TEExt mout = te_add(TEExt::from_affine(pk), te_mul_raw(out, z, 4));
-                    TEAffine p2[2] = {te_to_affine(min), te_neg(te_to_affine(mout))};
+                    // s*I' - c*O' with s split by the endomorphism (I' affine for psi; O' stays projective)
+                    const TEAffine min_a = te_to_affine(min);
+                    const TEExt nmout = te_neg(mout);
                     tr.update_byte(0x40);
                     if (thin) {
                         const TEAffine r = pts[(size_t)npts * i + 1];
@@ -176,10 +166,10 @@ struct IetfVerifySerialBody {
                         uint8_t cb[16];
                         vrf_squeeze(tr, cb, 16);
                         load_le_limbs8(ks[1], cb, 16);
-                        if (!te_ext_eq_affine(te_msm_small(p2, ks, 2), r)) st = ST_PEDERSEN_BAD;
+                        if (!te_ext_eq_affine(te_glv_straus2(min_a, ks[0], nmout, ks[1]), r)) st = ST_PEDERSEN_BAD;
                     } else {
                         load_le_limbs8(ks[1], pr + 32, 16);  // c
-                        TEAffine r = te_to_affine(te_msm_small(p2, ks, 2));  // s*I' - c*O'
+                        TEAffine r = te_to_affine(te_glv_straus2(min_a, ks[0], nmout, ks[1]));  // s*I' - c*O'
                         sha_absorb_point(tr, r);
                         uint8_t cb[16];
                         vrf_squeeze(tr, cb, 16);
@@ -481,7 +471,7 @@ struct IetfProveBody {  // thin == 0: O | c | s (80 bytes);  thin != 0: O | R | 
                 fn_raw_limbs(xr, x);
                 TEAffine input = vrf_encode_to_curve(su, blob + vi.in_off, vi.in_len);
                 TEAffine pk, output;
-                te_to_affine2(te_mul_fixed(su.g_tab, xr), te_mul_raw(input, xr, 8), pk, output);
+                te_to_affine2(te_mul_fixed(su.g_tab, xr), te_mul_glv(input, xr), pk, output);
                 VrfHash tr;
                 tr.init(su.hash_kind);
                 tr.update(su.suite_id, su.suite_id_len);

@@ -77,6 +77,24 @@ int ht_te_subgroup(const uint8_t* xy64) {
     TEAffine p{fr_in(xy64), fr_in(xy64 + 32)};
     return (te_in_prime_subgroup(p) ? 1 : 0) | (te_in_prime_subgroup_by_order(p) ? 2 : 0);
 }
+// GLV: out32 = encode(k * P) through te_mul_glv; split16x2 = |k1| (16 bytes LE) | |k2| (16 bytes LE); returns sign bits (1: k1 < 0, 2: k2 < 0)
+int ht_te_mul_glv(const uint8_t* point32, const uint8_t* k32, uint8_t* out32, uint8_t* split32) {
+    TEAffine p;
+    if (!te_decode(p, point32)) return -1;
+    uint32_t k[8], k1[8], k2[8];
+    for (int i = 0; i < 8; i++) k[i] = (uint32_t)k32[4 * i] | ((uint32_t)k32[4 * i + 1] << 8) | ((uint32_t)k32[4 * i + 2] << 16) | ((uint32_t)k32[4 * i + 3] << 24);
+    bool n1, n2;
+    te_glv_split(k, k1, n1, k2, n2);
+    for (int i = 4; i < 8; i++)
+        if (k1[i] | k2[i]) return -2;  // halves must fit 128 bits
+    for (int i = 0; i < 4; i++)
+        for (int b = 0; b < 4; b++) {
+            split32[4 * i + b] = (uint8_t)(k1[i] >> (8 * b));
+            split32[16 + 4 * i + b] = (uint8_t)(k2[i] >> (8 * b));
+        }
+    te_encode(out32, te_to_affine(te_mul_glv(p, k)));
+    return (n1 ? 1 : 0) | (n2 ? 2 : 0);
+}
 // reduce len bytes (little-endian) mod the Bandersnatch group order; out 32 LE
 void ht_fn_from_bytes_mod(const uint8_t* in, int len, uint8_t* out) {
     Fn x = fp_from_le_bytes_mod<Fn>(in, len).from_mont();

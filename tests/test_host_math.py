@@ -181,6 +181,26 @@ def test_subgroup_test_by_two_descent(lib):
     assert lib.ht_te_subgroup(enc(g)) == 3 and lib.ht_te_subgroup(enc(bs.IDENTITY)) == 3 and lib.ht_te_subgroup(enc(t2)) == 0
 
 
+def test_glv_split_and_multiplication(lib):
+    """te.cuh te_glv_split / te_endomorphism / te_mul_glv: k = k1 + k2 lambda (mod n) with 128-bit halves, and the joint
+    multiplication equals the plain one (oracle) -- incl. scalars 0, 1, n - 1 and the reference's golden scalar multiplications."""
+    lam = 0x13B4F3DC4A39A493EDF849562B38C72BCFC49DB970A5056ED13D21408783DF05
+    rng = random.Random(14)
+    g = load("bandersnatch_reference.json")
+    cases = [(bytes.fromhex(e["base"]), int(e["k"], 16), bytes.fromhex(e["out"])) for e in g["scalar_mul"]]
+    base = bs.mul(bs.GENERATOR, 777)
+    for k in [0, 1, 2, bs.N - 1, bs.N - 2, bs.N // 2, (1 << 252) - 1] + [rng.randrange(bs.N) for _ in range(40)]:
+        cases.append((bs.point_to_string(base), k, bs.point_to_string(bs.mul(base, k))))
+    for enc, k, want in cases:
+        out, split = _buf(32), _buf(32)
+        signs = lib.ht_te_mul_glv(enc, (k % bs.N).to_bytes(32, "little"), out, split)
+        assert signs >= 0, signs
+        k1 = int.from_bytes(split.raw[:16], "little") * (-1 if signs & 1 else 1)
+        k2 = int.from_bytes(split.raw[16:], "little") * (-1 if signs & 2 else 1)
+        assert (k1 + k2 * lam - k) % bs.N == 0 and abs(k1) < 1 << 127 and abs(k2) < 1 << 127
+        assert out.raw == want, hex(k)
+
+
 def test_bandersnatch_against_reference_goldens(lib):
     g = load("bandersnatch_reference.json")
     for e in g["dec_point"]:

@@ -363,6 +363,22 @@ def main() -> None:
     c.append(f"#define DR_TE_A_MINUS_D {m8(te_a - te_d)}")
     c.append(f"#define DR_TE_A_MINUS_S {m8(te_a - s_ad)}  // a - sqrt(a d)")
     c.append(f"#define DR_TE_D_MINUS_S {m8(te_d - s_ad)}  // d - sqrt(a d)")
+    # GLV on Bandersnatch (curve/glv.py:128-189, specs/bandersnatch.py:65-67): endomorphism constants (Montgomery) and the short
+    # lattice basis v1 = (a1, b1), v2 = (a2, -a1) of {(x, y): x + y lambda = 0 mod n} with the two Barrett factors floor(2^256 |b| / n)
+    glv_lambda = 0x13B4F3DC4A39A493EDF849562B38C72BCFC49DB970A5056ED13D21408783DF05
+    glv_b = 0x52C9F28B828426A561F00D3A63511A882EA712770D9AF4D6EE0F014D172510B4
+    glv_c = 0x6CC624CF865457C3A97C6EFD6C17D1078456ABCFFF36F4E9515C806CDF650B3D
+    order = FIELDS["fn"]
+    a1, b1, a2 = 0x555FE2004BE6928E4B02F94A9789181F, 0x0814B3EEE55E8F5DF8E2591A23D61F44, 0x102967DDCABD1EBBF1C4B23447AC3E88
+    assert (a1 + b1 * glv_lambda) % order == 0 and (a2 - a1 * glv_lambda) % order == 0 and a1 * a1 + b1 * a2 == order
+    raw = lambda x, k: "{" + ", ".join(f"0x{v:08x}u" for v in limbs(x, k)) + "}"  # noqa: E731
+    c.append(f"#define DR_TE_GLV_B {m8(glv_b)}")
+    c.append(f"#define DR_TE_GLV_C {m8(glv_c)}")
+    c.append(f"#define DR_TE_GLV_A1 {raw(a1, 4)}")
+    c.append(f"#define DR_TE_GLV_B1 {raw(b1, 4)}")
+    c.append(f"#define DR_TE_GLV_A2 {raw(a2, 4)}")
+    c.append(f"#define DR_TE_GLV_G1 {raw((a1 << 256) // order, 5)}  // floor(2^256 a1 / n)")
+    c.append(f"#define DR_TE_GLV_G2 {raw((b1 << 256) // order, 4)}  // floor(2^256 b1 / n)")
     c.append(f"#define DR_TE_D {m8(te_d)}")
     c.append(f"#define DR_TE_2D {m8(2 * te_d)}")
     c.append(f"#define DR_ELL2_A_OVER_B {m8(mont_a * pow(mont_b, -1, P))}")
