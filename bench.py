@@ -513,7 +513,7 @@ def _shard(total: int, parts: int, index: int) -> tuple[int, int]:
 # table entry at a random address straddles 64-byte DRAM atoms (2 or 3 of them), so the traffic exceeds the algorithmic table bytes;
 # the kernel is bound by the integer pipe, not by these reads.
 NCU_TRAFFIC = {
-    "glv": {"bytes": 22.27e9, "launch": "CommitBodyT<true> grid (4, 1024) x 128 threads (1024 x 6145 coefficients, bench.py --total 1024), 40.7 ms under ncu: 20.03 GB read + 2.24 GB written (register spills); algorithmic table bytes of that launch 9.66e9 (profiles/r02_ncu_full_CommitBody_glv16.csv)"},
+    "glv": {"bytes": 21.81e9, "launch": "CommitBodyT<true> grid (4, 1024) x 128 threads (1024 x 6145 coefficients, bench.py --total 1024), 39.8 ms under ncu: 19.91 GB read + 1.90 GB written (register spills); algorithmic table bytes of that launch 9.66e9 (profiles/r02_ncu_full_CommitBody_glv16.csv)"},
     "plain": {"bytes": 23.0e9, "launch": "CommitBody grid (2, 1024) x 128 threads, 44.6 ms under ncu; algorithmic table bytes of that launch 10.9e9 (profiles/r01_ncu_full_CommitBody_w18.csv)"},
 }
 

@@ -323,6 +323,8 @@ static void ietf_verify_batch(Ctx* ctx, const dr_vrf_suite* suite, uint32_t thin
     h2d(ctx->stream, denc.p, enc.data(), enc.size());
     h2d(ctx->stream, dpr.p, proofs, (size_t)plen * n);
     launch(ctx->stream, Dim3((npts * m + 63) / 64), 64, 0, TeDecodeManyBody(), (const uint8_t*)denc.p, 32u * npts, npts, npts * m, pts.p, dok.p);
+    auto g_table = ctx->fixed_table(su.generator);  // s * G of the large-batch kernel comes from the window table
+    su.g_tab = g_table->tab.p;
     if (m >= VRF_VERIFY_COOP_BELOW.load())
         launch(ctx->stream, Dim3((m + 63) / 64), 64, 0, IetfVerifySerialBody(), su, thin, (const VerifyInput*)items.in.p, (const uint8_t*)items.blob.p, (const uint8_t*)dpr.p,
                (const TEAffine*)pts.p, (const uint8_t*)dok.p, m, dst.p);

@@ -291,8 +291,9 @@ DR_HD TEExt te_endomorphism(const TEAffine& p) {
 }
 
 // sum_j k_j P_j for up to three points in EXTENDED coordinates and scalars of `nlimbs` limbs: Straus with shared doublings, 4-bit windows
+template <int MAXN = 3>
 DR_HD_COLD TEExt te_straus_ext(const TEExt* pts, const uint32_t (*ks)[8], int n, int nlimbs) {
-    TEExt tab[3][16];
+    TEExt tab[MAXN][16];
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         tab[j][0] = TEExt::identity();
@@ -326,7 +327,7 @@ DR_HD_COLD TEExt te_mul_glv(const TEAffine& p, const uint32_t* k) {
     te_glv_split(k, ks[0], n1, ks[1], n2);
     TEExt pts[2] = {TEExt::from_affine(n1 ? te_neg(p) : p), te_endomorphism(p)};
     if (n2) pts[1] = te_neg(pts[1]);
-    return te_straus_ext(pts, ks, 2, 4);
+    return te_straus_ext<2>(pts, ks, 2, 4);
 }
 
 // k P + c Q: P affine in the prime subgroup with a full-length scalar k (split by the endomorphism), Q any point with a scalar of at
@@ -338,7 +339,20 @@ DR_HD_COLD TEExt te_glv_straus2(const TEAffine& p, const uint32_t* k, const TEEx
     for (int i = 0; i < 8; i++) ks[2][i] = i < 4 ? c128[i] : 0u;
     TEExt pts[3] = {TEExt::from_affine(n1 ? te_neg(p) : p), te_endomorphism(p), q};
     if (n2) pts[1] = te_neg(pts[1]);
-    return te_straus_ext(pts, ks, 3, 4);
+    return te_straus_ext<3>(pts, ks, 3, 4);
+}
+// a P + b Q + c R with P, Q affine in the prime subgroup (full-length scalars a, b, split by the endomorphism) and a 128-bit scalar c
+// for R: five tables, ONE pass over 32 windows (the Tiny / Thin verification equation with the delinearisation folded into the scalars)
+DR_HD_COLD TEExt te_glv_straus3(const TEAffine& p, const uint32_t* a, const TEAffine& q, const uint32_t* b, const TEExt& r, const uint32_t* c128) {
+    uint32_t ks[5][8];
+    bool n[4];
+    te_glv_split(a, ks[0], n[0], ks[1], n[1]);
+    te_glv_split(b, ks[2], n[2], ks[3], n[3]);
+    for (int i = 0; i < 8; i++) ks[4][i] = i < 4 ? c128[i] : 0u;
+    TEExt pts[5] = {TEExt::from_affine(n[0] ? te_neg(p) : p), te_endomorphism(p), TEExt::from_affine(n[2] ? te_neg(q) : q), te_endomorphism(q), r};
+    if (n[1]) pts[1] = te_neg(pts[1]);
+    if (n[3]) pts[3] = te_neg(pts[3]);
+    return te_straus_ext<5>(pts, ks, 5, 4);
 }
 
 DR_HD bool te_in_prime_subgroup(const TEAffine& p) {
