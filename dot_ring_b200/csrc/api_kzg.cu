@@ -150,7 +150,7 @@ int dr_kzg_open(dr_ctx* c, dr_srs* s, const uint8_t* coeffs_le32, size_t n, size
     h2d(ctx->stream, xraw.p, points_le32, batch * 32);
     launch(ctx->stream, Dim3((uint32_t)((total + 255) / 256)), 256, 0, FrToMontBody(), (const uint8_t*)raw.p, poly.p, total, (uint32_t*)nullptr);
     launch(ctx->stream, Dim3((uint32_t)((batch + 255) / 256)), 256, 0, FrToMontBody(), (const uint8_t*)xraw.p, xs.p, batch, (uint32_t*)nullptr);
-    launch(ctx->stream, Dim3((uint32_t)batch), 256, 257 * sizeof(Fr), KzgOpenBody(), poly.p, (uint32_t)n, (const Fr*)xs.p, ys.p);
+    launch(ctx->stream, Dim3((uint32_t)batch), 256, synthetic_div_smem(256), KzgOpenBody(), poly.p, (uint32_t)n, (const Fr*)xs.p, ys.p);
     if (n > 1) {
         commit_device(ctx, srs, poly.p, n, (uint32_t)(n - 1), (uint32_t)batch, res.p);
         launch(ctx->stream, Dim3((uint32_t)((batch + 63) / 64)), 64, 0, G1EncodeBody(), (const G1Affine*)res.p, (uint32_t)batch, enc.p, (uint8_t*)nullptr);

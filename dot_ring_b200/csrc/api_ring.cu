@@ -436,7 +436,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         launch(ctx->stream, Dim3(pb), tb, 0, Transcript3Body(), sc.st.p, m);
         pt.mark(ctx, 4);
         launch(ctx->stream, Dim3((qlen + 127) / 128, m), 128, 0, AggOpenBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.wit_coef.p, (const Fr*)sc.quot.p, qlen, sc.aggopen.p);
-        launch(ctx->stream, Dim3(2, m), 256, 257 * sizeof(Fr), OpenQuotientsBody(), rg, (const ProofState*)sc.st.p, sc.aggopen.p, qlen, sc.lin.p);
+        launch(ctx->stream, Dim3(2, m), 256, synthetic_div_smem(256), OpenQuotientsBody(), rg, (const ProofState*)sc.st.p, sc.aggopen.p, qlen, sc.lin.p);
         pt.mark(ctx, 2);
         commit_device_pair(ctx, ring->srs, sc.aggopen.p, qlen, 3 * N, sc.lin.p, N, N - 1, m, sc.res.p);
         launch(ctx->stream, Dim3((m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 1u, 0x05u, sc.st.p, m);

@@ -880,14 +880,16 @@ struct QuotientFoldBody {
         DR_THREAD_LOOP(t, ctx) {
             uint32_t j = ctx.bx * ctx.nthreads + t;
             if (j < qstride) {
-                Fr acc = Fr::zero();
+                // e[idx] = sum_{tt=0..3} tail[tt] * c[idx - tt], q[j] = sum_idx e[idx]: sum the taps first, multiply once per tap
+                // (tail[3] = 1): 3 multiplications per coefficient instead of up to 16
+                Fr taps[4] = {Fr::zero(), Fr::zero(), Fr::zero(), Fr::zero()};
                 for (uint32_t idx = N + j; idx < N4 + 4; idx += N) {
-                    // e[idx] = sum_{tt=0..3} tail[tt] * c[idx - tt]
+#pragma unroll
                     for (uint32_t tt = 0; tt < 4; tt++) {
-                        if (idx >= tt && idx - tt < N4) acc = acc + rg.tail[tt] * c[idx - tt];
+                        if (idx >= tt && idx - tt < N4) taps[tt] = taps[tt] + c[idx - tt];
                     }
                 }
-                q[j] = acc;
+                q[j] = rg.tail[0] * taps[0] + rg.tail[1] * taps[1] + rg.tail[2] * taps[2] + taps[3];
             }
         }
     }
@@ -1055,6 +1057,7 @@ struct AggOpenBody {
 
 // ---- N. synthetic division by (X - x) (pcs/utils.py:27-35): in place, poly[i] <- q[i], one block per polynomial.
 // r_i = sum_{k>=i} a_k x^(k-i);  q_i = r_{i+1}, q_{n-1} = 0.
+DR_HD size_t synthetic_div_smem(uint32_t threads) { return ((size_t)5 * threads + 1) * sizeof(Fr); }
 DR_HD void block_synthetic_div(const BlockCtx& ctx, Fr* poly, uint32_t n, const Fr& x, Fr* sm) {
     const uint32_t T = ctx.nthreads;
     const uint32_t L = (n + T - 1) / T;
@@ -1072,38 +1075,52 @@ DR_HD void block_synthetic_div(const BlockCtx& ctx, Fr* poly, uint32_t n, const 
         sm[t] = acc;  // local suffix at the chunk start
     }
     DR_BLOCK_SYNC();
-    // pass 2: full suffix at each chunk start, serial over chunks: R_t = S_t + x^(len_t) * R_{t+1}
+    // pass 2: full suffix at each chunk start, R_t = S_t + x^(len_t) * R_{t+1}: a suffix scan of affine maps.  Every chunk holds
+    // (A_t, B_t) with R_t = A_t + B_t * R_{t+d}; a round composes it with the pair d chunks further on, so log2(T) rounds of two
+    // multiplications replace a serial walk over all chunks by one thread (which was most of this kernel's time).
+    // sm layout: [0, T] S / final carries (pass 4 reads entry T), then two ping-pong pairs of T entries each: 5 T + 1 elements
+    Fr* A0 = sm + T + 1;
+    Fr* B0 = A0 + T;
+    Fr* A1 = B0 + T;
+    Fr* B1 = A1 + T;
+    const uint32_t nchunks = (n + L - 1) / L;
     DR_THREAD_LOOP(t, ctx) {
-        if (t == 0) {
-            Fr xl = Fr::one(), base = x;
-            uint32_t e = L;
+        if (t < nchunks) {
+            const uint32_t len = (t + 1) * L <= n ? L : n - t * L;
+            Fr mult = Fr::one(), base = x;
+            uint32_t e = len;
 #pragma unroll 1
             while (e) {
-                if (e & 1) xl = xl * base;
+                if (e & 1) mult = mult * base;
                 base = base.sqr();
                 e >>= 1;
             }
-            uint32_t nchunks = (n + L - 1) / L;
-            Fr carry = Fr::zero();  // R_{t+1}
-#pragma unroll 1
-            for (int c = (int)nchunks - 1; c >= 0; c--) {
-                Fr s = sm[c];
-                uint32_t len = ((uint32_t)c + 1) * L <= n ? L : n - (uint32_t)c * L;
-                Fr mult = xl;
-                if (len != L) {  // last (short) chunk
-                    mult = Fr::one();
-                    Fr b2 = x;
-                    uint32_t e2 = len;
-#pragma unroll 1
-                    while (e2) {
-                        if (e2 & 1) mult = mult * b2;
-                        b2 = b2.sqr();
-                        e2 >>= 1;
-                    }
+            A0[t] = sm[t];
+            B0[t] = mult;
+        }
+    }
+    DR_BLOCK_SYNC();
+    bool flip = false;
+    for (uint32_t d = 1; d < nchunks; d <<= 1) {
+        Fr *Ai = flip ? A1 : A0, *Bi = flip ? B1 : B0, *Ao = flip ? A0 : A1, *Bo = flip ? B0 : B1;
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < nchunks) {
+                if (t + d < nchunks) {
+                    Ao[t] = Ai[t] + Bi[t] * Ai[t + d];
+                    Bo[t] = Bi[t] * Bi[t + d];
+                } else {  // nothing beyond: R_{t+d} = 0
+                    Ao[t] = Ai[t];
+                    Bo[t] = Bi[t];
                 }
-                sm[c] = carry;  // what chunk c needs: R_{c+1}
-                carry = s + mult * carry;
             }
+        }
+        DR_BLOCK_SYNC();
+        flip = !flip;
+    }
+    {
+        const Fr* R = flip ? A1 : A0;  // R[t] = full suffix at the start of chunk t
+        DR_THREAD_LOOP(t, ctx) {
+            if (t < nchunks) sm[t] = t + 1 < nchunks ? R[t + 1] : Fr::zero();  // what chunk t needs: R_{t+1}
         }
     }
     DR_BLOCK_SYNC();
