@@ -592,6 +592,8 @@ def run_reference(args) -> None:
     value = workers * args.steps / wall
     line = {
         "impl": "reference",
+        "impl_note": "PORT: the CPU oracle's restatement of the reference's algorithm (Python + a plain-C Pippenger), one process per host core; the reference's own package "
+                     "cannot be built offline (its setup.py clones blst).  Its published native-blst figure is ~2x this port per core (docs/BENCHMARK.md:72: 1.9 proofs/s on an M1 Max core).",
         "metric": "ring_vrf_proofs_per_s",
         "value": value,
         "unit": "proofs/s",
