@@ -205,7 +205,13 @@ static uint32_t commit_slices(Ctx* ctx, uint32_t n, uint32_t batch) {
 }
 
 // the dense commit kernel alone: partials[b * slices + s] = XYZZ sum of slice s of polynomial b
+// partial sums a CTA of the dense commit kernel leaves for the finish kernel (see CommitBodyT)
+// (only for moderately sliced launches: with hundreds of slices per polynomial -- a single proof -- the finish kernel's lanes would
+// fold hundreds of partial sums each)
+static uint32_t commit_keep(uint32_t slices) { return slices > 1 && slices <= 16 ? 32u : 1u; }
+
 static void commit_launch(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_t n, uint32_t batch, uint32_t slices, G1* partials) {
+    const uint32_t keep = commit_keep(slices);
     const uint32_t threads = COMMIT_THREADS;
     PhaseTimer& pt = ctx->phases;
     const int enclosing = pt.current;
@@ -214,9 +220,9 @@ static void commit_launch(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, 
         pt.kernel_launches++;
     }
     if (srs->geom.glv)
-        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials);
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitGlvBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials, keep);
     else
-        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials);
+        launch_lb<COMMIT_THREADS, DR_COMMIT_MINB>(ctx->stream, Dim3(slices, batch), threads, threads * sizeof(G1), CommitBody(), (const G1Affine*)srs->table.p, srs->geom, scalars, stride, n, partials, keep);
     if (pt.active) pt.mark(ctx, enclosing);
 }
 
@@ -247,10 +253,10 @@ void commit_device(Ctx* ctx, Srs* srs, const Fr* scalars, size_t stride, uint32_
         launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
         return;
     }
-    const uint32_t slices = commit_slices(ctx, n, batch);
-    ctx->partials.ensure((size_t)batch * slices);
+    const uint32_t slices = commit_slices(ctx, n, batch), keep = commit_keep(slices);
+    ctx->partials.ensure((size_t)batch * slices * keep);
     commit_launch(ctx, srs, scalars, stride, n, batch, slices, ctx->partials.p);
-    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices, batch, out_affine);
+    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, slices * keep, batch, out_affine);
 }
 
 // Two commitments of the same batch whose results nothing needs in between (the prover's two opening proofs): both commit kernels,
@@ -266,10 +272,11 @@ void commit_device_pair(Ctx* ctx, Srs* srs, const Fr* scalars_a, size_t stride_a
         return;
     }
     if (n_a > srs->n || n_b > srs->n) throw Error(DR_EINVAL, "polynomial degree exceeds SRS size");
-    ctx->partials.ensure((size_t)2 * batch * sa);
+    const uint32_t keep = commit_keep(sa);
+    ctx->partials.ensure((size_t)2 * batch * sa * keep);
     commit_launch(ctx, srs, scalars_a, stride_a, n_a, batch, sa, ctx->partials.p);
-    commit_launch(ctx, srs, scalars_b, stride_b, n_b, batch, sa, ctx->partials.p + (size_t)batch * sa);
-    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, sa, 2 * batch, out_affine);
+    commit_launch(ctx, srs, scalars_b, stride_b, n_b, batch, sa, ctx->partials.p + (size_t)batch * sa * keep);
+    launch_commit_finish(ctx->stream, (const G1*)ctx->partials.p, sa * keep, 2 * batch, out_affine);
 }
 
 }  // namespace dr

@@ -383,7 +383,11 @@ DR_HD int msm_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) 
 // SRS points 0..n-1.  Each block accumulates its slice of points and tree-reduces to one XYZZ partial.
 template <bool GLV>
 struct CommitBodyT {
-    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, const Fr* scalars, size_t scalar_stride, uint32_t n, G1* partials) const {
+    // keep: how many partial sums a CTA leaves (a power of two <= nthreads).  1 = the CTA folds itself completely (large batches:
+    // one slice per polynomial, the tree is ~1 % of a CTA's life); 32 = the tree stops after the cross-warp levels and the finish
+    // kernel folds the rest (sliced launches of small batches: a full 7-level tree of dependent additions, with three of four
+    // warps idle, was ~6 % of a CTA's life there).  partials[(by * slices + bx) * keep + t].
+    DR_HD void operator()(const BlockCtx& ctx, const G1Affine* table, TableGeom g, const Fr* scalars, size_t scalar_stride, uint32_t n, G1* partials, uint32_t keep) const {
         G1* sm = (G1*)ctx.smem;
         const uint32_t slices = ctx.gx;
         const uint32_t per = (n + slices - 1) / slices;
@@ -427,7 +431,7 @@ struct CommitBodyT {
             }
         }
         DR_BLOCK_SYNC();
-        for (uint32_t stride = ctx.nthreads >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t stride = ctx.nthreads >> 1; stride >= keep; stride >>= 1) {
             DR_STRIDE_LOOP(t, stride, ctx) {
                 G1 a = sm[t];
                 g1_add(a, sm[t + stride]);
@@ -436,7 +440,7 @@ struct CommitBodyT {
             DR_BLOCK_SYNC();
         }
         DR_THREAD_LOOP(t, ctx) {
-            if (t == 0) partials[(size_t)ctx.by * slices + ctx.bx] = sm[0];
+            if (t < keep) partials[((size_t)ctx.by * slices + ctx.bx) * keep + t] = sm[t];
         }
     }
 };
