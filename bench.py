@@ -357,11 +357,13 @@ def run_ours(args) -> None:
     for e in engines:
         e.ctx.sync()
     dev_ms, phases, kernel_ms, kernel_launches = 0.0, [0.0] * 6, 0.0, 0
+    step_ms = []
     t_start = time.perf_counter()
     last = None
     for a, d, zk in prepared:
         last = prove(a, d, zk)
         dev_ms += ring.native.last_call_ms  # one CUDA event pair around the whole call (slowest device of a pool)
+        step_ms.append(round(ring.native.last_call_ms, 3))
         ph = ring.native.prove_phase_ms()
         phases = [x + y for x, y in zip(phases, ph)]
         km, kl = ring.native.commit_kernel_ms()
@@ -480,6 +482,7 @@ def run_ours(args) -> None:
             "algorithmic_table_bytes_per_launch": table_bytes_per_launch,
             "hbm_gbs_for_table_reads": dense_madds * 96 * mine * args.steps / pool_devices / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None,
         },
+        "step_ms_rank0": step_ms,
         "phase_ms_per_step": {k: v / args.steps for k, v in zip(["pedersen+witness", "interpolate", "commit(msm)", "lde+constraints+quotient", "evals+openings", "transcripts+assembly"], phases)},
         "setup": {"srs_table_s": table_s, "ring_s": ring_s, "device": info["name"], "sm_count": info["sm_count"]},
     }
