@@ -331,6 +331,9 @@ int dr_ctx_create(int device, dr_ctx** out) {
     DR_CUDA(cudaSetDevice(device));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DR_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    DR_CUDA(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
+    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+    DR_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     DR_CUDA(cudaEventCreate(&ctx->ev_fork));
     DR_CUDA(cudaEventCreate(&ctx->ev_join));
     // Fix the per-thread stack once: kernels here need between 0 and ~16 KB of local memory, and letting the runtime grow the
@@ -345,6 +348,7 @@ int dr_ctx_create(int device, dr_ctx** out) {
 #else
     ctx->stream = 0;
     ctx->side = 0;
+    ctx->side2 = 0;
 #endif
     *out = (dr_ctx*)ctx.release();
     DR_API_END
@@ -357,6 +361,7 @@ void dr_ctx_destroy(dr_ctx* c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
+    cudaStreamSynchronize(ctx->side2);
     current_stream() = ctx->stream;
 #endif
     ctx->plans.clear();
@@ -366,6 +371,9 @@ void dr_ctx_destroy(dr_ctx* c) {
     cudaEventDestroy(ctx->ev_stop);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_fork2);
+    cudaEventDestroy(ctx->ev_join2);
+    cudaStreamDestroy(ctx->side2);
     cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     current_stream() = nullptr;

@@ -69,8 +69,10 @@ struct Ctx {
     Stream stream{};
     // work that nothing on the main stream waits for until the end of a pass (second half of the Pedersen prover) runs here
     Stream side{};
+    // a second one for work that overlaps a shorter stretch of the main stream (witness interpolation next to the witness commitments)
+    Stream side2{};
 #if !defined(DR_HOST_EMULATION)
-    cudaEvent_t ev_fork{}, ev_join{};
+    cudaEvent_t ev_fork{}, ev_join{}, ev_fork2{}, ev_join2{};
     cudaEvent_t ev_start{}, ev_stop{};
 #else
     std::chrono::steady_clock::time_point t_start;
@@ -133,6 +135,18 @@ struct Ctx {
 #if !defined(DR_HOST_EMULATION)
         DR_CUDA(cudaEventRecord(ev_join, side));
         DR_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+#endif
+    }
+    void fork_side2() {
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaEventRecord(ev_fork2, stream));
+        DR_CUDA(cudaStreamWaitEvent(side2, ev_fork2, 0));
+#endif
+    }
+    void join_side2() {
+#if !defined(DR_HOST_EMULATION)
+        DR_CUDA(cudaEventRecord(ev_join2, side2));
+        DR_CUDA(cudaStreamWaitEvent(stream, ev_join2, 0));
 #endif
     }
     // ms between the last fork and the completion of the side stream's work (after a stream sync); diagnostics only

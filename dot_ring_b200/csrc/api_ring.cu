@@ -387,8 +387,12 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
             launch(ctx->stream, Dim3((m + 3) / 4), wt, witness_coop_smem(wt), WitnessBody(), rg, sc.st.p, m, (const Shake128*)ring->prefix.p);
         }
         pt.mark(ctx, 1);
+        // The coefficient form of the witness columns is first needed by the low-degree extension, the commitments by the transcript:
+        // on the fused path the interpolation runs on a second side stream next to the (sparse) commitments.
+        const bool overlap_intt = !large && !ctx->dense_witness_commit;
         if (!large) {
-            launch(ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
+            if (overlap_intt) ctx->fork_side2();
+            launch(overlap_intt ? ctx->side2 : ctx->stream, Dim3(4, m), nthr, ntt_smem, WitnessInttBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
         } else {
             launch(ctx->stream, Dim3((N + 127) / 128, 4, m), 128, 0, WitnessEvalBody(), rg, (const ProofState*)sc.st.p, sc.wit_coef.p);
             ntt_device(ctx, *big_plan, sc.wit_coef.p, sc.wit_coef.p, 4 * (size_t)m, true, sc.ntt_tmp);
@@ -407,6 +411,7 @@ int dr_ring_prove_batch(dr_ctx* c, dr_ring* r, size_t n, const uint8_t* blob, co
         launch(ctx->stream, Dim3((4 * m + 127) / 128), 128, 0, StoreCommitBody(), (const G1Affine*)sc.res.p, 4u, 0x01030200u, sc.st.p, m);
         pt.mark(ctx, 5);
         launch(ctx->stream, Dim3(pb), tb, 0, Transcript1Body(), sc.st.p, m);
+        if (overlap_intt) ctx->join_side2();
         pt.mark(ctx, 3);
         if (!large) {
             launch(ctx->stream, Dim3(16, m), nthr, ntt_smem, WitnessLdeBody(), rg, (const ProofState*)sc.st.p, (const Fr*)sc.wit_coef.p, sc.lde.p);
